@@ -1,0 +1,142 @@
+/*
+ * msbt.h -- C-ABI of libmsbt.so, the B200 (sm_100a) replacement for the arithmetic that
+ * MetaSBT obtains by spawning the external `howdesbt` binary.
+ *
+ * The reference has no FFI: its "operator interface" for this path is argv + stdout text of
+ *     howdesbt makebf | bfoperate | bfdistance | dumpbf | query
+ * launched with subprocess.check_call from /root/reference/metasbt/core.py.  Each entry
+ * point below names the call site it replaces.  Signatures use plain pointers and sizes
+ * only (no torch, no C++ types); device pointers are raw CUdeviceptr-compatible addresses
+ * owned by the caller; `stream` is a cudaStream_t passed as void*.  Every function returns
+ * 0 on success or a negative code (MSBT_E*), never throws, and is asynchronous on `stream`
+ * unless stated otherwise.  msbt_last_error(ctx) gives the message for the last failure.
+ *
+ * Filter layout (device and `.bf` payload alike): ceil(num_bits/64) little-endian u64 words,
+ * bit i = (word[i >> 6] >> (i & 63)) & 1 (sdsl::bit_vector).
+ */
+#ifndef MSBT_H
+#define MSBT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSBT_ABI_VERSION 1
+
+#define MSBT_OK 0
+#define MSBT_EINVAL (-22)  /* bad argument */
+#define MSBT_ENOMEM (-12)  /* device or host allocation failed */
+#define MSBT_ENOSPC (-28)  /* caller-provided buffer too small */
+#define MSBT_ECUDA (-5)    /* CUDA runtime error; see msbt_last_error */
+
+typedef struct msbt_ctx msbt_ctx;
+
+/* One context per GPU per host thread.  Owns library scratch (tile tables, counters). */
+int msbt_ctx_create(int device, msbt_ctx **out);
+void msbt_ctx_destroy(msbt_ctx *ctx);
+const char *msbt_last_error(const msbt_ctx *ctx);
+int msbt_abi_version(void);
+int msbt_sync(msbt_ctx *ctx, void *stream);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t msbt_launch_count(const msbt_ctx *ctx);
+
+/* ---------------------------------------------------------------- host-side ingest (no GPU)
+ * FASTA text -> 2-bit packed valid bases + run table.  Replaces howdesbt's own FASTA reader
+ * (the file argument of `makebf`, core.py:3928, and of `query`, core.py:2046).
+ * Records start at '>' lines, sequence lines are concatenated, whitespace is skipped, case is
+ * folded, every other non-ACGT byte and every record boundary ends a run; runs shorter than
+ * `min_run` (pass k) are dropped because they hold no k-mer.
+ *   packed   : u64 words, 32 bases each, first base in the top two bits, zero padded, followed
+ *              by MSBT_PACK_PAD_WORDS zero words; capacity in words
+ *   run_ends : cumulative end offset (in bases of the packed stream) of each kept run
+ * Call with packed == NULL to get the sizes only.  Synchronous, host only. */
+#define MSBT_PACK_PAD_WORDS 3
+int msbt_fasta_pack(const char *text, size_t n, uint32_t min_run,
+                    uint64_t *packed, size_t packed_cap_words,
+                    uint32_t *run_ends, size_t run_cap,
+                    uint64_t *n_bases_out, uint64_t *n_runs_out);
+
+/* One genome of a construction / query batch. */
+typedef struct {
+    uint64_t packed_word_off; /* first word of this genome inside d_packed */
+    uint64_t n_bases;         /* valid bases (< 2^32) */
+    uint64_t run_off;         /* first entry of this genome inside d_run_ends */
+    uint32_t n_runs;
+    uint32_t filter_index;    /* output filter = d_filters + filter_index * filter_stride_words */
+} msbt_genome_desc;
+
+/* ---------------------------------------------------------------- K1: howdesbt makebf
+ * Replaces core.py:3920-3931 (Entry.sketch).  For every genome of the batch: every length-k
+ * window inside a run -> canonical k-mer -> MurmurHash3_x64_128(seed) first half ->
+ * pos = h % modulus -> set bit pos of its filter if pos < num_bits (--hashes=1).
+ * min_abund <= 1: every k-mer; min_abund >= 2: only k-mers whose exact canonical multiplicity
+ * inside the genome is >= min_abund (k <= 32 only in this version).
+ * The output filters are fully written (zero-filled first) -- callers need not clear them.
+ * `h_descs` is host memory and is consumed before the call returns.
+ * variant: 0 = auto, 1 = direct (memset + red.or into HBM), 2 = L2-staged regions. */
+int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *d_run_ends,
+                          const msbt_genome_desc *h_descs, uint32_t n_genomes,
+                          uint32_t k, uint64_t seed, uint64_t modulus, uint64_t num_bits,
+                          uint32_t min_abund, uint64_t *d_filters, uint64_t filter_stride_words,
+                          int variant, void *stream);
+
+/* ---------------------------------------------------------------- K2: howdesbt bfoperate --or
+ * Replaces core.py:3851-3857 (Entry.index).  d_dst = OR of the n source filters.
+ * `h_srcs` is a host array of n device pointers, consumed before the call returns. */
+int msbt_bf_or_reduce(msbt_ctx *ctx, const uint64_t *const *h_srcs, uint32_t n, uint64_t words,
+                      uint64_t *d_dst, void *stream);
+
+/* ---------------------------------------------------------------- K3': howdesbt dumpbf --show:density
+ * Replaces core.py:3588-3593 (Entry.get_density).  d_out[i] = popcount(filter i). */
+int msbt_bf_popcount(msbt_ctx *ctx, const uint64_t *const *h_filters, uint32_t n, uint64_t words,
+                     uint64_t *d_out, void *stream);
+
+/* ---------------------------------------------------------------- K3: howdesbt bfdistance
+ * Replaces BOTH spawns of core.py:1747-1753 (--show:intersect) and :1768-1774 (--show:union)
+ * (Database.dist) with one pass: d_intersect[j] = popc(focus & target_j),
+ * d_union[j] = popc(focus | target_j). */
+int msbt_bf_and_popcount_1vN(msbt_ctx *ctx, const uint64_t *d_focus,
+                             const uint64_t *const *h_targets, uint32_t n, uint64_t words,
+                             uint64_t *d_intersect, uint64_t *d_union, void *stream);
+
+/* All pairs among n filters (Entry.get_boundaries, core.py:4036-4081, which calls dist once
+ * per source).  d_intersect is a dense n*n row-major u64 matrix; the diagonal holds
+ * popcount(filter i), so union(i,j) = I[i][i] + I[j][j] - I[i][j]. */
+int msbt_bf_and_popcount_allpairs(msbt_ctx *ctx, const uint64_t *const *h_filters, uint32_t n,
+                                  uint64_t words, uint64_t *d_intersect, void *stream);
+
+/* ---------------------------------------------------------------- K4: howdesbt query --distinctkmers
+ * Replaces core.py:2039-2047 (Database.profile).
+ * Step 1: the query's distinct positions are exactly the set bits of its own min=1 filter
+ * (App. A6 corollary), so they are produced by K1 + this ordered extraction:
+ * d_positions (u32, ascending) receives at most `cap` entries, *d_count (u64) the true count. */
+int msbt_bf_extract_positions(msbt_ctx *ctx, const uint64_t *d_filter, uint64_t words,
+                              uint32_t *d_positions, uint64_t cap, uint64_t *d_count, void *stream);
+
+/* Step 2: hits[q][l] = #{p in positions of query q : bit p of leaf filter l is set}.
+ * d_positions holds all queries back to back; h_query_offsets (host, n_queries+1 entries)
+ * delimits them.  d_hits is n_queries * n_leaves u32, row-major. */
+int msbt_query_batch(msbt_ctx *ctx, const uint64_t *const *h_leaves, uint32_t n_leaves,
+                     const uint32_t *d_positions, const uint64_t *h_query_offsets,
+                     uint32_t n_queries, uint32_t *d_hits, void *stream);
+
+/* Bit-sliced leaf matrix for large leaf counts: row p holds bit p of every
+ * leaf, ceil(n_leaves/32) u32 words per row.  Rows [row_begin, row_end) only, so that a rank
+ * that owns a bit range builds and probes just its shard. */
+int msbt_bitslice_build(msbt_ctx *ctx, const uint64_t *const *h_leaves, uint32_t n_leaves,
+                        uint64_t row_begin, uint64_t row_end, uint32_t *d_sliced, void *stream);
+
+/* Same result as msbt_query_batch restricted to positions in [row_begin, row_end); partial
+ * hit matrices of different ranges add up to the full one (NCCL sum across ranks). */
+int msbt_query_batch_sliced(msbt_ctx *ctx, const uint32_t *d_sliced, uint32_t n_leaves,
+                            uint64_t row_begin, uint64_t row_end,
+                            const uint32_t *d_positions, const uint64_t *h_query_offsets,
+                            uint32_t n_queries, uint32_t *d_hits, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSBT_H */

@@ -1,0 +1,1028 @@
+// msbt_kernels.cu -- sm_100a kernels + C-ABI (include/msbt.h) for the MetaSBT hot path.
+//
+// What each kernel replaces (all in /root/reference/metasbt/core.py):
+//   kmer_bloom_*      howdesbt makebf       :3920-3931
+//   bf_or_reduce      howdesbt bfoperate    :3851-3857
+//   bf_popcount       howdesbt dumpbf       :3588-3593
+//   bf_and_popcount_* howdesbt bfdistance   :1747-1753, :1768-1774 (and the loop :4036-4081)
+//   bf_extract / query_* howdesbt query     :2039-2047
+//
+// None of this is a dense contraction: every kernel is HBM/L2-bound integer work, so there
+// are no tensor-core instructions here by design (BASELINE.json north_star).  The rules that
+// matter are coalesced 128-bit access, one scattered memory operation per k-mer at most, and
+// persistent grids sized in multiples of the SM count.
+#include <cuda_runtime.h>
+#include <errno.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/msbt.h"
+#include "msbt_spec.h"
+#include "msbt_kmer.h"
+
+// --------------------------------------------------------------------------- context
+
+struct msbt_ctx {
+    int device;
+    int num_sms;
+    char err[512];
+    uint64_t launches;
+    // library-owned device scratch, grown on demand
+    void *d_scratch;
+    size_t scratch_bytes;
+    // pinned staging for small host tables handed to kernels
+    void *h_stage;
+    size_t stage_bytes;
+    cudaEvent_t stage_free;  // recorded after the last H2D that read h_stage
+    bool stage_busy;
+};
+
+static int fail(msbt_ctx *ctx, int code, const char *fmt, ...) {
+    if (ctx) {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(ctx->err, sizeof(ctx->err), fmt, ap);
+        va_end(ap);
+    }
+    return code;
+}
+
+#define CU_TRY(ctx, call)                                                                  \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return fail(ctx, MSBT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+static int ensure_scratch(msbt_ctx *ctx, size_t bytes) {
+    if (bytes <= ctx->scratch_bytes) return MSBT_OK;
+    if (ctx->d_scratch) {
+        CU_TRY(ctx, cudaDeviceSynchronize());
+        CU_TRY(ctx, cudaFree(ctx->d_scratch));
+        ctx->d_scratch = nullptr;
+        ctx->scratch_bytes = 0;
+    }
+    size_t want = bytes + bytes / 4 + 4096;
+    if (cudaMalloc(&ctx->d_scratch, want) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(ctx, MSBT_ENOMEM, "cudaMalloc(%zu) for scratch failed", want);
+    }
+    ctx->scratch_bytes = want;
+    return MSBT_OK;
+}
+
+// Copy a small host table to device scratch at `d_dst` through pinned staging, asynchronously
+// on `stream`.  The staging buffer is recycled only after the previous copy has finished.
+static int stage_to_device(msbt_ctx *ctx, void *d_dst, const void *h_src, size_t bytes, size_t stage_off,
+                           cudaStream_t stream) {
+    memcpy((char *)ctx->h_stage + stage_off, h_src, bytes);
+    CU_TRY(ctx, cudaMemcpyAsync(d_dst, (char *)ctx->h_stage + stage_off, bytes, cudaMemcpyHostToDevice, stream));
+    return MSBT_OK;
+}
+
+static int stage_begin(msbt_ctx *ctx, size_t bytes) {
+    if (ctx->stage_busy) {
+        CU_TRY(ctx, cudaEventSynchronize(ctx->stage_free));
+        ctx->stage_busy = false;
+    }
+    if (bytes > ctx->stage_bytes) {
+        if (ctx->h_stage) CU_TRY(ctx, cudaFreeHost(ctx->h_stage));
+        ctx->h_stage = nullptr;
+        ctx->stage_bytes = 0;
+        size_t want = bytes + bytes / 2 + 4096;
+        if (cudaMallocHost(&ctx->h_stage, want) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, MSBT_ENOMEM, "cudaMallocHost(%zu) failed", want);
+        }
+        ctx->stage_bytes = want;
+    }
+    return MSBT_OK;
+}
+
+static int stage_end(msbt_ctx *ctx, cudaStream_t stream) {
+    CU_TRY(ctx, cudaEventRecord(ctx->stage_free, stream));
+    ctx->stage_busy = true;
+    return MSBT_OK;
+}
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+extern "C" int msbt_abi_version(void) { return MSBT_ABI_VERSION; }
+
+extern "C" int msbt_ctx_create(int device, msbt_ctx **out) {
+    if (!out) return MSBT_EINVAL;
+    *out = nullptr;
+    msbt_ctx *ctx = new (std::nothrow) msbt_ctx();
+    if (!ctx) return MSBT_ENOMEM;
+    memset(ctx, 0, sizeof(*ctx));
+    ctx->device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->stage_free, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        // No CPU fallback exists: without a usable GPU the library refuses to construct.
+        fprintf(stderr, "msbt_ctx_create(device=%d): %s\n", device, cudaGetErrorString(e));
+        delete ctx;
+        return MSBT_ECUDA;
+    }
+    *out = ctx;
+    return MSBT_OK;
+}
+
+extern "C" void msbt_ctx_destroy(msbt_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+    if (ctx->stage_free) cudaEventDestroy(ctx->stage_free);
+    delete ctx;
+}
+
+extern "C" const char *msbt_last_error(const msbt_ctx *ctx) { return ctx ? ctx->err : "null context"; }
+extern "C" uint64_t msbt_launch_count(const msbt_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int msbt_sync(msbt_ctx *ctx, void *stream) {
+    if (!ctx) return MSBT_EINVAL;
+    CU_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+    return MSBT_OK;
+}
+
+#define LAUNCH_CHECK(ctx)                 \
+    do {                                  \
+        (ctx)->launches++;                \
+        CU_TRY(ctx, cudaGetLastError());  \
+    } while (0)
+
+// --------------------------------------------------------------------------- host FASTA ingest
+
+extern "C" int msbt_fasta_pack(const char *text, size_t n, uint32_t min_run, uint64_t *packed,
+                               size_t packed_cap_words, uint32_t *run_ends, size_t run_cap,
+                               uint64_t *n_bases_out, uint64_t *n_runs_out) {
+    if (!text && n) return MSBT_EINVAL;
+    if (min_run > 64) return MSBT_EINVAL;
+    static const struct Lut {
+        uint8_t v[256];
+        Lut() {
+            for (int i = 0; i < 256; i++) v[i] = MSBT_BASE_INVALID;
+            v['A'] = v['a'] = 0; v['C'] = v['c'] = 1; v['G'] = v['g'] = 2; v['T'] = v['t'] = 3;
+            v[' '] = v['\t'] = v['\r'] = 5;  // skipped, does not break a run
+            v['\n'] = 6;
+        }
+    } lut;
+    const bool write = packed != nullptr;
+    uint64_t nb = 0;       // bases committed to the packed stream
+    uint64_t nruns = 0;
+    uint64_t cur = 0;      // word being filled
+    uint32_t run_len = 0;  // length of the current run, saturating at min_run once committed
+    uint8_t pending[64];   // a run is committed only once it has reached min_run bases
+    int rc = MSBT_OK;
+    auto commit = [&](uint8_t v) -> bool {
+        if (write) {
+            const uint64_t w = nb >> 5;
+            if (w + MSBT_PACK_PAD_WORDS >= packed_cap_words) return false;
+            cur |= (uint64_t)v << (62 - 2 * (nb & 31));
+            if ((nb & 31) == 31) { packed[w] = cur; cur = 0; }
+        }
+        nb++;
+        return true;
+    };
+    auto end_run = [&]() {
+        if (run_len >= min_run && run_len > 0) {
+            if (write) {
+                if (nruns < run_cap) run_ends[nruns] = (uint32_t)nb; else rc = MSBT_ENOSPC;
+            }
+            nruns++;
+        }
+        run_len = 0;
+    };
+    bool line_start = true;
+    for (size_t i = 0; i < n;) {
+        const unsigned char c = (unsigned char)text[i];
+        if (line_start && c == '>') {
+            const void *nl = memchr(text + i, '\n', n - i);
+            i = nl ? (size_t)((const char *)nl - text) : n;
+            end_run();
+            continue;
+        }
+        i++;
+        const uint8_t v = lut.v[c];
+        if (v < 4) {
+            line_start = false;
+            if (run_len + 1 < min_run) {
+                pending[run_len++] = v;
+            } else {
+                if (run_len + 1 == min_run) {  // the run just became long enough: flush what was held back
+                    for (uint32_t t = 0; t < run_len; t++)
+                        if (!commit(pending[t])) return MSBT_ENOSPC;
+                }
+                if (!commit(v)) return MSBT_ENOSPC;
+                if (run_len < 0xFFFFFFFFu) run_len++;
+                if (nb >> 32) return MSBT_EINVAL;  // run table is u32
+            }
+        } else if (v == 6) {
+            line_start = true;
+        } else if (v == 5) {
+            line_start = false;
+        } else {
+            line_start = false;
+            end_run();
+        }
+    }
+    end_run();
+    if (write) {
+        const uint64_t w = (nb + 31) >> 5;
+        if (w + MSBT_PACK_PAD_WORDS > packed_cap_words) return MSBT_ENOSPC;
+        if (nb & 31) packed[nb >> 5] = cur;
+        for (uint64_t p = 0; p < MSBT_PACK_PAD_WORDS; p++) packed[w + p] = 0;
+    }
+    if (n_bases_out) *n_bases_out = nb;
+    if (n_runs_out) *n_runs_out = nruns;
+    return rc;
+}
+
+// --------------------------------------------------------------------------- K1: k-mer -> Bloom
+
+// One tile = one CTA iteration = TILE_THREADS threads x 32 k-mer starts (one packed word each).
+constexpr int TILE_THREADS = 256;
+constexpr uint32_t TILE_BASES = TILE_THREADS * 32;
+
+struct DevGenome {
+    uint64_t packed_word_off;
+    uint64_t run_off;
+    uint64_t filter_word_off;  // in u64 words
+    uint32_t n_bases;
+    uint32_t n_runs;
+    uint32_t tile_begin;  // first global tile index of this genome
+    uint32_t pad;
+};
+
+struct KmerSpec {
+    msbt_pos_spec pos;
+    uint32_t k;
+};
+
+__device__ __forceinline__ uint32_t find_genome(const DevGenome *__restrict__ g, uint32_t n, uint32_t tile) {
+    uint32_t lo = 0, hi = n;  // last genome with tile_begin <= tile
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (g[mid].tile_begin <= tile) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// Variant 1 ("direct"): filters are zero-filled by a preceding memset; every k-mer issues one
+// RED.OR.b32 straight to its filter word.  One scattered memory operation per k-mer.
+template <int KW>
+__global__ void __launch_bounds__(TILE_THREADS, 4)
+kmer_bloom_direct_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ run_ends,
+                         const DevGenome *__restrict__ genomes, uint32_t n_genomes, uint32_t n_tiles,
+                         KmerSpec spec, uint32_t *__restrict__ filters) {
+    const uint32_t k = spec.k;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint32_t gi = find_genome(genomes, n_genomes, tile);
+        const DevGenome g = genomes[gi];
+        const uint32_t w = (tile - g.tile_begin) * TILE_THREADS + threadIdx.x;
+        const uint32_t s0 = w * 32;
+        if (s0 >= g.n_bases) continue;
+        const uint32_t vm = valid_mask(run_ends + g.run_off, g.n_runs, s0, k);
+        if (vm == 0) continue;
+        KmerWalker<KW> kw;
+        kw.init(packed + g.packed_word_off + w, k);
+        uint32_t *__restrict__ out = filters + 2 * g.filter_word_off;
+#pragma unroll 4
+        for (uint32_t j = 0; j < 32; j++) {
+            if ((vm >> j) & 1) {
+                uint64_t lo, hi;
+                kw.canonical(lo, hi);
+                uint64_t pos = msbt_position(msbt_kmer_hash(lo, hi, k, spec.pos.seed), spec.pos);
+                if (pos < spec.pos.num_bits) atomicOr(out + (pos >> 5), 1u << (pos & 31));
+            }
+            kw.roll(j);
+        }
+    }
+}
+
+// ---- exact multiplicity path (min_abund >= 2, k <= 32): open-addressing count table.
+constexpr uint64_t HT_EMPTY = ~0ULL;  // never a canonical k-mer for k <= 32 (all-T's rc is all-A = 0)
+
+__device__ __forceinline__ uint64_t ht_slot(uint64_t key, uint64_t mask) { return msbt_fmix64(key ^ 0x9E3779B97F4A7C15ULL) & mask; }
+
+__global__ void __launch_bounds__(TILE_THREADS, 4)
+kmer_count_insert_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ run_ends, DevGenome g,
+                         uint32_t k, unsigned long long *__restrict__ keys, uint32_t *__restrict__ counts,
+                         uint64_t slot_mask) {
+    const uint32_t n_words = (g.n_bases + 31) / 32;
+    for (uint32_t w = blockIdx.x * TILE_THREADS + threadIdx.x; w < n_words; w += gridDim.x * TILE_THREADS) {
+        const uint32_t s0 = w * 32;
+        const uint32_t vm = valid_mask(run_ends + g.run_off, g.n_runs, s0, k);
+        if (vm == 0) continue;
+        KmerWalker<1> kw;
+        kw.init(packed + g.packed_word_off + w, k);
+        for (uint32_t j = 0; j < 32; j++) {
+            if ((vm >> j) & 1) {
+                uint64_t lo, hi;
+                kw.canonical(lo, hi);
+                uint64_t slot = ht_slot(lo, slot_mask);
+                while (true) {
+                    unsigned long long old = atomicCAS(keys + slot, (unsigned long long)HT_EMPTY, (unsigned long long)lo);
+                    if (old == HT_EMPTY || old == lo) {
+                        atomicAdd(counts + slot, 1u);
+                        break;
+                    }
+                    slot = (slot + 1) & slot_mask;
+                }
+            }
+            kw.roll(j);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+kmer_count_emit_kernel(const unsigned long long *__restrict__ keys, const uint32_t *__restrict__ counts,
+                       uint64_t n_slots, uint32_t min_abund, KmerSpec spec, uint32_t *__restrict__ out) {
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
+        unsigned long long key = keys[s];
+        if (key != HT_EMPTY && counts[s] >= min_abund) {
+            uint64_t pos = msbt_position(msbt_kmer_hash(key, 0, spec.k, spec.pos.seed), spec.pos);
+            if (pos < spec.pos.num_bits) atomicOr(out + (pos >> 5), 1u << (pos & 31));
+        }
+    }
+}
+
+extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *d_run_ends,
+                                     const msbt_genome_desc *h_descs, uint32_t n_genomes, uint32_t k,
+                                     uint64_t seed, uint64_t modulus, uint64_t num_bits, uint32_t min_abund,
+                                     uint64_t *d_filters, uint64_t filter_stride_words, int variant,
+                                     void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (k < 1 || k > 64) return fail(ctx, MSBT_EINVAL, "k=%u outside 1..64", k);
+    if (modulus == 0 || num_bits == 0) return fail(ctx, MSBT_EINVAL, "modulus and num_bits must be > 0");
+    const uint64_t words = (num_bits + 63) / 64;
+    if (filter_stride_words < words) return fail(ctx, MSBT_EINVAL, "filter stride %llu < %llu words", (unsigned long long)filter_stride_words, (unsigned long long)words);
+    if (n_genomes == 0) return MSBT_OK;
+    if (!d_packed || !d_run_ends || !h_descs || !d_filters) return fail(ctx, MSBT_EINVAL, "null pointer argument");
+    if (min_abund >= 2 && k > 32) return fail(ctx, MSBT_EINVAL, "min_abund >= 2 supports k <= 32 only (k=%u)", k);
+    if (variant < 0 || variant > 2) return fail(ctx, MSBT_EINVAL, "unknown variant %d", variant);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+
+    KmerSpec spec;
+    spec.pos = msbt_make_pos_spec(modulus, num_bits, seed);
+    spec.k = k;
+
+    // device genome table with tile prefix
+    std::vector<DevGenome> dg(n_genomes);
+    uint64_t tiles = 0;
+    uint64_t max_bases = 0;
+    for (uint32_t i = 0; i < n_genomes; i++) {
+        const msbt_genome_desc &d = h_descs[i];
+        if (d.n_bases >> 32) return fail(ctx, MSBT_EINVAL, "genome %u has >= 2^32 bases", i);
+        dg[i].packed_word_off = d.packed_word_off;
+        dg[i].run_off = d.run_off;
+        dg[i].filter_word_off = (uint64_t)d.filter_index * filter_stride_words;
+        dg[i].n_bases = (uint32_t)d.n_bases;
+        dg[i].n_runs = d.n_runs;
+        dg[i].tile_begin = (uint32_t)tiles;
+        dg[i].pad = 0;
+        tiles += (d.n_bases + TILE_BASES - 1) / TILE_BASES;
+        max_bases = std::max<uint64_t>(max_bases, d.n_bases);
+        if (tiles >> 31) return fail(ctx, MSBT_EINVAL, "batch too large (%llu tiles)", (unsigned long long)tiles);
+    }
+
+    // zero-fill every output filter (the reference always writes a complete new file)
+    for (uint32_t i = 0; i < n_genomes; i++)
+        CU_TRY(ctx, cudaMemsetAsync(d_filters + dg[i].filter_word_off, 0, words * 8, stream));
+
+    if (min_abund >= 2) {
+        uint64_t n_slots = 1024;
+        while (n_slots < 2 * max_bases) n_slots <<= 1;
+        size_t keys_b = n_slots * 8, cnt_b = n_slots * 4;
+        int rc = ensure_scratch(ctx, keys_b + cnt_b);
+        if (rc) return rc;
+        unsigned long long *keys = (unsigned long long *)ctx->d_scratch;
+        uint32_t *counts = (uint32_t *)((char *)ctx->d_scratch + keys_b);
+        for (uint32_t i = 0; i < n_genomes; i++) {
+            if (dg[i].n_bases < k) continue;
+            uint64_t slots = 1024;
+            while (slots < 2ull * dg[i].n_bases) slots <<= 1;
+            CU_TRY(ctx, cudaMemsetAsync(keys, 0xFF, slots * 8, stream));
+            CU_TRY(ctx, cudaMemsetAsync(counts, 0, slots * 4, stream));
+            uint32_t n_words = (dg[i].n_bases + 31) / 32;
+            int grid = (int)std::min<uint64_t>((n_words + TILE_THREADS - 1) / TILE_THREADS, (uint64_t)ctx->num_sms * 8);
+            kmer_count_insert_kernel<<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, dg[i], k, keys, counts, slots - 1);
+            LAUNCH_CHECK(ctx);
+            int grid2 = (int)std::min<uint64_t>((slots + 255) / 256, (uint64_t)ctx->num_sms * 8);
+            kmer_count_emit_kernel<<<grid2, 256, 0, stream>>>(keys, counts, slots, min_abund, spec,
+                                                              (uint32_t *)(d_filters + dg[i].filter_word_off));
+            LAUNCH_CHECK(ctx);
+        }
+        return MSBT_OK;
+    }
+
+    if (tiles == 0) return MSBT_OK;
+    size_t table_b = align_up(sizeof(DevGenome) * n_genomes, 256);
+    int rc = ensure_scratch(ctx, table_b);
+    if (rc) return rc;
+    rc = stage_begin(ctx, table_b);
+    if (rc) return rc;
+    rc = stage_to_device(ctx, ctx->d_scratch, dg.data(), sizeof(DevGenome) * n_genomes, 0, stream);
+    if (rc) return rc;
+    rc = stage_end(ctx, stream);
+    if (rc) return rc;
+
+    int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * 8);
+    if (k <= 32)
+        kmer_bloom_direct_kernel<1><<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, (const DevGenome *)ctx->d_scratch,
+                                                                     n_genomes, (uint32_t)tiles, spec, (uint32_t *)d_filters);
+    else
+        kmer_bloom_direct_kernel<2><<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, (const DevGenome *)ctx->d_scratch,
+                                                                     n_genomes, (uint32_t)tiles, spec, (uint32_t *)d_filters);
+    LAUNCH_CHECK(ctx);
+    return MSBT_OK;
+}
+
+// --------------------------------------------------------------------------- K2 / K3 filter algebra
+
+__device__ __forceinline__ uint4 ld_stream(const uint4 *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ uint32_t popc4(uint4 v) { return __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w); }
+
+__device__ __forceinline__ uint64_t block_sum_u64(uint64_t v) {
+    __shared__ uint64_t warp_part[32];
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) warp_part[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    v = (threadIdx.x < nw) ? warp_part[threadIdx.x] : 0;
+    if (wid == 0)
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;  // valid in thread 0
+}
+
+// dst = OR of n sources; `vec` = number of uint4 (two u64 words) per filter.
+__global__ void __launch_bounds__(256)
+bf_or_reduce_kernel(const uint4 *const *__restrict__ srcs, uint32_t n, uint64_t vec, uint4 *__restrict__ dst) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < vec; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 acc = make_uint4(0, 0, 0, 0);
+        uint32_t s = 0;
+        for (; s + 4 <= n; s += 4) {
+            uint4 a = ld_stream(srcs[s] + i), b = ld_stream(srcs[s + 1] + i);
+            uint4 c = ld_stream(srcs[s + 2] + i), d = ld_stream(srcs[s + 3] + i);
+            acc.x |= a.x | b.x | c.x | d.x;
+            acc.y |= a.y | b.y | c.y | d.y;
+            acc.z |= a.z | b.z | c.z | d.z;
+            acc.w |= a.w | b.w | c.w | d.w;
+        }
+        for (; s < n; s++) {
+            uint4 a = ld_stream(srcs[s] + i);
+            acc.x |= a.x; acc.y |= a.y; acc.z |= a.z; acc.w |= a.w;
+        }
+        dst[i] = acc;
+    }
+}
+
+// scalar tail for an odd number of u64 words
+__global__ void bf_or_tail_kernel(const uint64_t *const *__restrict__ srcs, uint32_t n, uint64_t w, uint64_t *__restrict__ dst) {
+    uint64_t acc = 0;
+    for (uint32_t s = 0; s < n; s++) acc |= srcs[s][w];
+    dst[w] = acc;
+}
+
+// out[f] += popcount of a slice of filter f.  grid = (chunks, n)
+__global__ void __launch_bounds__(256)
+bf_popcount_kernel(const uint64_t *const *__restrict__ filters, uint64_t words, unsigned long long *__restrict__ out) {
+    const uint64_t *__restrict__ f = filters[blockIdx.y];
+    const uint64_t vec = words >> 1;
+    const uint4 *fv = (const uint4 *)f;
+    uint64_t c = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < vec; i += (uint64_t)gridDim.x * blockDim.x)
+        c += popc4(ld_stream(fv + i));
+    if ((words & 1) && blockIdx.x == 0 && threadIdx.x == 0) c += __popcll(f[words - 1]);
+    c = block_sum_u64(c);
+    if (threadIdx.x == 0 && c) atomicAdd(out + blockIdx.y, (unsigned long long)c);
+}
+
+// One focus against TB targets per CTA pass: the focus slice is read once per TB targets.
+constexpr int DIST_TB = 4;
+__global__ void __launch_bounds__(256)
+bf_dist_1vN_kernel(const uint64_t *__restrict__ focus, const uint64_t *const *__restrict__ targets, uint32_t n,
+                   uint64_t words, unsigned long long *__restrict__ out_and, unsigned long long *__restrict__ out_or) {
+    const uint32_t t0 = blockIdx.y * DIST_TB;
+    const uint64_t vec = words >> 1;
+    const uint4 *fv = (const uint4 *)focus;
+    const uint4 *tv[DIST_TB];
+#pragma unroll
+    for (int t = 0; t < DIST_TB; t++) tv[t] = (const uint4 *)targets[min(t0 + t, n - 1)];
+    uint64_t ca[DIST_TB] = {0}, co[DIST_TB] = {0};
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < vec; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 a = ld_stream(fv + i);
+        uint4 b[DIST_TB];
+#pragma unroll
+        for (int t = 0; t < DIST_TB; t++) b[t] = ld_stream(tv[t] + i);
+#pragma unroll
+        for (int t = 0; t < DIST_TB; t++) {
+            ca[t] += __popc(a.x & b[t].x) + __popc(a.y & b[t].y) + __popc(a.z & b[t].z) + __popc(a.w & b[t].w);
+            co[t] += __popc(a.x | b[t].x) + __popc(a.y | b[t].y) + __popc(a.z | b[t].z) + __popc(a.w | b[t].w);
+        }
+    }
+    if ((words & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        uint64_t a = focus[words - 1];
+#pragma unroll
+        for (int t = 0; t < DIST_TB; t++) {
+            uint64_t b = ((const uint64_t *)tv[t])[words - 1];
+            ca[t] += __popcll(a & b);
+            co[t] += __popcll(a | b);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < DIST_TB; t++) {
+        uint64_t sa = block_sum_u64(ca[t]);
+        uint64_t so = block_sum_u64(co[t]);
+        if (threadIdx.x == 0 && t0 + t < n) {
+            if (sa) atomicAdd(out_and + t0 + t, (unsigned long long)sa);
+            if (so) atomicAdd(out_or + t0 + t, (unsigned long long)so);
+        }
+    }
+}
+
+// All pairs: CTA (bx, by, bz) handles filters I = by*AP_T.., J = bz*AP_T.. over word chunks bx.
+// Each thread keeps AP_T x AP_T partial counts; the 2*AP_T slices are read once per tile pair.
+constexpr int AP_T = 4;
+__global__ void __launch_bounds__(256)
+bf_allpairs_kernel(const uint64_t *const *__restrict__ filters, uint32_t n, uint64_t words,
+                   unsigned long long *__restrict__ out) {
+    const uint32_t i0 = blockIdx.y * AP_T, j0 = blockIdx.z * AP_T;
+    if (j0 + AP_T <= i0) return;  // strictly-lower tiles: covered by symmetry
+    const uint64_t vec = words >> 1;
+    const uint4 *iv[AP_T], *jv[AP_T];
+#pragma unroll
+    for (int t = 0; t < AP_T; t++) {
+        iv[t] = (const uint4 *)filters[min(i0 + t, n - 1)];
+        jv[t] = (const uint4 *)filters[min(j0 + t, n - 1)];
+    }
+    uint32_t c[AP_T][AP_T] = {{0}};
+    uint64_t acc[AP_T][AP_T] = {{0}};
+    uint32_t iters = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < vec; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 a[AP_T], b[AP_T];
+#pragma unroll
+        for (int t = 0; t < AP_T; t++) { a[t] = ld_stream(iv[t] + i); b[t] = ld_stream(jv[t] + i); }
+#pragma unroll
+        for (int x = 0; x < AP_T; x++)
+#pragma unroll
+            for (int y = 0; y < AP_T; y++)
+                c[x][y] += __popc(a[x].x & b[y].x) + __popc(a[x].y & b[y].y) + __popc(a[x].z & b[y].z) + __popc(a[x].w & b[y].w);
+        if (++iters == (1u << 24)) {  // 128 bits per iteration: flush long before u32 overflow
+#pragma unroll
+            for (int x = 0; x < AP_T; x++)
+#pragma unroll
+                for (int y = 0; y < AP_T; y++) { acc[x][y] += c[x][y]; c[x][y] = 0; }
+            iters = 0;
+        }
+    }
+    if ((words & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+#pragma unroll
+        for (int x = 0; x < AP_T; x++)
+#pragma unroll
+            for (int y = 0; y < AP_T; y++)
+                acc[x][y] += __popcll(((const uint64_t *)iv[x])[words - 1] & ((const uint64_t *)jv[y])[words - 1]);
+    }
+#pragma unroll
+    for (int x = 0; x < AP_T; x++)
+#pragma unroll
+        for (int y = 0; y < AP_T; y++) {
+            uint64_t s = block_sum_u64(acc[x][y] + c[x][y]);
+            const uint32_t fi = i0 + x, fj = j0 + y;
+            if (threadIdx.x == 0 && fi < n && fj < n && fi <= fj && s) {
+                atomicAdd(out + (uint64_t)fi * n + fj, (unsigned long long)s);
+                if (fi != fj) atomicAdd(out + (uint64_t)fj * n + fi, (unsigned long long)s);
+            }
+        }
+}
+
+// Upload a host array of n device pointers into scratch; returns the device copy.
+static int upload_ptrs(msbt_ctx *ctx, const uint64_t *const *h_ptrs, uint32_t n, cudaStream_t stream,
+                       const uint64_t *const **d_out) {
+    size_t bytes = align_up((size_t)n * sizeof(void *), 256);
+    int rc = ensure_scratch(ctx, bytes);
+    if (rc) return rc;
+    rc = stage_begin(ctx, bytes);
+    if (rc) return rc;
+    rc = stage_to_device(ctx, ctx->d_scratch, h_ptrs, (size_t)n * sizeof(void *), 0, stream);
+    if (rc) return rc;
+    rc = stage_end(ctx, stream);
+    if (rc) return rc;
+    *d_out = (const uint64_t *const *)ctx->d_scratch;
+    return MSBT_OK;
+}
+
+static int check_ptrs(msbt_ctx *ctx, const uint64_t *const *h, uint32_t n) {
+    if (!h) return fail(ctx, MSBT_EINVAL, "null pointer table");
+    for (uint32_t i = 0; i < n; i++) {
+        if (!h[i]) return fail(ctx, MSBT_EINVAL, "filter %u is a null pointer", i);
+        if (((uintptr_t)h[i]) & 15) return fail(ctx, MSBT_EINVAL, "filter %u is not 16-byte aligned", i);
+    }
+    return MSBT_OK;
+}
+
+static int stream_grid(const msbt_ctx *ctx, uint64_t vec, int per_sm) {
+    uint64_t want = (vec + 255) / 256;
+    return (int)std::max<uint64_t>(1, std::min<uint64_t>(want, (uint64_t)ctx->num_sms * per_sm));
+}
+
+extern "C" int msbt_bf_or_reduce(msbt_ctx *ctx, const uint64_t *const *h_srcs, uint32_t n, uint64_t words,
+                                 uint64_t *d_dst, void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0 || words == 0 || !d_dst) return fail(ctx, MSBT_EINVAL, "bf_or_reduce: empty input");
+    int rc = check_ptrs(ctx, h_srcs, n);
+    if (rc) return rc;
+    if (((uintptr_t)d_dst) & 15) return fail(ctx, MSBT_EINVAL, "destination is not 16-byte aligned");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t *const *d_srcs;
+    rc = upload_ptrs(ctx, h_srcs, n, stream, &d_srcs);
+    if (rc) return rc;
+    const uint64_t vec = words >> 1;
+    if (vec) {
+        bf_or_reduce_kernel<<<stream_grid(ctx, vec, 8), 256, 0, stream>>>((const uint4 *const *)d_srcs, n, vec, (uint4 *)d_dst);
+        LAUNCH_CHECK(ctx);
+    }
+    if (words & 1) {
+        bf_or_tail_kernel<<<1, 1, 0, stream>>>(d_srcs, n, words - 1, d_dst);
+        LAUNCH_CHECK(ctx);
+    }
+    return MSBT_OK;
+}
+
+extern "C" int msbt_bf_popcount(msbt_ctx *ctx, const uint64_t *const *h_filters, uint32_t n, uint64_t words,
+                                uint64_t *d_out, void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return MSBT_OK;
+    if (words == 0 || !d_out) return fail(ctx, MSBT_EINVAL, "bf_popcount: empty input");
+    int rc = check_ptrs(ctx, h_filters, n);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t *const *d_f;
+    rc = upload_ptrs(ctx, h_filters, n, stream, &d_f);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaMemsetAsync(d_out, 0, (size_t)n * 8, stream));
+    const uint64_t vec = std::max<uint64_t>(words >> 1, 1);
+    uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((vec + 255) / 256, std::max<uint64_t>(1, (uint64_t)ctx->num_sms * 8 / n)));
+    for (uint32_t off = 0; off < n; off += 65535) {
+        uint32_t cnt = std::min<uint32_t>(65535, n - off);
+        bf_popcount_kernel<<<dim3((unsigned)gx, cnt), 256, 0, stream>>>(d_f + off, words, (unsigned long long *)d_out + off);
+        LAUNCH_CHECK(ctx);
+    }
+    return MSBT_OK;
+}
+
+extern "C" int msbt_bf_and_popcount_1vN(msbt_ctx *ctx, const uint64_t *d_focus, const uint64_t *const *h_targets,
+                                        uint32_t n, uint64_t words, uint64_t *d_intersect, uint64_t *d_union,
+                                        void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return MSBT_OK;
+    if (words == 0 || !d_focus || !d_intersect || !d_union) return fail(ctx, MSBT_EINVAL, "bf_and_popcount_1vN: null/empty input");
+    if (((uintptr_t)d_focus) & 15) return fail(ctx, MSBT_EINVAL, "focus is not 16-byte aligned");
+    int rc = check_ptrs(ctx, h_targets, n);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t *const *d_t;
+    rc = upload_ptrs(ctx, h_targets, n, stream, &d_t);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaMemsetAsync(d_intersect, 0, (size_t)n * 8, stream));
+    CU_TRY(ctx, cudaMemsetAsync(d_union, 0, (size_t)n * 8, stream));
+    const uint64_t vec = std::max<uint64_t>(words >> 1, 1);
+    const uint32_t groups = (n + DIST_TB - 1) / DIST_TB;
+    uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((vec + 255) / 256, std::max<uint64_t>(1, (uint64_t)ctx->num_sms * 8 / groups)));
+    for (uint32_t off = 0; off < groups; off += 65535) {
+        uint32_t cnt = std::min<uint32_t>(65535, groups - off);
+        uint32_t first = off * DIST_TB;
+        bf_dist_1vN_kernel<<<dim3((unsigned)gx, cnt), 256, 0, stream>>>(d_focus, d_t + first, n - first, words,
+                                                                       (unsigned long long *)d_intersect + first,
+                                                                       (unsigned long long *)d_union + first);
+        LAUNCH_CHECK(ctx);
+    }
+    return MSBT_OK;
+}
+
+extern "C" int msbt_bf_and_popcount_allpairs(msbt_ctx *ctx, const uint64_t *const *h_filters, uint32_t n,
+                                             uint64_t words, uint64_t *d_intersect, void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return MSBT_OK;
+    if (words == 0 || !d_intersect) return fail(ctx, MSBT_EINVAL, "bf_and_popcount_allpairs: null/empty input");
+    int rc = check_ptrs(ctx, h_filters, n);
+    if (rc) return rc;
+    const uint32_t tiles = (n + AP_T - 1) / AP_T;
+    if (tiles > 65535) return fail(ctx, MSBT_EINVAL, "allpairs: n=%u too large for one call", n);
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t *const *d_f;
+    rc = upload_ptrs(ctx, h_filters, n, stream, &d_f);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaMemsetAsync(d_intersect, 0, (size_t)n * n * 8, stream));
+    const uint64_t vec = std::max<uint64_t>(words >> 1, 1);
+    const uint64_t pair_tiles = (uint64_t)tiles * (tiles + 1) / 2;
+    uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((vec + 255) / 256, std::max<uint64_t>(1, (uint64_t)ctx->num_sms * 8 / pair_tiles)));
+    bf_allpairs_kernel<<<dim3((unsigned)gx, tiles, tiles), 256, 0, stream>>>(d_f, n, words, (unsigned long long *)d_intersect);
+    LAUNCH_CHECK(ctx);
+    return MSBT_OK;
+}
+
+// --------------------------------------------------------------------------- K4: query
+
+constexpr int EX_THREADS = 256;
+constexpr int EX_WORDS_PER_THREAD = 4;  // u64 words
+constexpr int EX_CHUNK = EX_THREADS * EX_WORDS_PER_THREAD;
+
+// pass 1: per-chunk popcounts
+__global__ void __launch_bounds__(EX_THREADS)
+bf_extract_count_kernel(const uint64_t *__restrict__ f, uint64_t words, unsigned long long *__restrict__ chunk_counts) {
+    const uint64_t base = (uint64_t)blockIdx.x * EX_CHUNK + (uint64_t)threadIdx.x * EX_WORDS_PER_THREAD;
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < EX_WORDS_PER_THREAD; i++)
+        if (base + i < words) c += __popcll(f[base + i]);
+    c = block_sum_u64(c);
+    if (threadIdx.x == 0) chunk_counts[blockIdx.x] = c;
+}
+
+// pass 2: exclusive scan of chunk counts by one CTA (in place); total -> *d_count
+__global__ void __launch_bounds__(1024)
+bf_extract_scan_kernel(unsigned long long *__restrict__ chunk_counts, uint64_t n_chunks, unsigned long long *__restrict__ d_count) {
+    __shared__ unsigned long long part[1024];
+    const uint64_t per = (n_chunks + 1023) / 1024;
+    const uint64_t b = threadIdx.x * per, e = min(b + per, n_chunks);
+    unsigned long long s = 0;
+    for (uint64_t i = b; i < e; i++) s += chunk_counts[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < 1024; i++) { unsigned long long t = part[i]; part[i] = run; run += t; }
+        *d_count = run;
+    }
+    __syncthreads();
+    unsigned long long run = part[threadIdx.x];
+    for (uint64_t i = b; i < e; i++) { unsigned long long t = chunk_counts[i]; chunk_counts[i] = run; run += t; }
+}
+
+// pass 3: ordered emission
+__global__ void __launch_bounds__(EX_THREADS)
+bf_extract_emit_kernel(const uint64_t *__restrict__ f, uint64_t words, const unsigned long long *__restrict__ chunk_offsets,
+                       uint32_t *__restrict__ out, uint64_t cap) {
+    __shared__ uint32_t warp_tot[EX_THREADS / 32];
+    const uint64_t base = (uint64_t)blockIdx.x * EX_CHUNK + (uint64_t)threadIdx.x * EX_WORDS_PER_THREAD;
+    uint64_t v[EX_WORDS_PER_THREAD];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int i = 0; i < EX_WORDS_PER_THREAD; i++) {
+        v[i] = (base + i < words) ? f[base + i] : 0;
+        mine += __popcll(v[i]);
+    }
+    // exclusive prefix inside the CTA
+    uint32_t incl = mine;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w2 = 0; w2 < wid; w2++) woff += warp_tot[w2];
+    uint64_t o = chunk_offsets[blockIdx.x] + woff + (incl - mine);
+#pragma unroll
+    for (int i = 0; i < EX_WORDS_PER_THREAD; i++) {
+        uint64_t x = v[i];
+        while (x) {
+            int b = __ffsll((long long)x) - 1;
+            x &= x - 1;
+            if (o < cap) out[o] = (uint32_t)(((base + i) << 6) + b);
+            o++;
+        }
+    }
+}
+
+extern "C" int msbt_bf_extract_positions(msbt_ctx *ctx, const uint64_t *d_filter, uint64_t words,
+                                         uint32_t *d_positions, uint64_t cap, uint64_t *d_count, void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!d_filter || !d_count || words == 0) return fail(ctx, MSBT_EINVAL, "bf_extract_positions: null/empty input");
+    if (words > (1ull << 26)) return fail(ctx, MSBT_EINVAL, "bf_extract_positions: positions are u32 (num_bits <= 2^32)");
+    if (cap && !d_positions) return fail(ctx, MSBT_EINVAL, "bf_extract_positions: null output");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t n_chunks = (words + EX_CHUNK - 1) / EX_CHUNK;
+    // chunk table lives past the first 64 KiB of scratch (pointer tables use the front)
+    const size_t off = 1 << 16;
+    int rc = ensure_scratch(ctx, off + n_chunks * 8);
+    if (rc) return rc;
+    unsigned long long *chunks = (unsigned long long *)((char *)ctx->d_scratch + off);
+    bf_extract_count_kernel<<<(unsigned)n_chunks, EX_THREADS, 0, stream>>>(d_filter, words, chunks);
+    LAUNCH_CHECK(ctx);
+    bf_extract_scan_kernel<<<1, 1024, 0, stream>>>(chunks, n_chunks, (unsigned long long *)d_count);
+    LAUNCH_CHECK(ctx);
+    if (cap) {
+        bf_extract_emit_kernel<<<(unsigned)n_chunks, EX_THREADS, 0, stream>>>(d_filter, words, chunks, d_positions, cap);
+        LAUNCH_CHECK(ctx);
+    }
+    return MSBT_OK;
+}
+
+// Row-major probe: CTA (leaf-group, query).  Each thread walks positions with stride and
+// tests QL leaves per position so the position stream is read once per QL leaves.
+constexpr int QL = 4;
+__global__ void __launch_bounds__(256)
+query_rowmajor_kernel(const uint64_t *const *__restrict__ leaves, uint32_t n_leaves, const uint32_t *__restrict__ positions,
+                      const unsigned long long *__restrict__ q_off, uint32_t *__restrict__ hits) {
+    const uint32_t q = blockIdx.y, l0 = blockIdx.x * QL;
+    const uint64_t b = q_off[q], e = q_off[q + 1];
+    const uint32_t *lf[QL];
+#pragma unroll
+    for (int t = 0; t < QL; t++) lf[t] = (const uint32_t *)leaves[min(l0 + t, n_leaves - 1)];
+    uint32_t c[QL] = {0};
+    for (uint64_t i = b + threadIdx.x; i < e; i += blockDim.x) {
+        const uint32_t p = positions[i];
+#pragma unroll
+        for (int t = 0; t < QL; t++) c[t] += (__ldg(lf[t] + (p >> 5)) >> (p & 31)) & 1u;
+    }
+#pragma unroll
+    for (int t = 0; t < QL; t++) {
+        uint64_t s = block_sum_u64(c[t]);
+        if (threadIdx.x == 0 && l0 + t < n_leaves) hits[(uint64_t)q * n_leaves + l0 + t] = (uint32_t)s;
+    }
+}
+
+static int upload_offsets(msbt_ctx *ctx, const uint64_t *h_off, uint32_t n_queries, size_t scratch_off,
+                          cudaStream_t stream, const unsigned long long **d_out) {
+    size_t bytes = (size_t)(n_queries + 1) * 8;
+    int rc = ensure_scratch(ctx, scratch_off + bytes);
+    if (rc) return rc;
+    // staging area after the pointer table region
+    rc = stage_to_device(ctx, (char *)ctx->d_scratch + scratch_off, h_off, bytes, scratch_off, stream);
+    if (rc) return rc;
+    *d_out = (const unsigned long long *)((char *)ctx->d_scratch + scratch_off);
+    return MSBT_OK;
+}
+
+extern "C" int msbt_query_batch(msbt_ctx *ctx, const uint64_t *const *h_leaves, uint32_t n_leaves,
+                                const uint32_t *d_positions, const uint64_t *h_query_offsets, uint32_t n_queries,
+                                uint32_t *d_hits, void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_queries == 0 || n_leaves == 0) return MSBT_OK;
+    if (!h_query_offsets || !d_hits) return fail(ctx, MSBT_EINVAL, "query_batch: null argument");
+    if (n_queries > 65535) return fail(ctx, MSBT_EINVAL, "query_batch: at most 65535 queries per call");
+    int rc = check_ptrs(ctx, h_leaves, n_leaves);
+    if (rc) return rc;
+    for (uint32_t q = 0; q < n_queries; q++)
+        if (h_query_offsets[q + 1] < h_query_offsets[q]) return fail(ctx, MSBT_EINVAL, "query offsets must be non-decreasing");
+    if (h_query_offsets[n_queries] && !d_positions) return fail(ctx, MSBT_EINVAL, "query_batch: null positions");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t ptr_b = align_up((size_t)n_leaves * sizeof(void *), 256);
+    const size_t off_b = (size_t)(n_queries + 1) * 8;
+    rc = ensure_scratch(ctx, ptr_b + off_b);
+    if (rc) return rc;
+    rc = stage_begin(ctx, ptr_b + off_b);
+    if (rc) return rc;
+    rc = stage_to_device(ctx, ctx->d_scratch, h_leaves, (size_t)n_leaves * sizeof(void *), 0, stream);
+    if (rc) return rc;
+    const unsigned long long *d_off;
+    rc = upload_offsets(ctx, h_query_offsets, n_queries, ptr_b, stream, &d_off);
+    if (rc) return rc;
+    rc = stage_end(ctx, stream);
+    if (rc) return rc;
+    const uint32_t groups = (n_leaves + QL - 1) / QL;
+    query_rowmajor_kernel<<<dim3(groups, n_queries), 256, 0, stream>>>((const uint64_t *const *)ctx->d_scratch, n_leaves,
+                                                                      d_positions, d_off, d_hits);
+    LAUNCH_CHECK(ctx);
+    return MSBT_OK;
+}
+
+// Bit-slice transpose: thread block handles 32 rows x 32 leaves at a time through shared memory.
+// sliced[(p - row_begin) * lw + (l >> 5)] bit (l & 31) = bit p of leaf l.
+__global__ void __launch_bounds__(256)
+bitslice_kernel(const uint64_t *const *__restrict__ leaves, uint32_t n_leaves, uint64_t row_begin, uint64_t row_end,
+                uint32_t lw, uint32_t *__restrict__ sliced) {
+    // CTA: 8 warps; warp handles one 32-row block (one u32 word of each of 32 leaves) for a leaf group.
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint64_t first_word = row_begin >> 5;                 // row_begin is a multiple of 32
+    const uint64_t n_rowwords = (row_end - row_begin + 31) >> 5;
+    const uint32_t lg = blockIdx.y;                              // leaf group (32 leaves)
+    const uint32_t leaf = lg * 32 + lane;
+    const uint32_t *lf = (leaf < n_leaves) ? (const uint32_t *)leaves[leaf] : nullptr;
+    for (uint64_t rw = (uint64_t)blockIdx.x * 8 + warp; rw < n_rowwords; rw += (uint64_t)gridDim.x * 8) {
+        uint32_t v = lf ? lf[first_word + rw] : 0u;  // lane = leaf: word holding rows rw*32..+31
+        // 32x32 bit transpose across the warp: out lane r gets bit r of every lane's v
+        uint32_t outw = 0;
+#pragma unroll
+        for (int r = 0; r < 32; r++) {
+            uint32_t bal = __ballot_sync(0xffffffffu, (v >> r) & 1u);
+            if (lane == r) outw = bal;
+        }
+        const uint64_t row = rw * 32 + lane;  // relative row
+        if (row_begin + row < row_end) sliced[row * lw + lg] = outw;
+    }
+}
+
+// Sliced probe: CTA = (leaf-word group, query).  Thread owns one u32 column word (32 leaves) and
+// walks the query's positions; vertical (bit-plane) counters absorb 15 rows between flushes.
+__global__ void __launch_bounds__(128)
+query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint32_t lw, uint64_t row_begin, uint64_t row_end,
+                    const uint32_t *__restrict__ positions, const unsigned long long *__restrict__ q_off,
+                    uint32_t *__restrict__ hits) {
+    const uint32_t q = blockIdx.y;
+    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= lw) return;
+    const uint64_t b = q_off[q], e = q_off[q + 1];
+    uint32_t cnt[32];
+#pragma unroll
+    for (int i = 0; i < 32; i++) cnt[i] = 0;
+    uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;  // bit planes of a 4-bit vertical counter
+    uint32_t pending = 0;
+    for (uint64_t i = b; i < e; i++) {
+        const uint64_t p = positions[i];
+        if (p < row_begin || p >= row_end) continue;
+        uint32_t x = __ldg(sliced + (p - row_begin) * lw + col);
+        // ripple-carry add of the 1-bit row x into planes p0..p3
+        uint32_t c0 = p0 & x; p0 ^= x;
+        uint32_t c1 = p1 & c0; p1 ^= c0;
+        uint32_t c2 = p2 & c1; p2 ^= c1;
+        p3 ^= c2;
+        if (++pending == 15) {
+#pragma unroll
+            for (int l = 0; l < 32; l++)
+                cnt[l] += ((p0 >> l) & 1u) + 2u * ((p1 >> l) & 1u) + 4u * ((p2 >> l) & 1u) + 8u * ((p3 >> l) & 1u);
+            p0 = p1 = p2 = p3 = 0;
+            pending = 0;
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < 32; l++) {
+        uint32_t c = cnt[l] + ((p0 >> l) & 1u) + 2u * ((p1 >> l) & 1u) + 4u * ((p2 >> l) & 1u) + 8u * ((p3 >> l) & 1u);
+        const uint32_t leaf = col * 32 + l;
+        if (leaf < n_leaves) hits[(uint64_t)q * n_leaves + leaf] = c;
+    }
+}
+
+extern "C" int msbt_bitslice_build(msbt_ctx *ctx, const uint64_t *const *h_leaves, uint32_t n_leaves,
+                                   uint64_t row_begin, uint64_t row_end, uint32_t *d_sliced, void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_leaves == 0 || row_end <= row_begin) return MSBT_OK;
+    if (!d_sliced) return fail(ctx, MSBT_EINVAL, "bitslice_build: null output");
+    if (row_begin & 31) return fail(ctx, MSBT_EINVAL, "bitslice_build: row_begin must be a multiple of 32");
+    int rc = check_ptrs(ctx, h_leaves, n_leaves);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint64_t *const *d_l;
+    rc = upload_ptrs(ctx, h_leaves, n_leaves, stream, &d_l);
+    if (rc) return rc;
+    const uint32_t lw = (n_leaves + 31) / 32;
+    if (lw > 65535) return fail(ctx, MSBT_EINVAL, "bitslice_build: too many leaves");
+    const uint64_t n_rowwords = (row_end - row_begin + 31) >> 5;
+    uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((n_rowwords + 7) / 8, (uint64_t)ctx->num_sms * 32));
+    bitslice_kernel<<<dim3((unsigned)gx, lw), 256, 0, stream>>>(d_l, n_leaves, row_begin, row_end, lw, d_sliced);
+    LAUNCH_CHECK(ctx);
+    return MSBT_OK;
+}
+
+extern "C" int msbt_query_batch_sliced(msbt_ctx *ctx, const uint32_t *d_sliced, uint32_t n_leaves, uint64_t row_begin,
+                                       uint64_t row_end, const uint32_t *d_positions, const uint64_t *h_query_offsets,
+                                       uint32_t n_queries, uint32_t *d_hits, void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_queries == 0 || n_leaves == 0) return MSBT_OK;
+    if (!d_sliced || !h_query_offsets || !d_hits) return fail(ctx, MSBT_EINVAL, "query_batch_sliced: null argument");
+    if (n_queries > 65535) return fail(ctx, MSBT_EINVAL, "query_batch_sliced: at most 65535 queries per call");
+    for (uint32_t q = 0; q < n_queries; q++)
+        if (h_query_offsets[q + 1] < h_query_offsets[q]) return fail(ctx, MSBT_EINVAL, "query offsets must be non-decreasing");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const size_t off_b = (size_t)(n_queries + 1) * 8;
+    int rc = ensure_scratch(ctx, off_b);
+    if (rc) return rc;
+    rc = stage_begin(ctx, off_b);
+    if (rc) return rc;
+    const unsigned long long *d_off;
+    rc = upload_offsets(ctx, h_query_offsets, n_queries, 0, stream, &d_off);
+    if (rc) return rc;
+    rc = stage_end(ctx, stream);
+    if (rc) return rc;
+    const uint32_t lw = (n_leaves + 31) / 32;
+    query_sliced_kernel<<<dim3((lw + 127) / 128, n_queries), 128, 0, stream>>>(d_sliced, n_leaves, lw, row_begin, row_end,
+                                                                             d_positions, d_off, d_hits);
+    LAUNCH_CHECK(ctx);
+    return MSBT_OK;
+}

@@ -1,0 +1,344 @@
+/*
+ * oracle/msbt_oracle.c -- CPU restatement of the HowDeSBT arithmetic that MetaSBT drives.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the shipped package (metasbt_b200/) may import,
+ * link or execute this file; only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs use it, and only as the checker / CPU baseline.
+ *
+ * PARITY UNPINNED.  The arithmetic of this path lives in the third-party binary `howdesbt`
+ * (github.com/medvedevgroup/HowDe-SBT; C++ with sdsl-lite, CRoaring, Jellyfish), which is
+ * neither vendored under /root/reference nor version-pinned by it (only core.py:38 names
+ * the `Makefile_full` build flavour), and the reference's own test (metasbt.py:1389-1555)
+ * asserts file existence only.  This file therefore restates the published algorithm of
+ * HowDeSBT as recorded in SURVEY.md Appendix A and anchors on the reference's call sites:
+ *
+ *   makebf      core.py:3920-3931   --k --min --bits --hashes=1 --seed=0,0
+ *   bfoperate   core.py:3851-3857   --or over a list
+ *   bfdistance  core.py:1747-1753, 1768-1774   --show:intersect / --show:union
+ *   dumpbf      core.py:3588-3593   --show:density
+ *   query       core.py:2039-2047   --sort --distinctkmers --threshold
+ *
+ * The one piece with a published known-answer is MurmurHash3_x64_128 (Austin Appleby,
+ * public domain, smhasher); tests/test_oracle.py pins it against its well-known vectors.
+ *
+ * Everything is single-threaded, scalar and written to be obviously correct, not fast.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ MurmurHash3_x64_128 */
+
+static inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+
+static inline uint64_t fmix64(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdULL;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ULL;
+    k ^= k >> 33;
+    return k;
+}
+
+/* Byte-wise restatement of smhasher's MurmurHash3_x64_128 (little-endian block reads). */
+void orc_murmur3_x64_128(const void *key, int len, uint32_t seed, uint64_t out[2]) {
+    const uint8_t *data = (const uint8_t *)key;
+    const int nblocks = len / 16;
+    uint64_t h1 = seed, h2 = seed;
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+
+    for (int i = 0; i < nblocks; i++) {
+        uint64_t k1 = 0, k2 = 0;
+        for (int b = 0; b < 8; b++) {
+            k1 |= (uint64_t)data[i * 16 + b] << (8 * b);
+            k2 |= (uint64_t)data[i * 16 + 8 + b] << (8 * b);
+        }
+        k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1;
+        h1 = rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2;
+        h2 = rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    }
+
+    const uint8_t *tail = data + nblocks * 16;
+    uint64_t k1 = 0, k2 = 0;
+    int rem = len & 15;
+    for (int b = rem - 1; b >= 8; b--) k2 ^= (uint64_t)tail[b] << (8 * (b - 8));
+    if (rem > 8) { k2 *= c2; k2 = rotl64(k2, 33); k2 *= c1; h2 ^= k2; }
+    for (int b = (rem > 8 ? 8 : rem) - 1; b >= 0; b--) k1 ^= (uint64_t)tail[b] << (8 * b);
+    if (rem > 0) { k1 *= c1; k1 = rotl64(k1, 31); k1 *= c2; h1 ^= k1; }
+
+    h1 ^= (uint64_t)len; h2 ^= (uint64_t)len;
+    h1 += h2; h2 += h1;
+    h1 = fmix64(h1); h2 = fmix64(h2);
+    h1 += h2; h2 += h1;
+    out[0] = h1; out[1] = h2;
+}
+
+/* ------------------------------------------------------------------ k-mers (App. A1) */
+
+/* A=0 C=1 G=2 T=3, case-insensitive; anything else is -1 and breaks the run. */
+static inline int base_code(unsigned char c) {
+    switch (c) {
+        case 'A': case 'a': return 0;
+        case 'C': case 'c': return 1;
+        case 'G': case 'g': return 2;
+        case 'T': case 't': return 3;
+        default: return -1;
+    }
+}
+
+typedef struct { uint64_t hi, lo; } mer128; /* value = sum base_t << 2(k-1-t): first base most significant */
+
+static inline int mer_less(mer128 a, mer128 b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); }
+
+/* k-mer of codes[0..k) and its reverse complement, built from scratch (no rolling state). */
+static void mer_build(const int8_t *codes, int k, mer128 *fwd, mer128 *rc) {
+    mer128 f = {0, 0}, r = {0, 0};
+    for (int t = 0; t < k; t++) {
+        f.hi = (f.hi << 2) | (f.lo >> 62);
+        f.lo = (f.lo << 2) | (uint64_t)codes[t];
+        r.hi = (r.hi << 2) | (r.lo >> 62);
+        r.lo = (r.lo << 2) | (uint64_t)(3 - codes[k - 1 - t]);
+    }
+    *fwd = f; *rc = r;
+}
+
+/* Hash of a canonical k-mer: MurmurHash3_x64_128 over its 2-bit packed little-endian
+ * bytes (last base in the two lowest bits of byte 0), length (k+3)/4 bytes, first half. */
+static uint64_t mer_hash(mer128 m, int k, uint64_t seed) {
+    uint8_t bytes[16];
+    for (int b = 0; b < 8; b++) {
+        bytes[b] = (uint8_t)(m.lo >> (8 * b));
+        bytes[8 + b] = (uint8_t)(m.hi >> (8 * b));
+    }
+    uint64_t out[2];
+    orc_murmur3_x64_128(bytes, (k + 3) / 4, (uint32_t)seed, out);
+    return out[0];
+}
+
+/* Hash of one k-mer given as text; returns 0 and sets *ok=0 if it holds a non-ACGT char. */
+uint64_t orc_kmer_hash(const char *kmer, int k, uint64_t seed, int *ok) {
+    int8_t codes[64];
+    *ok = 0;
+    if (k < 1 || k > 64) return 0;
+    for (int t = 0; t < k; t++) {
+        int c = base_code((unsigned char)kmer[t]);
+        if (c < 0) return 0;
+        codes[t] = (int8_t)c;
+    }
+    mer128 f, r;
+    mer_build(codes, k, &f, &r);
+    *ok = 1;
+    return mer_hash(mer_less(r, f) ? r : f, k, seed);
+}
+
+/* Canonical k-mers of a FASTA text, in file order.  Records start at '>' lines; sequence
+ * lines of a record are concatenated; whitespace is skipped; any other non-ACGT character
+ * and every record boundary breaks the run, so no k-mer spans either.  Joining records with
+ * "N" (core.py:1974-1996) therefore yields exactly this same multiset.
+ * Returns the number of k-mers; *out (malloc'd, caller frees with orc_free) holds them. */
+static size_t fasta_canonical_mers(const char *text, size_t n, int k, mer128 **out) {
+    size_t cap = 1024, cnt = 0;
+    mer128 *mers = (mer128 *)malloc(cap * sizeof(mer128));
+    int8_t *win = (int8_t *)malloc((size_t)k);
+    int run = 0; /* number of consecutive valid bases ending here, capped at k */
+    size_t i = 0;
+    int at_line_start = 1;
+    while (i < n) {
+        unsigned char c = (unsigned char)text[i];
+        if (at_line_start && c == '>') {
+            while (i < n && text[i] != '\n') i++;
+            run = 0;
+            continue;
+        }
+        if (c == '\n') { at_line_start = 1; i++; continue; }
+        at_line_start = 0;
+        if (c == '\r' || c == ' ' || c == '\t') { i++; continue; }
+        int code = base_code(c);
+        i++;
+        if (code < 0) { run = 0; continue; }
+        if (run == k) {
+            memmove(win, win + 1, (size_t)k - 1);
+            run = k - 1;
+        }
+        win[run++] = (int8_t)code;
+        if (run == k) {
+            mer128 f, r;
+            mer_build(win, k, &f, &r);
+            if (cnt == cap) { cap *= 2; mers = (mer128 *)realloc(mers, cap * sizeof(mer128)); }
+            mers[cnt++] = mer_less(r, f) ? r : f;
+        }
+    }
+    free(win);
+    *out = mers;
+    return cnt;
+}
+
+static int mer_cmp(const void *a, const void *b) {
+    const mer128 *x = (const mer128 *)a, *y = (const mer128 *)b;
+    if (x->hi != y->hi) return x->hi < y->hi ? -1 : 1;
+    if (x->lo != y->lo) return x->lo < y->lo ? -1 : 1;
+    return 0;
+}
+
+static int u64_cmp(const void *a, const void *b) {
+    uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+    return x < y ? -1 : (x > y ? 1 : 0);
+}
+
+/* makebf (core.py:3920-3931; App. A1): one filter per FASTA, one hash function, a k-mer is
+ * inserted iff its exact canonical multiplicity in this file is >= min_abund; the bit is
+ * set only if pos = h % modulus < num_bits.  `words` has ceil(num_bits/64) u64 and is
+ * zeroed here.  Returns the number of (distinct-or-not, see below) insertions:
+ * with min_abund<=1 every k-mer occurrence, else every distinct qualifying k-mer. */
+int64_t orc_makebf(const char *text, size_t n, int k, uint64_t seed, uint64_t modulus,
+                   uint64_t num_bits, uint32_t min_abund, uint64_t *words) {
+    if (k < 1 || k > 64 || modulus == 0) return -1;
+    memset(words, 0, ((num_bits + 63) / 64) * 8);
+    mer128 *mers;
+    size_t cnt = fasta_canonical_mers(text, n, k, &mers);
+    int64_t inserted = 0;
+    if (min_abund <= 1) {
+        for (size_t i = 0; i < cnt; i++) {
+            uint64_t pos = mer_hash(mers[i], k, seed) % modulus;
+            if (pos < num_bits) words[pos >> 6] |= 1ULL << (pos & 63);
+            inserted++;
+        }
+    } else {
+        qsort(mers, cnt, sizeof(mer128), mer_cmp);
+        size_t i = 0;
+        while (i < cnt) {
+            size_t j = i;
+            while (j < cnt && mer_cmp(&mers[i], &mers[j]) == 0) j++;
+            if (j - i >= min_abund) {
+                uint64_t pos = mer_hash(mers[i], k, seed) % modulus;
+                if (pos < num_bits) words[pos >> 6] |= 1ULL << (pos & 63);
+                inserted++;
+            }
+            i = j;
+        }
+    }
+    free(mers);
+    return inserted;
+}
+
+/* query --distinctkmers k-merisation (core.py:2039-2047; App. A6): the set of distinct
+ * hash positions (< num_bits) of ALL k-mers of the file (no min filter), sorted ascending.
+ * Returns the count; *out is malloc'd (free with orc_free). */
+int64_t orc_positions_distinct(const char *text, size_t n, int k, uint64_t seed, uint64_t modulus,
+                               uint64_t num_bits, uint64_t **out) {
+    if (k < 1 || k > 64 || modulus == 0) return -1;
+    mer128 *mers;
+    size_t cnt = fasta_canonical_mers(text, n, k, &mers);
+    uint64_t *pos = (uint64_t *)malloc((cnt ? cnt : 1) * sizeof(uint64_t));
+    size_t np = 0;
+    for (size_t i = 0; i < cnt; i++) {
+        uint64_t p = mer_hash(mers[i], k, seed) % modulus;
+        if (p < num_bits) pos[np++] = p;
+    }
+    free(mers);
+    qsort(pos, np, sizeof(uint64_t), u64_cmp);
+    size_t u = 0;
+    for (size_t i = 0; i < np; i++)
+        if (u == 0 || pos[u - 1] != pos[i]) pos[u++] = pos[i];
+    *out = pos;
+    return (int64_t)u;
+}
+
+void orc_free(void *p) { free(p); }
+
+/* query hit counting (App. A6): hits[l] = #{p in P : bit p of filter l is set}. */
+void orc_query_hits(const uint64_t *positions, uint64_t n_pos, const uint64_t *const *filters,
+                    uint64_t n_filters, uint64_t *hits) {
+    for (uint64_t l = 0; l < n_filters; l++) {
+        uint64_t h = 0;
+        for (uint64_t i = 0; i < n_pos; i++) {
+            uint64_t p = positions[i];
+            h += (filters[l][p >> 6] >> (p & 63)) & 1;
+        }
+        hits[l] = h;
+    }
+}
+
+/* ------------------------------------------------------------------ filter algebra */
+
+static inline uint64_t popc64(uint64_t x) { return (uint64_t)__builtin_popcountll(x); }
+
+/* bfoperate --or (core.py:3851-3857; App. A3). */
+void orc_bf_or(uint64_t *dst, const uint64_t *const *srcs, uint64_t n, uint64_t words) {
+    for (uint64_t w = 0; w < words; w++) {
+        uint64_t acc = 0;
+        for (uint64_t s = 0; s < n; s++) acc |= srcs[s][w];
+        dst[w] = acc;
+    }
+}
+
+/* dumpbf --show:density numerator (core.py:3588-3605; App. A5). */
+uint64_t orc_bf_popcount(const uint64_t *a, uint64_t words) {
+    uint64_t c = 0;
+    for (uint64_t w = 0; w < words; w++) c += popc64(a[w]);
+    return c;
+}
+
+/* bfdistance --show:intersect / --show:union (core.py:1747-1774; App. A4). */
+uint64_t orc_bf_and_popcount(const uint64_t *a, const uint64_t *b, uint64_t words) {
+    uint64_t c = 0;
+    for (uint64_t w = 0; w < words; w++) c += popc64(a[w] & b[w]);
+    return c;
+}
+
+uint64_t orc_bf_or_popcount(const uint64_t *a, const uint64_t *b, uint64_t words) {
+    uint64_t c = 0;
+    for (uint64_t w = 0; w < words; w++) c += popc64(a[w] | b[w]);
+    return c;
+}
+
+/* ------------------------------------------------------------------ CPU-baseline variant
+ * Same result as orc_makebf(min_abund=1) but structured the way a production CPU tool
+ * would do it (rolling forward / reverse-complement words, k <= 32, no k-mer list), so
+ * that bench.py's cpu_baseline is not a strawman.  tests/ check it against orc_makebf. */
+int64_t orc_makebf_rolling(const char *text, size_t n, int k, uint64_t seed, uint64_t modulus,
+                           uint64_t num_bits, uint64_t *words) {
+    if (k < 1 || k > 32 || modulus == 0) return -1;
+    memset(words, 0, ((num_bits + 63) / 64) * 8);
+    const uint64_t mask = (k == 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
+    const int len = (k + 3) / 4;
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    const int pow2 = (modulus & (modulus - 1)) == 0;
+    uint64_t fwd = 0, rc = 0;
+    int run = 0;
+    int64_t inserted = 0;
+    size_t i = 0;
+    int at_line_start = 1;
+    while (i < n) {
+        unsigned char c = (unsigned char)text[i];
+        if (at_line_start && c == '>') {
+            while (i < n && text[i] != '\n') i++;
+            run = 0;
+            continue;
+        }
+        i++;
+        if (c == '\n') { at_line_start = 1; continue; }
+        at_line_start = 0;
+        if (c == '\r' || c == ' ' || c == '\t') continue;
+        int code = base_code(c);
+        if (code < 0) { run = 0; continue; }
+        fwd = ((fwd << 2) | (uint64_t)code) & mask;
+        rc = (rc >> 2) | ((uint64_t)(3 - code) << (2 * (k - 1)));
+        if (run < k) run++;
+        if (run == k) {
+            uint64_t m = fwd < rc ? fwd : rc;
+            /* MurmurHash3_x64_128, len <= 8 tail-only path, first half */
+            uint64_t k1 = m * c1; k1 = rotl64(k1, 31); k1 *= c2;
+            uint64_t h1 = (uint32_t)seed ^ k1, h2 = (uint32_t)seed;
+            h1 ^= (uint64_t)len; h2 ^= (uint64_t)len;
+            h1 += h2; h2 += h1;
+            h1 = fmix64(h1); h2 = fmix64(h2);
+            h1 += h2;
+            uint64_t pos = pow2 ? (h1 & (modulus - 1)) : (h1 % modulus);
+            if (pos < num_bits) words[pos >> 6] |= 1ULL << (pos & 63);
+            inserted++;
+        }
+    }
+    return inserted;
+}

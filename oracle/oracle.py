@@ -1,0 +1,284 @@
+"""ctypes front-end and pure-Python twin of oracle/msbt_oracle.c.
+
+TEST INFRASTRUCTURE ONLY -- PARITY UNPINNED (see the header of msbt_oracle.c).
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+may import this module.  The shipped package (metasbt_b200/) never does.
+
+Two independent CPU restatements live here so that they can check each other:
+
+* ``lib()``      -- the C restatement compiled with gcc (fast enough for Mbp inputs);
+* ``py_*``       -- pure-Python integer arithmetic for tiny cases only.
+
+Reference call sites restated (all in /root/reference/metasbt/core.py):
+makebf :3920-3931, bfoperate --or :3851-3857, bfdistance :1747-1774, dumpbf :3588-3605,
+query :2039-2089, ANI formula :1816-1829.
+"""
+
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+import subprocess
+from typing import Iterable, List, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "msbt_oracle.c")
+_SO = os.path.join(_HERE, "_build", "libmsbt_oracle.so")
+_LIB = None
+
+MASK64 = (1 << 64) - 1
+
+
+def build(force: bool = False) -> str:
+    """Compile the C restatement with gcc into oracle/_build/ (git-ignored)."""
+    if force or not os.path.isfile(_SO) or os.path.getmtime(_SO) < os.path.getmtime(_SRC):
+        os.makedirs(os.path.dirname(_SO), exist_ok=True)
+        subprocess.check_call(
+            ["gcc", "-O2", "-Wall", "-Wextra", "-shared", "-fPIC", "-o", _SO, _SRC]
+        )
+    return _SO
+
+
+def lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        if not os.path.isfile(_SO) or (
+            os.path.isfile(_SRC) and os.path.getmtime(_SO) < os.path.getmtime(_SRC)
+        ):
+            build()
+        L = ctypes.CDLL(_SO)
+        u64, u32, i64 = ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int64
+        vp, cp, sz = ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t
+        L.orc_murmur3_x64_128.argtypes = [cp, ctypes.c_int, u32, vp]
+        L.orc_murmur3_x64_128.restype = None
+        L.orc_kmer_hash.argtypes = [cp, ctypes.c_int, u64, ctypes.POINTER(ctypes.c_int)]
+        L.orc_kmer_hash.restype = u64
+        L.orc_makebf.argtypes = [cp, sz, ctypes.c_int, u64, u64, u64, u32, vp]
+        L.orc_makebf.restype = i64
+        L.orc_makebf_rolling.argtypes = [cp, sz, ctypes.c_int, u64, u64, u64, vp]
+        L.orc_makebf_rolling.restype = i64
+        L.orc_positions_distinct.argtypes = [cp, sz, ctypes.c_int, u64, u64, u64, ctypes.POINTER(vp)]
+        L.orc_positions_distinct.restype = i64
+        L.orc_free.argtypes = [vp]
+        L.orc_free.restype = None
+        L.orc_query_hits.argtypes = [vp, u64, vp, u64, vp]
+        L.orc_query_hits.restype = None
+        L.orc_bf_or.argtypes = [vp, vp, u64, u64]
+        L.orc_bf_or.restype = None
+        for name in ("orc_bf_and_popcount", "orc_bf_or_popcount"):
+            getattr(L, name).argtypes = [vp, vp, u64]
+            getattr(L, name).restype = u64
+        L.orc_bf_popcount.argtypes = [vp, u64]
+        L.orc_bf_popcount.restype = u64
+        _LIB = L
+    return _LIB
+
+
+def _words(num_bits: int) -> int:
+    return (num_bits + 63) // 64
+
+
+def _ptr(a: np.ndarray) -> int:
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+# ------------------------------------------------------------------ C restatement
+
+
+def murmur3_x64_128(data: bytes, seed: int = 0) -> Tuple[int, int]:
+    out = np.zeros(2, dtype=np.uint64)
+    lib().orc_murmur3_x64_128(data, len(data), seed & 0xFFFFFFFF, _ptr(out))
+    return int(out[0]), int(out[1])
+
+
+def kmer_hash(kmer: str, seed: int = 0) -> int:
+    ok = ctypes.c_int(0)
+    h = lib().orc_kmer_hash(kmer.encode(), len(kmer), seed, ctypes.byref(ok))
+    if not ok.value:
+        raise ValueError(f"not an ACGT k-mer of length 1..64: {kmer!r}")
+    return int(h)
+
+
+def makebf(fasta: bytes, k: int, num_bits: int, min_abund: int = 1, seed: int = 0,
+           modulus: int | None = None, rolling: bool = False) -> np.ndarray:
+    """howdesbt makebf --k --min --bits --hashes=1 --seed=seed,0 -> u64 words of the filter."""
+    modulus = num_bits if modulus is None else modulus
+    words = np.zeros(_words(num_bits), dtype=np.uint64)
+    if rolling:
+        if min_abund > 1:
+            raise ValueError("rolling variant is min_abund=1 only")
+        rc = lib().orc_makebf_rolling(fasta, len(fasta), k, seed, modulus, num_bits, _ptr(words))
+    else:
+        rc = lib().orc_makebf(fasta, len(fasta), k, seed, modulus, num_bits, min_abund, _ptr(words))
+    if rc < 0:
+        raise ValueError("invalid makebf arguments")
+    return words
+
+
+def positions_distinct(fasta: bytes, k: int, num_bits: int, seed: int = 0,
+                       modulus: int | None = None) -> np.ndarray:
+    """Sorted distinct hash positions of all k-mers of the file (query --distinctkmers)."""
+    modulus = num_bits if modulus is None else modulus
+    p = ctypes.c_void_p()
+    n = lib().orc_positions_distinct(fasta, len(fasta), k, seed, modulus, num_bits, ctypes.byref(p))
+    if n < 0:
+        raise ValueError("invalid arguments")
+    try:
+        arr = np.ctypeslib.as_array(ctypes.cast(p, ctypes.POINTER(ctypes.c_uint64)), shape=(max(n, 1),))
+        return arr[:n].copy()
+    finally:
+        lib().orc_free(p)
+
+
+def query_hits(positions: np.ndarray, filters: Sequence[np.ndarray]) -> np.ndarray:
+    positions = np.ascontiguousarray(positions, dtype=np.uint64)
+    ptrs = (ctypes.c_void_p * len(filters))(*[_ptr(f) for f in filters])
+    hits = np.zeros(len(filters), dtype=np.uint64)
+    lib().orc_query_hits(_ptr(positions) if len(positions) else None, len(positions),
+                         ctypes.cast(ptrs, ctypes.c_void_p), len(filters), _ptr(hits))
+    return hits
+
+
+def bf_or(filters: Sequence[np.ndarray]) -> np.ndarray:
+    out = np.zeros_like(filters[0])
+    ptrs = (ctypes.c_void_p * len(filters))(*[_ptr(f) for f in filters])
+    lib().orc_bf_or(_ptr(out), ctypes.cast(ptrs, ctypes.c_void_p), len(filters), len(out))
+    return out
+
+
+def bf_popcount(a: np.ndarray) -> int:
+    return int(lib().orc_bf_popcount(_ptr(a), len(a)))
+
+
+def bf_and_popcount(a: np.ndarray, b: np.ndarray) -> int:
+    return int(lib().orc_bf_and_popcount(_ptr(a), _ptr(b), len(a)))
+
+
+def bf_or_popcount(a: np.ndarray, b: np.ndarray) -> int:
+    return int(lib().orc_bf_or_popcount(_ptr(a), _ptr(b), len(a)))
+
+
+# ------------------------------------------------------------------ host formulas (core.py)
+
+
+def ani_distance(intersect: int, union: int, kmer_size: int) -> float:
+    """core.py:1816-1829 (raises ZeroDivisionError when union == 0, like the reference)."""
+    jaccard_index = round(intersect / union, 5)
+    if jaccard_index == 0.0:
+        return 1.0
+    d = 1 - (1 + (1 / kmer_size) * math.log((2 * jaccard_index) / (1 + jaccard_index)))
+    return 1.0 if d > 1.0 else d
+
+
+# ------------------------------------------------------------------ pure-Python twin (tiny cases)
+
+
+def _rotl(x: int, r: int) -> int:
+    return ((x << r) | (x >> (64 - r))) & MASK64
+
+
+def _fmix(k: int) -> int:
+    k ^= k >> 33
+    k = (k * 0xFF51AFD7ED558CCD) & MASK64
+    k ^= k >> 33
+    k = (k * 0xC4CEB9FE1A85EC53) & MASK64
+    k ^= k >> 33
+    return k
+
+
+def py_murmur3_x64_128(data: bytes, seed: int = 0) -> Tuple[int, int]:
+    c1, c2 = 0x87C37B91114253D5, 0x4CF5AD432745937F
+    h1 = h2 = seed & 0xFFFFFFFF
+    n = len(data)
+    nb = n // 16
+    for i in range(nb):
+        k1 = int.from_bytes(data[16 * i:16 * i + 8], "little")
+        k2 = int.from_bytes(data[16 * i + 8:16 * i + 16], "little")
+        k1 = (k1 * c1) & MASK64; k1 = _rotl(k1, 31); k1 = (k1 * c2) & MASK64; h1 ^= k1
+        h1 = _rotl(h1, 27); h1 = (h1 + h2) & MASK64; h1 = (h1 * 5 + 0x52DCE729) & MASK64
+        k2 = (k2 * c2) & MASK64; k2 = _rotl(k2, 33); k2 = (k2 * c1) & MASK64; h2 ^= k2
+        h2 = _rotl(h2, 31); h2 = (h2 + h1) & MASK64; h2 = (h2 * 5 + 0x38495AB5) & MASK64
+    tail = data[16 * nb:]
+    if len(tail) > 8:
+        k2 = int.from_bytes(tail[8:], "little")
+        k2 = (k2 * c2) & MASK64; k2 = _rotl(k2, 33); k2 = (k2 * c1) & MASK64; h2 ^= k2
+    if len(tail) > 0:
+        k1 = int.from_bytes(tail[:8], "little")
+        k1 = (k1 * c1) & MASK64; k1 = _rotl(k1, 31); k1 = (k1 * c2) & MASK64; h1 ^= k1
+    h1 ^= n; h2 ^= n
+    h1 = (h1 + h2) & MASK64; h2 = (h2 + h1) & MASK64
+    h1 = _fmix(h1); h2 = _fmix(h2)
+    h1 = (h1 + h2) & MASK64; h2 = (h2 + h1) & MASK64
+    return h1, h2
+
+
+_CODE = {"A": 0, "C": 1, "G": 2, "T": 3}
+
+
+def py_canonical(kmer: str) -> int:
+    """Smaller of the k-mer and its reverse complement as base-4 integers, first base most significant."""
+    codes = [_CODE[c] for c in kmer.upper()]
+    f = 0
+    for c in codes:
+        f = (f << 2) | c
+    r = 0
+    for c in reversed(codes):
+        r = (r << 2) | (3 - c)
+    return min(f, r)
+
+
+def py_kmer_hash(kmer: str, seed: int = 0) -> int:
+    k = len(kmer)
+    return py_murmur3_x64_128(py_canonical(kmer).to_bytes(16, "little")[: (k + 3) // 4], seed)[0]
+
+
+def py_fasta_records(fasta: bytes) -> List[str]:
+    recs: List[List[str]] = []
+    for line in fasta.decode("latin-1").split("\n"):
+        if line.startswith(">"):
+            recs.append([])
+        else:
+            if not recs:
+                recs.append([])
+            recs[-1].append("".join(line.split()))
+    return ["".join(r) for r in recs]
+
+
+def py_kmers(fasta: bytes, k: int) -> Iterable[str]:
+    for rec in py_fasta_records(fasta):
+        for i in range(len(rec) - k + 1):
+            w = rec[i:i + k].upper()
+            if all(c in _CODE for c in w):
+                yield w
+
+
+def py_makebf(fasta: bytes, k: int, num_bits: int, min_abund: int = 1, seed: int = 0,
+              modulus: int | None = None) -> np.ndarray:
+    modulus = num_bits if modulus is None else modulus
+    counts: dict = {}
+    for w in py_kmers(fasta, k):
+        c = py_canonical(w)
+        counts[c] = counts.get(c, 0) + 1
+    bits = 0
+    for c, n in counts.items():
+        if n >= max(min_abund, 1):
+            pos = py_murmur3_x64_128(c.to_bytes(16, "little")[: (k + 3) // 4], seed)[0] % modulus
+            if pos < num_bits:
+                bits |= 1 << pos
+    nw = _words(num_bits)
+    return np.frombuffer(bits.to_bytes(nw * 8, "little"), dtype=np.uint64).copy()
+
+
+def py_positions_distinct(fasta: bytes, k: int, num_bits: int, seed: int = 0,
+                          modulus: int | None = None) -> np.ndarray:
+    modulus = num_bits if modulus is None else modulus
+    s = set()
+    for w in py_kmers(fasta, k):
+        pos = py_kmer_hash(w, seed) % modulus
+        if pos < num_bits:
+            s.add(pos)
+    return np.array(sorted(s), dtype=np.uint64)
