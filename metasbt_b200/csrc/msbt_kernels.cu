@@ -395,8 +395,18 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
     }
 
     // zero-fill every output filter (the reference always writes a complete new file)
-    for (uint32_t i = 0; i < n_genomes; i++)
-        CU_TRY(ctx, cudaMemsetAsync(d_filters + dg[i].filter_word_off, 0, words * 8, stream));
+    {
+        // one memset per maximal contiguous span of output filters (ascending filter_index, dense stride)
+        std::vector<uint64_t> offs(n_genomes);
+        for (uint32_t i = 0; i < n_genomes; i++) offs[i] = dg[i].filter_word_off;
+        std::sort(offs.begin(), offs.end());
+        for (uint32_t i = 0; i < n_genomes;) {
+            uint32_t j = i + 1;
+            while (j < n_genomes && filter_stride_words == words && offs[j] == offs[j - 1] + words) j++;
+            CU_TRY(ctx, cudaMemsetAsync(d_filters + offs[i], 0, (uint64_t)(j - i) * words * 8, stream));
+            i = j;
+        }
+    }
 
     if (min_abund >= 2) {
         uint64_t n_slots = 1024;

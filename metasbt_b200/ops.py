@@ -111,6 +111,33 @@ class GenomeBatch:
         self.d_words = None
         self.d_runs = None
 
+    @classmethod
+    def from_device_words(cls, words: Sequence[torch.Tensor], n_bases: Sequence[int], device: torch.device,
+                          keep_host_copy: bool = False) -> "GenomeBatch":
+        """Batch of single-run genomes whose packed words already live on the device (synthetic inputs)."""
+        self = cls.__new__(cls)
+        self.n = len(words)
+        descs = (_lib.GenomeDesc * max(self.n, 1))()
+        woff = 0
+        for i, (w, nb) in enumerate(zip(words, n_bases)):
+            descs[i].packed_word_off = woff
+            descs[i].n_bases = nb
+            descs[i].run_off = i
+            descs[i].n_runs = 1 if nb else 0
+            descs[i].filter_index = i
+            woff += w.numel()
+        self.descs = descs
+        self.total_bases = int(sum(n_bases))
+        self.device = device
+        self.d_words = torch.cat(list(words)) if self.n else torch.zeros(1, dtype=torch.int64, device=device)
+        self.d_runs = torch.tensor(list(n_bases) or [0], dtype=torch.int64).to(torch.int32).to(device)
+        self.h_words = self.h_runs = None
+        if keep_host_copy:
+            self.h_words = torch.empty(self.d_words.shape, dtype=torch.int64, pin_memory=True).copy_(self.d_words)
+            self.h_runs = torch.empty(self.d_runs.shape, dtype=torch.int32, pin_memory=True).copy_(self.d_runs)
+        self.h2d_bytes = self.d_words.numel() * 8 + self.d_runs.numel() * 4
+        return self
+
     def to_device(self, non_blocking: bool = True) -> "GenomeBatch":
         self.d_words = self.h_words.to(self.device, non_blocking=non_blocking)
         self.d_runs = self.h_runs.to(self.device, non_blocking=non_blocking)

