@@ -15,6 +15,7 @@
 #include <errno.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <math.h>
 #include <string.h>
 
 #include <algorithm>
@@ -39,6 +40,7 @@ struct msbt_ctx {
     size_t stage_bytes;
     cudaEvent_t stage_free;  // recorded after the last H2D that read h_stage
     bool stage_busy;
+    bool tiled_attr_set;  // dynamic-smem opt-in done for this device
 };
 
 static int fail(msbt_ctx *ctx, int code, const char *fmt, ...) {
@@ -277,12 +279,20 @@ __device__ __forceinline__ uint32_t find_genome(const DevGenome *__restrict__ g,
 
 // Variant 1 ("direct"): filters are zero-filled by a preceding memset; every k-mer issues one
 // RED.OR.b32 straight to its filter word.  One scattered memory operation per k-mer.
-template <int KW>
+#define MSBT_DIRECT_STEP(J)                                                                                  \
+    {                                                                                                        \
+        uint64_t lo_, hi_;                                                                                   \
+        kb.template get<J>(lo_, hi_);                                                                        \
+        const uint64_t pos_ = msbt_position_v<POW2>(msbt_kmer_hash_v<HV>(lo_, hi_, len, spec.pos.seed), spec.pos); \
+        if (((vg >> J) & 1u) && pos_ < spec.pos.num_bits) atomicOr(out + (pos_ >> 5), 1u << (pos_ & 31));    \
+    }
+
+template <int KW, int HV, bool POW2>
 __global__ void __launch_bounds__(TILE_THREADS, 4)
 kmer_bloom_direct_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ run_ends,
                          const DevGenome *__restrict__ genomes, uint32_t n_genomes, uint32_t n_tiles,
                          KmerSpec spec, uint32_t *__restrict__ filters) {
-    const uint32_t k = spec.k;
+    const uint32_t k = spec.k, len = (k + 3) >> 2;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t gi = find_genome(genomes, n_genomes, tile);
         const DevGenome g = genomes[gi];
@@ -291,19 +301,279 @@ kmer_bloom_direct_kernel(const uint64_t *__restrict__ packed, const uint32_t *__
         if (s0 >= g.n_bases) continue;
         const uint32_t vm = valid_mask(run_ends + g.run_off, g.n_runs, s0, k);
         if (vm == 0) continue;
-        KmerWalker<KW> kw;
-        kw.init(packed + g.packed_word_off + w, k);
+        KmerBlock<KW> kb;
+        kb.init(packed + g.packed_word_off + w, k);
         uint32_t *__restrict__ out = filters + 2 * g.filter_word_off;
-#pragma unroll 4
-        for (uint32_t j = 0; j < 32; j++) {
-            if ((vm >> j) & 1) {
-                uint64_t lo, hi;
-                kw.canonical(lo, hi);
-                uint64_t pos = msbt_position(msbt_kmer_hash(lo, hi, k, spec.pos.seed), spec.pos);
-                if (pos < spec.pos.num_bits) atomicOr(out + (pos >> 5), 1u << (pos & 31));
-            }
-            kw.roll(j);
+#pragma unroll 1
+        for (uint32_t grp = 0; grp < 4; grp++) {
+            const uint32_t vg = (vm >> (8 * grp)) & 0xFFu;
+            MSBT_DIRECT_STEP(0) MSBT_DIRECT_STEP(1) MSBT_DIRECT_STEP(2) MSBT_DIRECT_STEP(3)
+            MSBT_DIRECT_STEP(4) MSBT_DIRECT_STEP(5) MSBT_DIRECT_STEP(6) MSBT_DIRECT_STEP(7)
+            kb.advance8();
         }
+    }
+}
+
+// ---- Variant 2 ("tiled"): no memset, no read-modify-write in HBM.
+//   phase 1  kmer_partition_kernel : hash every k-mer, bucket its position by filter range.
+//            Per CTA chunk the buckets are staged in shared memory (one smem atomicAdd per
+//            k-mer), then flushed with one global reservation per (chunk, bucket) and
+//            sector-sized coalesced stores into an L2-resident scratch.
+//   phase 2  tile_build_kernel     : one CTA per 64 KiB filter tile: zero the tile in shared
+//            memory, atomicOr its bucket's positions into it (smem atomics run at ~950 Gop/s
+//            chip-wide, 5x the L2 RED rate -- profiles/r01_microbench_scatter.txt), then write
+//            the finished tile to HBM once with a TMA bulk store (cp.async.bulk).
+//   phase 3  overflow_fixup_kernel : positions that did not fit a staging slot (skewed inputs)
+//            are OR-ed in afterwards with RED; normally a handful per genome.
+// HBM traffic per genome = packed input + filter written once (+ the scratch if it spills L2).
+constexpr int PT_THREADS = 256;
+constexpr int PT_CAP = 16;                  // staged entries per bucket per chunk (expected <= 8)
+constexpr uint32_t PT_MAX_BUCKETS = 1024;   // buckets per filter
+constexpr uint32_t PT_CNT_WORDS = PT_MAX_BUCKETS;
+constexpr size_t PT_SMEM_BYTES = ((size_t)2 * PT_CNT_WORDS + (size_t)(PT_MAX_BUCKETS + 1) * 16) * 4;
+constexpr uint32_t TB_TILE_LOG2 = 19;       // 2^19 bits = 64 KiB per tile, 3 CTAs per SM
+constexpr uint32_t TB_TILE_WORDS32 = 1u << (TB_TILE_LOG2 - 5);
+constexpr int TB_THREADS = 256;
+
+struct TiledParams {
+    uint32_t g0;                  // first genome of the group in the DevGenome table
+    uint32_t n_group;             // genomes in the group
+    uint32_t tile0;               // input-tile index (whole batch) of the group's first chunk
+    uint32_t n_chunks;            // input chunks in the group
+    uint32_t bucket_shift;        // bucket = pos >> bucket_shift  (>= TB_TILE_LOG2)
+    uint32_t buckets_per_filter;  // <= PT_MAX_BUCKETS
+    uint32_t tiles_per_filter;
+    uint32_t gcap;                // scratch entries per bucket
+    uint64_t words;               // u64 words per filter
+    uint64_t ovf_cap;
+};
+
+__device__ __forceinline__ void overflow_push(unsigned long long *ovf_count, uint64_t *ovf, uint64_t cap, uint64_t bit) {
+    unsigned long long i = atomicAdd(ovf_count, 1ull);
+    if (i < cap) ovf[i] = bit;
+}
+
+__device__ __noinline__ void overflow_push_cold(unsigned long long *ovf_count, uint64_t *ovf, uint64_t cap, uint64_t bit) {
+    overflow_push(ovf_count, ovf, cap, bit);
+}
+
+// One k-mer of the unrolled group, split in three sweeps so that the eight hash chains of a group
+// are independent straight-line ALU work (ILP), the eight shared-memory atomics are issued back to
+// back (their latencies overlap), and only then the eight dependent stores.  Positions are 32-bit
+// here (the tiled path requires num_bits <= 2^32).  K-mers that must not be staged (outside a run,
+// or pos >= num_bits) are counted into a dummy bucket NB so that the hot path has no branch.
+#define MSBT_PT_HASH(J)                                                                                      \
+    {                                                                                                        \
+        uint64_t lo_, hi_;                                                                                   \
+        kb.template get<J>(lo_, hi_);                                                                        \
+        const uint64_t p_ = msbt_position_v<POW2>(msbt_kmer_hash_v<HV>(lo_, hi_, len, spec.pos.seed), spec.pos); \
+        pos8[J] = (uint32_t)p_;                                                                              \
+        const bool ok_ = ((vg >> J) & 1u) && (FULL || p_ < spec.pos.num_bits);                               \
+        ok8[J] = ok_;                                                                                        \
+        b8[J] = ok_ ? (pos8[J] >> P.bucket_shift) : NB;                                                      \
+    }
+#define PT_SKIP 0xFFFFFFFFu
+// Predicated shared-memory atomic / store in PTX so that skipped k-mers cost a predicate, not a branch.
+__device__ __forceinline__ uint32_t atoms_inc_if(uint32_t saddr, bool ok) {
+    uint32_t r;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\tmov.u32 %0, 0;\n\t@p atom.shared.add.u32 %0, [%1], 1;\n\t}"
+                 : "=r"(r) : "r"(saddr), "r"((uint32_t)ok) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_if(uint32_t saddr, uint32_t v, bool ok) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p st.shared.u32 [%0], %1;\n\t}" ::"r"(saddr), "r"(v), "r"((uint32_t)ok) : "memory");
+}
+#define MSBT_PT_RANK(J) r8[J] = atoms_inc_if(cnt_s + b8[J] * 4u, ok8[J]);
+#define MSBT_PT_STORE(J)                                                          \
+    sts_if(stage_s + (b8[J] * PT_CAP + r8[J]) * 4u, pos8[J], r8[J] < PT_CAP);     \
+    rmax = max(rmax, r8[J]);
+#define MSBT_PT_OVERFLOW(J) \
+    if (r8[J] >= PT_CAP) overflow_push_cold(ovf_count, ovf, P.ovf_cap, g.filter_word_off * 64 + pos8[J]);
+
+// FULL: modulus <= num_bits, i.e. every position is in range and the `pos < num_bits` test is dropped.
+template <int KW, int HV, bool POW2, bool FULL>
+__global__ void __launch_bounds__(PT_THREADS, 3)
+kmer_partition_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ run_ends,
+                      const DevGenome *__restrict__ genomes, TiledParams P, KmerSpec spec,
+                      uint32_t *__restrict__ gcnt, uint32_t *__restrict__ gbuf,
+                      unsigned long long *__restrict__ ovf_count, uint64_t *__restrict__ ovf) {
+    extern __shared__ __align__(16) uint32_t pt_smem[];
+    const uint32_t NB = P.buckets_per_filter;
+    // fixed layout (compile-time offsets keep the staging address arithmetic to one IMAD):
+    uint32_t *cnt = pt_smem;                    // [NB] entries staged per bucket
+    uint32_t *base = pt_smem + PT_CNT_WORDS;    // [NB] reserved offset in the global bucket
+    uint32_t *stage = pt_smem + 2 * PT_CNT_WORDS;  // [NB + 1][PT_CAP]; row NB is a dummy for skipped k-mers
+    const uint32_t cnt_s = (uint32_t)__cvta_generic_to_shared(cnt);
+    const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+    const uint32_t k = spec.k, len = (k + 3) >> 2;
+    for (uint32_t chunk = blockIdx.x; chunk < P.n_chunks; chunk += gridDim.x) {
+        const uint32_t tile = P.tile0 + chunk;
+        const uint32_t gl = find_genome(genomes + P.g0, P.n_group, tile);
+        const DevGenome g = genomes[P.g0 + gl];
+        for (uint32_t b = threadIdx.x; b < NB; b += PT_THREADS) cnt[b] = 0;
+        __syncthreads();
+        const uint32_t w = (tile - g.tile_begin) * PT_THREADS + threadIdx.x;
+        const uint32_t s0 = w * 32;
+        uint32_t vm = 0;
+        if (s0 < g.n_bases) vm = valid_mask(run_ends + g.run_off, g.n_runs, s0, k);
+        if (vm) {
+            KmerBlock<KW> kb;
+            kb.init(packed + g.packed_word_off + w, k);
+#pragma unroll 1
+            for (uint32_t grp = 0; grp < 4; grp++) {
+                const uint32_t vg = (vm >> (8 * grp)) & 0xFFu;
+                uint32_t pos8[8], b8[8], r8[8];
+                bool ok8[8];
+                MSBT_PT_HASH(0) MSBT_PT_HASH(1) MSBT_PT_HASH(2) MSBT_PT_HASH(3)
+                MSBT_PT_HASH(4) MSBT_PT_HASH(5) MSBT_PT_HASH(6) MSBT_PT_HASH(7)
+                MSBT_PT_RANK(0) MSBT_PT_RANK(1) MSBT_PT_RANK(2) MSBT_PT_RANK(3)
+                MSBT_PT_RANK(4) MSBT_PT_RANK(5) MSBT_PT_RANK(6) MSBT_PT_RANK(7)
+                uint32_t rmax = 0;
+                MSBT_PT_STORE(0) MSBT_PT_STORE(1) MSBT_PT_STORE(2) MSBT_PT_STORE(3)
+                MSBT_PT_STORE(4) MSBT_PT_STORE(5) MSBT_PT_STORE(6) MSBT_PT_STORE(7)
+                if (rmax >= PT_CAP) {  // rare: a staging row is full
+                    MSBT_PT_OVERFLOW(0) MSBT_PT_OVERFLOW(1) MSBT_PT_OVERFLOW(2) MSBT_PT_OVERFLOW(3)
+                    MSBT_PT_OVERFLOW(4) MSBT_PT_OVERFLOW(5) MSBT_PT_OVERFLOW(6) MSBT_PT_OVERFLOW(7)
+                }
+                kb.advance8();
+            }
+        }
+        __syncthreads();
+        // Flush: every (chunk, bucket) reserves a multiple of 4 entries so that the copy is one aligned
+        // 16-byte load + store per quad; the pad slots repeat the bucket's first entry (OR is idempotent).
+        // base[b] = PT_SKIP marks a bucket whose scratch is full: its entries take the overflow path.
+        uint32_t *gc = gcnt + (uint64_t)gl * NB;
+        for (uint32_t b = threadIdx.x; b < NB; b += PT_THREADS) {
+            const uint32_t n = min(cnt[b], (uint32_t)PT_CAP);
+            cnt[b] = n;
+            uint32_t o = 0;
+            if (n) {
+                const uint32_t n4 = (n + 3u) & ~3u;
+                o = atomicAdd(gc + b, n4);
+                o = (o + n4 <= P.gcap) ? b * P.gcap + o : PT_SKIP;
+            }
+            base[b] = o;
+        }
+        __syncthreads();
+        uint4 *gb4 = (uint4 *)(gbuf + (uint64_t)gl * NB * P.gcap);
+        const uint4 *stage4 = (const uint4 *)stage;
+#pragma unroll 4
+        for (uint32_t idx = threadIdx.x; idx < NB * (PT_CAP / 4); idx += PT_THREADS) {
+            const uint32_t b = idx / (PT_CAP / 4), q = idx % (PT_CAP / 4);
+            const uint32_t n = cnt[b];
+            if (q * 4 < n) {
+                uint4 v = stage4[idx];
+                const uint32_t first = stage[b * PT_CAP];
+                const uint32_t have = n - q * 4;  // valid entries in this quad (>= 1)
+                if (have < 2) v.y = first;
+                if (have < 3) v.z = first;
+                if (have < 4) v.w = first;
+                const uint32_t o = base[b];
+                if (o != PT_SKIP) {
+                    gb4[(o >> 2) + q] = v;
+                } else {
+                    const uint64_t fb = g.filter_word_off * 64;
+                    overflow_push_cold(ovf_count, ovf, P.ovf_cap, fb + v.x);
+                    overflow_push_cold(ovf_count, ovf, P.ovf_cap, fb + v.y);
+                    overflow_push_cold(ovf_count, ovf, P.ovf_cap, fb + v.z);
+                    overflow_push_cold(ovf_count, ovf, P.ovf_cap, fb + v.w);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// Work item = one bucket of one filter = TPB consecutive tiles.  The bucket's positions are pulled
+// into registers once (and prefetched for the next bucket while the last store of the current one
+// drains); each tile is then zeroed in shared memory, filled with smem atomicOr and written to HBM
+// with a single TMA bulk store whose completion is only awaited when the buffer is needed again.
+constexpr int TB_REG_ENTRIES = 24;  // positions per thread kept in registers (x256 threads = 6144 per bucket)
+
+__global__ void __launch_bounds__(TB_THREADS, 3)
+tile_build_kernel(const DevGenome *__restrict__ genomes, TiledParams P, const uint32_t *__restrict__ gcnt,
+                  const uint32_t *__restrict__ gbuf, uint64_t *__restrict__ filters) {
+    extern __shared__ __align__(128) uint32_t tb_tile[];
+    const uint32_t NB = P.buckets_per_filter;
+    const uint32_t n_items = P.n_group * NB;
+    const uint32_t tpb_log2 = P.bucket_shift - TB_TILE_LOG2;
+    const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(tb_tile);
+    uint32_t e[TB_REG_ENTRIES];
+    uint32_t n = 0;
+    const uint32_t *src = gbuf;
+    bool store_pending = false;
+
+    uint32_t item = blockIdx.x;
+    if (item < n_items) {
+        n = min(gcnt[item], P.gcap);
+        src = gbuf + (uint64_t)item * P.gcap;
+#pragma unroll
+        for (int u = 0; u < TB_REG_ENTRIES; u++) {
+            const uint32_t i = u * TB_THREADS + threadIdx.x;
+            e[u] = (i < n) ? __ldg(src + i) : 0u;
+        }
+    }
+    for (; item < n_items; item += gridDim.x) {
+        const uint32_t gl = item / NB, b = item % NB;
+        const uint64_t fw = genomes[P.g0 + gl].filter_word_off;
+        for (uint32_t sub = 0; sub < (1u << tpb_log2); sub++) {
+            const uint32_t tf = (b << tpb_log2) + sub;
+            if (tf >= P.tiles_per_filter) break;
+            if (store_pending && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            __syncthreads();
+            uint4 *tv = (uint4 *)tb_tile;
+            for (uint32_t i = threadIdx.x; i < TB_TILE_WORDS32 / 4; i += TB_THREADS) tv[i] = make_uint4(0, 0, 0, 0);
+            __syncthreads();
+#pragma unroll
+            for (int u = 0; u < TB_REG_ENTRIES; u++) {
+                const uint32_t i = u * TB_THREADS + threadIdx.x;
+                if (i < n && (e[u] >> TB_TILE_LOG2) == tf)
+                    atomicOr(tb_tile + ((e[u] & ((1u << TB_TILE_LOG2) - 1)) >> 5), 1u << (e[u] & 31));
+            }
+            for (uint32_t i = TB_REG_ENTRIES * TB_THREADS + threadIdx.x; i < n; i += TB_THREADS) {  // oversized buckets
+                const uint32_t p = __ldg(src + i);
+                if ((p >> TB_TILE_LOG2) == tf) atomicOr(tb_tile + ((p & ((1u << TB_TILE_LOG2) - 1)) >> 5), 1u << (p & 31));
+            }
+            // generic-proxy writes to smem must be visible to the async proxy before the bulk store reads them
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncthreads();
+            const uint64_t w0 = (uint64_t)tf * (TB_TILE_WORDS32 / 2);  // first u64 word of this tile in its filter
+            const uint64_t nw = min((uint64_t)(TB_TILE_WORDS32 / 2), P.words - w0);
+            uint64_t *dst = filters + fw + w0;
+            const uint32_t bytes = (uint32_t)(nw * 8);
+            if (((bytes & 15) == 0) && ((((uintptr_t)dst) & 15) == 0)) {
+                if (threadIdx.x == 0) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(saddr), "r"(bytes) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                store_pending = true;
+            } else {
+                const uint64_t *tw = (const uint64_t *)tb_tile;
+                for (uint64_t i = threadIdx.x; i < nw; i += TB_THREADS) dst[i] = tw[i];
+            }
+        }
+        const uint32_t next = item + gridDim.x;
+        if (next < n_items) {  // prefetch the next bucket while the last store drains
+            n = min(gcnt[next], P.gcap);
+            src = gbuf + (uint64_t)next * P.gcap;
+#pragma unroll
+            for (int u = 0; u < TB_REG_ENTRIES; u++) {
+                const uint32_t i = u * TB_THREADS + threadIdx.x;
+                e[u] = (i < n) ? __ldg(src + i) : 0u;
+            }
+        }
+    }
+    if (store_pending && threadIdx.x == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+overflow_fixup_kernel(const unsigned long long *__restrict__ ovf_count, const uint64_t *__restrict__ ovf, uint64_t cap,
+                      uint32_t *__restrict__ filters32) {
+    const uint64_t n = min((uint64_t)*ovf_count, cap);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t a = ovf[i];
+        atomicOr(filters32 + (a >> 5), 1u << (a & 31));
     }
 }
 
@@ -354,6 +624,158 @@ kmer_count_emit_kernel(const unsigned long long *__restrict__ keys, const uint32
     }
 }
 
+static uint32_t ceil_log2_u64(uint64_t x) {
+    uint32_t l = 0;
+    while ((1ull << l) < x && l < 63) l++;
+    return l;
+}
+
+static int stage_genome_table(msbt_ctx *ctx, const std::vector<DevGenome> &dg, size_t *table_bytes, cudaStream_t stream) {
+    const size_t table_b = align_up(sizeof(DevGenome) * dg.size(), 256);
+    int rc = ensure_scratch(ctx, table_b);
+    if (rc) return rc;
+    rc = stage_begin(ctx, table_b);
+    if (rc) return rc;
+    rc = stage_to_device(ctx, ctx->d_scratch, dg.data(), sizeof(DevGenome) * dg.size(), 0, stream);
+    if (rc) return rc;
+    rc = stage_end(ctx, stream);
+    if (rc) return rc;
+    *table_bytes = table_b;
+    return MSBT_OK;
+}
+
+static int build_tiled(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *d_run_ends,
+                       const std::vector<DevGenome> &dg, uint64_t total_tiles, const KmerSpec &spec, uint64_t words,
+                       uint64_t *d_filters, cudaStream_t stream) {
+    const uint32_t n_genomes = (uint32_t)dg.size();
+    const uint64_t num_bits = spec.pos.num_bits;
+    const uint32_t k = spec.k;
+    // bucket geometry
+    uint32_t bucket_shift = TB_TILE_LOG2;
+    while (((num_bits + (1ull << bucket_shift) - 1) >> bucket_shift) > PT_MAX_BUCKETS) bucket_shift++;
+    const uint32_t NB = (uint32_t)((num_bits + (1ull << bucket_shift) - 1) >> bucket_shift);
+    const uint32_t TPF = (uint32_t)((num_bits + (1ull << TB_TILE_LOG2) - 1) >> TB_TILE_LOG2);
+    (void)ceil_log2_u64;
+
+    auto kmers_of = [&](const DevGenome &g) -> uint64_t { return g.n_bases >= k ? (uint64_t)g.n_bases - k + 1 : 0; };
+    auto gcap_for = [&](uint64_t max_kmers) -> uint64_t {
+        // positions are uniform over [0, modulus): expected entries per bucket, plus 8 sigma and slack
+        const double frac = std::min(1.0, (double)(1ull << bucket_shift) / (double)spec.pos.modulus);
+        const double e = (double)max_kmers * frac;
+        // each chunk that touches a bucket may add up to 3 pad entries (expected 1.5)
+        const double chunks = (double)((max_kmers + TILE_BASES - 1) / TILE_BASES);
+        const double touched = chunks * std::min(1.0, (double)TILE_BASES * frac);
+        uint64_t cap = (uint64_t)(e + 8.0 * sqrt(e) + 2.0 * touched + 64.0);
+        cap = std::min<uint64_t>(cap, max_kmers + 3 * (uint64_t)chunks + 8);
+        return (cap + 7) / 8 * 8;
+    };
+
+    // groups of consecutive genomes whose bucket scratch stays around 64 MB (L2-resident)
+    const uint64_t SCRATCH_TARGET = 64ull << 20;
+    struct Group { uint32_t g0, n; uint64_t gcap, kmers; };
+    std::vector<Group> groups;
+    uint64_t max_gbuf = 0, max_kmers_group = 0, max_gcnt = 0;
+    for (uint32_t i = 0; i < n_genomes;) {
+        uint32_t j = i;
+        uint64_t mk = 0, sum_k = 0;
+        while (j < n_genomes) {
+            const uint64_t mk2 = std::max(mk, kmers_of(dg[j]));
+            const uint64_t need = (uint64_t)(j - i + 1) * NB * gcap_for(mk2) * 4;
+            if (j > i && need > SCRATCH_TARGET) break;
+            if ((uint64_t)(j - i + 1) * TPF > (1u << 30)) break;
+            mk = mk2;
+            sum_k += kmers_of(dg[j]);
+            j++;
+        }
+        Group gr{i, j - i, gcap_for(mk), sum_k};
+        if (((uint64_t)NB * gr.gcap) >> 32) return 1;  // not applicable: caller falls back to the direct variant
+        groups.push_back(gr);
+        max_gbuf = std::max(max_gbuf, (uint64_t)gr.n * NB * gr.gcap * 4);
+        max_gcnt = std::max(max_gcnt, (uint64_t)gr.n * NB * 4);
+        max_kmers_group = std::max(max_kmers_group, sum_k);
+        i = j;
+    }
+
+    size_t table_b = 0;
+    // scratch layout: [genome table][ovf_count (256 B)][gcnt][gbuf][ovf list]
+    const size_t t_b = align_up(sizeof(DevGenome) * n_genomes, 256);
+    const size_t cnt_off = t_b, gcnt_off = cnt_off + 256;
+    const size_t gbuf_off = align_up(gcnt_off + max_gcnt, 256);
+    const size_t ovf_off = align_up(gbuf_off + max_gbuf, 256);
+    const size_t total = ovf_off + max_kmers_group * 8 + 256;
+    int rc = ensure_scratch(ctx, total);
+    if (rc) return rc;
+    rc = stage_genome_table(ctx, dg, &table_b, stream);
+    if (rc) return rc;
+    char *S = (char *)ctx->d_scratch;
+    const DevGenome *d_genomes = (const DevGenome *)S;
+    unsigned long long *ovf_count = (unsigned long long *)(S + cnt_off);
+    uint32_t *gcnt = (uint32_t *)(S + gcnt_off);
+    uint32_t *gbuf = (uint32_t *)(S + gbuf_off);
+    uint64_t *ovf = (uint64_t *)(S + ovf_off);
+
+    const size_t pt_smem = PT_SMEM_BYTES;
+    static_assert(PT_CAP == 16, "PT_SMEM_BYTES assumes 16 staging slots");
+    const size_t tb_smem = (size_t)TB_TILE_WORDS32 * 4;
+    if (!ctx->tiled_attr_set) {
+        const int pt_max = (int)PT_SMEM_BYTES;
+#define MSBT_PT_ATTR(KW, HV) \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_partition_kernel<KW, HV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pt_max)); \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_partition_kernel<KW, HV, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pt_max)); \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_partition_kernel<KW, HV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, pt_max)); \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_partition_kernel<KW, HV, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, pt_max));
+        MSBT_PT_ATTR(1, 0) MSBT_PT_ATTR(2, 1) MSBT_PT_ATTR(2, 2)
+#undef MSBT_PT_ATTR
+        CU_TRY(ctx, cudaFuncSetAttribute(tile_build_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb_smem));
+        ctx->tiled_attr_set = true;
+    }
+    (void)total_tiles;
+    for (const Group &gr : groups) {
+        TiledParams P;
+        P.g0 = gr.g0;
+        P.n_group = gr.n;
+        P.tile0 = dg[gr.g0].tile_begin;
+        const DevGenome &last = dg[gr.g0 + gr.n - 1];
+        P.n_chunks = last.tile_begin + (uint32_t)(((uint64_t)last.n_bases + TILE_BASES - 1) / TILE_BASES) - P.tile0;
+        P.bucket_shift = bucket_shift;
+        P.buckets_per_filter = NB;
+        P.tiles_per_filter = TPF;
+        P.gcap = (uint32_t)gr.gcap;
+        P.words = words;
+        P.ovf_cap = max_kmers_group;
+        // ovf_count and gcnt are adjacent: one memset clears both
+        CU_TRY(ctx, cudaMemsetAsync(S + cnt_off, 0, 256 + (size_t)gr.n * NB * 4, stream));
+        if (P.n_chunks) {
+            const int grid = (int)std::min<uint64_t>(P.n_chunks, (uint64_t)ctx->num_sms * 3);
+#define MSBT_PT_LAUNCH(KW, HV)                                                                                         \
+    {                                                                                                                  \
+        if (p2 && full) kmer_partition_kernel<KW, HV, true, true><<<grid, PT_THREADS, pt_smem, stream>>>(d_packed, d_run_ends, d_genomes, P, spec, gcnt, gbuf, ovf_count, ovf); \
+        else if (p2) kmer_partition_kernel<KW, HV, true, false><<<grid, PT_THREADS, pt_smem, stream>>>(d_packed, d_run_ends, d_genomes, P, spec, gcnt, gbuf, ovf_count, ovf); \
+        else if (full) kmer_partition_kernel<KW, HV, false, true><<<grid, PT_THREADS, pt_smem, stream>>>(d_packed, d_run_ends, d_genomes, P, spec, gcnt, gbuf, ovf_count, ovf); \
+        else kmer_partition_kernel<KW, HV, false, false><<<grid, PT_THREADS, pt_smem, stream>>>(d_packed, d_run_ends, d_genomes, P, spec, gcnt, gbuf, ovf_count, ovf); \
+    }
+            const int hv = msbt_hash_variant(k);
+            const bool p2 = spec.pos.pow2 != 0, full = spec.pos.modulus <= spec.pos.num_bits;
+            if (hv == 0) MSBT_PT_LAUNCH(1, 0)
+            else if (hv == 1) MSBT_PT_LAUNCH(2, 1)
+            else MSBT_PT_LAUNCH(2, 2)
+#undef MSBT_PT_LAUNCH
+            LAUNCH_CHECK(ctx);
+        }
+        {
+            const uint64_t n_items = (uint64_t)gr.n * NB;
+            const int grid = (int)std::min<uint64_t>(n_items, (uint64_t)ctx->num_sms * 3);
+            tile_build_kernel<<<grid, TB_THREADS, tb_smem, stream>>>(d_genomes, P, gcnt, gbuf, d_filters);
+            LAUNCH_CHECK(ctx);
+        }
+        if (P.n_chunks) {
+            overflow_fixup_kernel<<<ctx->num_sms, 256, 0, stream>>>(ovf_count, ovf, P.ovf_cap, (uint32_t *)d_filters);
+            LAUNCH_CHECK(ctx);
+        }
+    }
+    return MSBT_OK;
+}
+
 extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *d_run_ends,
                                      const msbt_genome_desc *h_descs, uint32_t n_genomes, uint32_t k,
                                      uint64_t seed, uint64_t modulus, uint64_t num_bits, uint32_t min_abund,
@@ -392,6 +814,24 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
         tiles += (d.n_bases + TILE_BASES - 1) / TILE_BASES;
         max_bases = std::max<uint64_t>(max_bases, d.n_bases);
         if (tiles >> 31) return fail(ctx, MSBT_EINVAL, "batch too large (%llu tiles)", (unsigned long long)tiles);
+    }
+
+    // variant choice: the tiled path needs distinct output filters and u32 positions
+    bool distinct = true;
+    {
+        std::vector<uint64_t> offs(n_genomes);
+        for (uint32_t i = 0; i < n_genomes; i++) offs[i] = dg[i].filter_word_off;
+        std::sort(offs.begin(), offs.end());
+        for (uint32_t i = 1; i < n_genomes; i++) distinct = distinct && offs[i] != offs[i - 1];
+    }
+    const bool tiled_ok = distinct && min_abund <= 1 && num_bits <= (1ull << 32);
+    if (variant == 2 && !tiled_ok)
+        return fail(ctx, MSBT_EINVAL, "variant 2 needs distinct filter_index values, min_abund <= 1 and num_bits <= 2^32");
+    const bool tiled = tiled_ok && (variant == 2 || (variant == 0 && num_bits >= (1ull << TB_TILE_LOG2)));
+    if (tiled) {
+        const int rc = build_tiled(ctx, d_packed, d_run_ends, dg, tiles, spec, words, d_filters, stream);
+        if (rc <= 0) return rc;
+        if (variant == 2) return fail(ctx, MSBT_EINVAL, "variant 2: bucket scratch exceeds 2^32 entries per filter");
     }
 
     // zero-fill every output filter (the reference always writes a complete new file)
@@ -446,12 +886,17 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
     if (rc) return rc;
 
     int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * 8);
-    if (k <= 32)
-        kmer_bloom_direct_kernel<1><<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, (const DevGenome *)ctx->d_scratch,
-                                                                     n_genomes, (uint32_t)tiles, spec, (uint32_t *)d_filters);
-    else
-        kmer_bloom_direct_kernel<2><<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, (const DevGenome *)ctx->d_scratch,
-                                                                     n_genomes, (uint32_t)tiles, spec, (uint32_t *)d_filters);
+#define MSBT_DIRECT_LAUNCH(KW, HV, P2)                                                                                   \
+    kmer_bloom_direct_kernel<KW, HV, P2><<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, (const DevGenome *)ctx->d_scratch, \
+                                                                           n_genomes, (uint32_t)tiles, spec, (uint32_t *)d_filters)
+    {
+        const int hv = msbt_hash_variant(k);
+        const bool p2 = spec.pos.pow2 != 0;
+        if (hv == 0) { if (p2) MSBT_DIRECT_LAUNCH(1, 0, true); else MSBT_DIRECT_LAUNCH(1, 0, false); }
+        else if (hv == 1) { if (p2) MSBT_DIRECT_LAUNCH(2, 1, true); else MSBT_DIRECT_LAUNCH(2, 1, false); }
+        else { if (p2) MSBT_DIRECT_LAUNCH(2, 2, true); else MSBT_DIRECT_LAUNCH(2, 2, false); }
+    }
+#undef MSBT_DIRECT_LAUNCH
     LAUNCH_CHECK(ctx);
     return MSBT_OK;
 }

@@ -25,16 +25,42 @@ def build(ctx, fastas, k, num_bits, min_abund=1, modulus=None, variant=0):
     return out, [to_np(out[i, :w]) for i in range(len(fastas))]
 
 
+@pytest.mark.parametrize("variant", [1, 2])
 @pytest.mark.parametrize("k", [1, 9, 21, 31, 32, 33, 51, 64])
-def test_makebf_messy_batches(ctx, oracle, k):
+def test_makebf_messy_batches(ctx, oracle, k, variant):
     rng = random.Random(k)
     fastas = [util.messy_fasta(rng, rng.randint(1, 6), rng.choice([10, 300, 5000]), rng.choice(["ACGT", "ACGTN", "ACGTacgtNnRY"]))
               for _ in range(9)]
     fastas += [b"", b">empty\n", b">short\nACG\n"]
     for num_bits, modulus in ((1 << 16, None), (100003, None), (1 << 14, 20011), (20011, 1 << 14)):
-        _, got = build(ctx, fastas, k, num_bits, modulus=modulus)
+        _, got = build(ctx, fastas, k, num_bits, modulus=modulus, variant=variant)
         for f, g in zip(fastas, got):
             assert np.array_equal(g, oracle.makebf(f, k, num_bits, 1, 0, modulus))
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("num_bits", [64, 1000, (1 << 19) - 64, 1 << 19, (1 << 19) + 64, (1 << 21) + 192, 3 * (1 << 20) + 8])
+def test_makebf_filter_sizes_and_tile_edges(ctx, oracle, num_bits, variant):
+    """Filter sizes around the 64 KiB tile boundary, odd word counts, tiny filters."""
+    rng = random.Random(num_bits)
+    fastas = [util.messy_fasta(rng, 3, 4000, "ACGTN") for _ in range(5)]
+    _, got = build(ctx, fastas, 21, num_bits, variant=variant)
+    for f, g in zip(fastas, got):
+        assert np.array_equal(g, oracle.makebf(f, 21, num_bits))
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_makebf_skewed_inputs_overflow_path(ctx, oracle, variant):
+    """Low-complexity genomes put (almost) every k-mer into a few buckets: the staging slots and the
+    scratch buckets overflow and the fix-up pass must restore every bit."""
+    k, num_bits = 15, 1 << 22
+    fastas = [b">polyA\n" + b"A" * 200000 + b"\n",
+              b">repeat\n" + b"ACGTTGCA" * 40000 + b"\n",
+              util.codes_to_fasta(util.synthetic_codes(3, 150000), "rand"),
+              b">mix\n" + b"AC" * 50000 + util.codes_to_fasta(util.synthetic_codes(4, 50000), "x").split(b"\n", 1)[1]]
+    _, got = build(ctx, fastas, k, num_bits, variant=variant)
+    for f, g in zip(fastas, got):
+        assert np.array_equal(g, oracle.makebf(f, k, num_bits, rolling=True))
 
 
 @pytest.mark.parametrize("k,min_abund", [(9, 2), (21, 2), (31, 3), (32, 2)])
@@ -52,14 +78,15 @@ def test_makebf_min_abundance_k_gt_32_rejected(ctx):
         build(ctx, [b">r\n" + b"ACGT" * 50 + b"\n"], 33, 1 << 12, min_abund=2)
 
 
-@pytest.mark.parametrize("k,num_bits", [(31, 1 << 22), (21, 1 << 24), (51, 1 << 22)])
-def test_makebf_synthetic_genomes(ctx, oracle, k, num_bits):
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("k,num_bits", [(31, 1 << 22), (21, 1 << 24), (51, 1 << 22), (31, 1 << 27)])
+def test_makebf_synthetic_genomes(ctx, oracle, k, num_bits, variant):
     from metasbt_b200 import ops
     n = 300_000
     codes = [util.synthetic_codes(0x5EED0000 + g, n + 1000 * g) for g in range(4)]
     packed = [ops.pack_codes(c) for c in codes]
     batch = ops.GenomeBatch(packed, ctx.device)
-    out = ctx.build_filters(batch, k, num_bits)
+    out = ctx.build_filters(batch, k, num_bits, variant=variant)
     torch.cuda.synchronize()
     w = ops.filter_words(num_bits)
     for g, c in enumerate(codes):
@@ -69,7 +96,8 @@ def test_makebf_synthetic_genomes(ctx, oracle, k, num_bits):
         assert np.array_equal(ops.pack_fasta(fa, k).words, packed[g].words)
 
 
-def test_makebf_filter_index_and_rebuild(ctx, oracle):
+@pytest.mark.parametrize("variant", [1, 2])
+def test_makebf_filter_index_and_rebuild(ctx, oracle, variant):
     """Filters are fully rewritten (stale bits cleared) and filter_index routes outputs."""
     from metasbt_b200 import ops
     k, num_bits = 15, 1 << 14
@@ -78,7 +106,7 @@ def test_makebf_filter_index_and_rebuild(ctx, oracle):
     packed = [ops.pack_fasta(f, k) for f in fastas]
     out = torch.full((5, ops.filter_stride_words(num_bits)), -1, dtype=torch.int64, device=ctx.device)
     batch = ops.GenomeBatch(packed, ctx.device, filter_indices=[4, 0, 2])
-    ctx.build_filters(batch, k, num_bits, out=out)
+    ctx.build_filters(batch, k, num_bits, out=out, variant=variant)
     torch.cuda.synchronize()
     w = ops.filter_words(num_bits)
     for f, idx in zip(fastas, [4, 0, 2]):

@@ -31,7 +31,7 @@ def emu(built):
         subprocess.check_call(["g++", "-O2", "-Wall", "-shared", "-fPIC", "-o", so, src])
     L = ctypes.CDLL(so)
     L.emu_makebf.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
-                             ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p]
+                             ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int]
     L.emu_makebf.restype = ctypes.c_int
     return L
 
@@ -105,19 +105,20 @@ def test_fasta_pack_errors(built):
     assert L.msbt_fasta_pack(text, len(text), 4, words.ctypes.data, 1, ends.ctypes.data, 1, ctypes.byref(nb), ctypes.byref(nr)) == built.MSBT_ENOSPC
 
 
-@pytest.mark.parametrize("k", [1, 2, 9, 16, 21, 31, 32, 33, 34, 51, 63, 64])
-def test_device_kmer_code_on_host_matches_oracle(emu, oracle, k):
+@pytest.mark.parametrize("impl", [0, 1], ids=["walker", "block"])
+@pytest.mark.parametrize("k", [1, 2, 9, 16, 21, 31, 32, 33, 34, 51, 60, 61, 63, 64])
+def test_device_kmer_code_on_host_matches_oracle(emu, oracle, k, impl):
     """The per-thread code the kernels run (walker, run mask, hash, modulus) == oracle makebf."""
     from metasbt_b200 import ops
     rng = random.Random(1000 + k)
     for trial in range(12):
         fa = util.messy_fasta(rng, rng.randint(1, 5), rng.choice([10, 100, 700, 3000]), rng.choice(["ACGT", "ACGTN", "ACGTacgtNnRY"]))
-        num_bits = rng.choice([64, 1000, 4096, 12345, (1 << 16) + 3])
+        num_bits = rng.choice([64, 1000, 4096, 12345, (1 << 16), (1 << 16) + 3])
         modulus = rng.choice([num_bits, num_bits, num_bits + 17, max(1, num_bits - 5)])
         pg = ops.pack_fasta(fa, k)
         w = np.zeros((num_bits + 63) // 64, dtype=np.uint64)
         ends = pg.run_ends if len(pg.run_ends) else np.zeros(1, dtype=np.uint32)
-        assert emu.emu_makebf(pg.words.ctypes.data, ends.ctypes.data, len(pg.run_ends), pg.n_bases, k, 0, modulus, num_bits, w.ctypes.data) == 0
+        assert emu.emu_makebf(pg.words.ctypes.data, ends.ctypes.data, len(pg.run_ends), pg.n_bases, k, 0, modulus, num_bits, w.ctypes.data, impl) == 0
         assert np.array_equal(w, oracle.makebf(fa, k, num_bits, 1, 0, modulus))
 
 
