@@ -1,0 +1,159 @@
+"""File-level operators: the five `howdesbt` subcommands MetaSBT spawns, as in-process batch calls
+over HBM-resident filters.  core.py talks to this interface only.
+
+    makebf      -> CudaBackend.sketch_many      (core.py:3920-3931)
+    bfoperate   -> CudaBackend.union            (core.py:3851-3857)
+    dumpbf      -> CudaBackend.popcounts        (core.py:3588-3593)
+    bfdistance  -> CudaBackend.dist_one_vs_many / dist_all_pairs   (core.py:1747-1774, 4036-4081)
+    query       -> CudaBackend.query_many       (core.py:2039-2047)
+
+Filters are cached on the device by absolute path (LRU, bounded in bytes), so that the repeated
+reads the reference pays per spawn (every `bfdistance`/`query` call re-reads every listed file)
+happen once.  `.bf` files stay the persistent store and are byte-compatible (bffile.py).
+There is no CPU implementation here: without libmsbt.so and a CUDA device, construction fails.
+"""
+
+from __future__ import annotations
+
+import os
+from collections import OrderedDict
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import bffile, ops
+
+
+def read_fasta_bytes(path: str) -> bytes:
+    with open(path, "rb") as f:
+        return f.read()
+
+
+class CudaBackend:
+    def __init__(self, kmer_size: int, num_bits: int, device: Optional[int] = None,
+                 cache_bytes: int = 96 << 30, sketch_batch_bytes: int = 16 << 30):
+        self.k = int(kmer_size)
+        self.num_bits = int(num_bits)
+        self.ctx = ops.default_context(device)
+        self.words = ops.filter_words(self.num_bits)
+        self.stride = ops.filter_stride_words(self.num_bits)
+        self.cache_bytes = cache_bytes
+        self.sketch_batch = max(1, sketch_batch_bytes // (self.stride * 8))
+        self._cache: "OrderedDict[str, torch.Tensor]" = OrderedDict()
+        self._bytes = 0
+
+    # ------------------------------------------------------------------ device filter cache
+    def _put(self, path: str, t: torch.Tensor) -> None:
+        path = os.path.abspath(path)
+        if path in self._cache:
+            self._bytes -= self._cache.pop(path).numel() * 8
+        self._cache[path] = t
+        self._bytes += t.numel() * 8
+        while self._bytes > self.cache_bytes and len(self._cache) > 1:
+            _, old = self._cache.popitem(last=False)
+            self._bytes -= old.numel() * 8
+
+    def forget(self, path: str) -> None:
+        t = self._cache.pop(os.path.abspath(path), None)
+        if t is not None:
+            self._bytes -= t.numel() * 8
+
+    def filter(self, path: str) -> torch.Tensor:
+        """Device tensor (int64[stride]) of the filter stored at `path` (cached)."""
+        path = os.path.abspath(path)
+        t = self._cache.get(path)
+        if t is not None:
+            self._cache.move_to_end(path)
+            return t
+        header, words = bffile.read_bf(path)
+        if header.num_bits != self.num_bits or header.kmer_size != self.k:
+            raise ValueError(f"{path}: filter has k={header.kmer_size}, bits={header.num_bits}; "
+                             f"database uses k={self.k}, bits={self.num_bits}")
+        host = torch.zeros(self.stride, dtype=torch.int64)
+        host.numpy().view(np.uint64)[: self.words] = words
+        t = host.to(self.ctx.device)
+        self._put(path, t)
+        return t
+
+    def _write(self, path: str, t: torch.Tensor) -> None:
+        header = bffile.BloomHeader(kmer_size=self.k, num_bits=self.num_bits)
+        bffile.write_bf(path, header, t[: self.words].cpu().numpy().view(np.uint64))
+
+    # ------------------------------------------------------------------ makebf
+    def sketch_many(self, fasta_paths: Sequence[str], out_paths: Sequence[str], min_abund: int) -> None:
+        """howdesbt makebf --k --min --bits --hashes=1 --seed=0,0 <fasta> --out=<bf> for every pair."""
+        for lo in range(0, len(fasta_paths), self.sketch_batch):
+            fa = fasta_paths[lo: lo + self.sketch_batch]
+            packed = [ops.pack_fasta(read_fasta_bytes(p), self.k) for p in fa]
+            batch = ops.GenomeBatch(packed, self.ctx.device)
+            filt = self.ctx.build_filters(batch, self.k, self.num_bits, min_abund=min_abund)
+            for i, out in enumerate(out_paths[lo: lo + self.sketch_batch]):
+                row = filt[i].clone()
+                self._write(out, row)
+                self._put(out, row)
+
+    def sketch_resident(self, fasta_paths: Sequence[str], min_abund: int = 1) -> torch.Tensor:
+        """Filters of the given FASTA files left on the device only (query side of `profile`)."""
+        packed = [ops.pack_fasta(read_fasta_bytes(p), self.k) for p in fasta_paths]
+        batch = ops.GenomeBatch(packed, self.ctx.device)
+        return self.ctx.build_filters(batch, self.k, self.num_bits, min_abund=min_abund)
+
+    # ------------------------------------------------------------------ bfoperate --or
+    def union(self, src_paths: Sequence[str], out_path: str) -> None:
+        rows = [self.filter(p) for p in src_paths]
+        out = self.ctx.bf_or(rows, self.num_bits)
+        if self.stride > self.words:
+            out[self.words:] = 0
+        self._write(out_path, out)
+        self._put(out_path, out)
+
+    def copy(self, src_path: str, out_path: str) -> None:
+        t = self.filter(src_path).clone()
+        self._write(out_path, t)
+        self._put(out_path, t)
+
+    # ------------------------------------------------------------------ dumpbf --show:density
+    def popcounts(self, paths: Sequence[str]) -> List[int]:
+        if not paths:
+            return []
+        rows = [self.filter(p) for p in paths]
+        return [int(x) for x in self.ctx.bf_popcount(rows, self.num_bits).cpu()]
+
+    # ------------------------------------------------------------------ bfdistance
+    def dist_one_vs_many(self, focus_path: str, target_paths: Sequence[str]) -> List[Tuple[int, int]]:
+        """[(intersection, union)] of the focus against every target, in target order."""
+        if not target_paths:
+            return []
+        inter, union = self.ctx.bf_dist(self.filter(focus_path), [self.filter(p) for p in target_paths], self.num_bits)
+        i, u = inter.cpu().tolist(), union.cpu().tolist()
+        return list(zip(i, u))
+
+    def dist_all_pairs(self, paths: Sequence[str]) -> np.ndarray:
+        """Dense intersection matrix; diagonal = popcounts (union_ij = I_ii + I_jj - I_ij)."""
+        rows = [self.filter(p) for p in paths]
+        return self.ctx.bf_allpairs(rows, self.num_bits).cpu().numpy()
+
+    # ------------------------------------------------------------------ query --distinctkmers
+    def query_positions(self, fasta_path: str) -> torch.Tensor:
+        """Distinct hash positions of ALL k-mers of the file (no min filter), ascending, on the device.
+        They are the set bits of the file's own min=1 filter (App. A6), so: K1 + ordered extraction."""
+        q = self.sketch_resident([fasta_path], min_abund=1)
+        return self.ctx.extract_positions(q[0], self.num_bits)
+
+    def query_hits(self, positions: torch.Tensor, leaf_paths: Sequence[str]) -> Tuple[List[int], int]:
+        """(hits per leaf, total) for one query against the leaves of a flat tree."""
+        total = int(positions.numel())
+        if not leaf_paths:
+            return [], total
+        leaves = [self.filter(p) for p in leaf_paths]
+        hits = self.ctx.query_batch(leaves, [positions])
+        return [int(x) for x in hits[0].cpu()], total
+
+    def query_many(self, query_filters: Sequence[torch.Tensor], leaf_paths: Sequence[str]):
+        """hits[q][l] and totals[q] for device-resident query filters against the given leaves."""
+        leaves = [self.filter(p) for p in leaf_paths]
+        positions = [self.ctx.extract_positions(q, self.num_bits) for q in query_filters]
+        hits = self.ctx.query_batch(leaves, positions)
+        totals = [int(p.numel()) for p in positions]
+        return hits.cpu().numpy(), totals

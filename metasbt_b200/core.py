@@ -1,0 +1,775 @@
+"""Database / Entry: the `metasbt.core` API surface that sits on the hot path, re-implemented over
+in-process GPU operators (backend.CudaBackend -> libmsbt.so) instead of `howdesbt` subprocesses.
+
+Scope: what `metasbt index` and `metasbt profile` reach -- Database.{set_configs, add,
+update, dist, profile}, Entry.{sketch, index, get_density, get_boundaries, get_children,
+get_full_taxonomy, is_known, add_children} -- with the same signatures, exceptions, on-disk layout
+and result files (`clusters.tsv`, `genomes.tsv`, `metadata.json`, `<name>.txt`,
+`tree/index.detbrief.sbt`, `tmp/profiles/<genome>.txt`) as /root/reference/metasbt/core.py.
+Out of scope and raising NotImplementedError: kitsune/ntcard estimation (pass --kmer-size and
+--filter-size), flat=False trees (howdesbt cluster/build), qc/dereplicate/characterize/merge/remove.
+
+Differences that are deliberate (documented in DESIGN.md):
+* process fan-outs (mp.Pool over dist/_profile, core.py:4036, metasbt.py:1124) are batch calls;
+* wherever the reference iterates a Python `set` (order depends on PYTHONHASHSEED: core.py:3746,
+  3979; metasbt.py:509) this code iterates in sorted order, so runs are reproducible;
+* Entry.get_boundaries uses Database.tmp in the single-process branch (the reference passes the
+  non-existent `self.tmp`, core.py:4072, and would raise AttributeError).
+"""
+
+from __future__ import annotations
+
+import datetime
+import errno
+import json
+import math
+import os
+import random
+import re
+import shutil
+import statistics
+import sys
+from collections import OrderedDict
+from pathlib import Path
+from typing import Any, Dict, Iterable, List, Optional, Sequence, Set, Tuple
+
+__version__ = "0.1.5-b200"
+
+LEVELS = ["kingdom", "phylum", "class", "order", "family", "genus", "species"]
+_MSBT_ID = re.compile(r"^MSBT[0-9]*$")
+
+# backends shared by the static Database.dist (keyed by (kmer_size, num_bits))
+_BACKENDS: Dict[Tuple[int, int], Any] = {}
+
+
+def get_backend(kmer_size: int, num_bits: int):
+    key = (int(kmer_size), int(num_bits))
+    if key not in _BACKENDS:
+        from .backend import CudaBackend  # fails loudly without libmsbt.so / a CUDA device
+        _BACKENDS[key] = CudaBackend(*key)
+    return _BACKENDS[key]
+
+
+def register_backend(kmer_size: int, num_bits: int, backend) -> None:
+    """Install a backend instance for (k, bits) -- used by tests to inject a checker backend."""
+    _BACKENDS[(int(kmer_size), int(num_bits))] = backend
+
+
+def ani_distance(intersect: int, union: int, kmer_size: int) -> float:
+    """Jaccard (rounded to 5 decimals) -> ANI distance, exactly as core.py:1816-1829."""
+    jaccard_index = round(intersect / union, 5)
+    if jaccard_index == 0.0:
+        return 1.0
+    ani = 1 - (1 + (1 / kmer_size) * math.log((2 * jaccard_index) / (1 + jaccard_index)))
+    return 1.0 if ani > 1.0 else ani
+
+
+class Database(object):
+    """Database object (reference: core.py:44-3341)."""
+
+    LEVELS = LEVELS
+
+    def __init__(self, name: str, folder: str, tmp: str, flat: bool = True, nproc: int = os.cpu_count(), backend=None):
+        self.version = __version__
+        if not name:
+            raise ValueError("Invalid Database name!")
+        if not folder:
+            raise ValueError("Invalid Database path!")
+        self.name = name
+        self.root = folder
+        os.makedirs(tmp, exist_ok=True)
+        self.tmp = tmp
+        self.nproc = nproc
+        if self.nproc is None or self.nproc < 1 or self.nproc > os.cpu_count():
+            self.nproc = os.cpu_count()
+        self._backend = backend
+        self._touched: List[str] = list()       # taxonomies created or modified by add() (reference: __clusters)
+        self._unknowns: List["Entry"] = list()
+        self.clusters: Dict[str, Dict[str, "Entry"]] = {level: OrderedDict() for level in LEVELS}
+        self.genomes: Dict[str, "Entry"] = OrderedDict()
+
+        if not os.path.isdir(self.root):
+            # new database (core.py:134-158)
+            if not flat:
+                raise NotImplementedError("flat=False (howdesbt cluster/build trees) is outside the B200 hot path")
+            self.flat = flat
+            os.makedirs(self.root)
+            os.makedirs(os.path.join(self.root, "clusters"))
+            os.makedirs(os.path.join(self.root, "sketches"))
+            self.metadata: Dict[str, Any] = dict()
+            self.metadata["clusters_count"] = 0
+            self.metadata["flat"] = self.flat
+            self.report: Dict[str, Any] = dict()
+        else:
+            # existing database (core.py:160-250)
+            clusters_folder = os.path.join(self.root, "clusters")
+            if not os.path.isdir(clusters_folder):
+                raise FileNotFoundError(errno.ENOENT, os.strerror(errno.ENOENT), clusters_folder)
+            sketches_folder = os.path.join(self.root, "sketches")
+            if not os.path.isdir(sketches_folder):
+                raise FileNotFoundError(errno.ENOENT, os.strerror(errno.ENOENT), sketches_folder)
+            metadata_json_filepath = os.path.join(self.root, "metadata.json")
+            if not os.path.isfile(metadata_json_filepath):
+                raise FileNotFoundError(errno.ENOENT, os.strerror(errno.ENOENT), metadata_json_filepath)
+            with open(metadata_json_filepath) as metadata_json_file:
+                self.metadata = json.loads("".join(metadata_json_file.readlines()))
+            if not self._validate_metadata(self.metadata):
+                raise Exception("Database metadata did not pass the validation!")
+            self.flat = self.metadata["flat"]
+            if not self.flat:
+                raise NotImplementedError("flat=False databases are outside the B200 hot path")
+            report_filepath = os.path.join(self.root, "clusters.tsv")
+            if not os.path.isfile(report_filepath):
+                raise FileNotFoundError(errno.ENOENT, os.strerror(errno.ENOENT), report_filepath)
+            self.report = self._load_report(report_filepath)
+            if not self.report:
+                raise Exception("Unable to retrieve the database report!")
+            for cluster_id, row in self.report.items():
+                taxonomy = row["taxonomy"]
+                level = row["level"]
+                cluster_name = taxonomy.split("|")[-1]
+                cluster_folder = os.path.join(clusters_folder, self._get_cluster_batch(cluster_id), cluster_id)
+                parent = None if level == "kingdom" else taxonomy.split("|")[-2]
+                children = row["references"].union(row["mags"])
+                cluster_obj = Entry(self, cluster_id, cluster_name, level, folder=cluster_folder, parent=parent, children=children)
+                if not cluster_obj.sketch_filepath:
+                    raise Exception(f"No sketch found for cluster {cluster_id}")
+                self.clusters[level][cluster_name] = cluster_obj
+                if level == "species":
+                    for genome_id in sorted(children):
+                        genome_obj = Entry(self, genome_id, genome_id, "genome", parent=cluster_name, taxonomy=taxonomy,
+                                           known=genome_id in row["references"])
+                        if not genome_obj.sketch_filepath:
+                            raise Exception(f"No sketch found for genome {genome_id}")
+                        self.genomes[genome_id] = genome_obj
+
+    # ------------------------------------------------------------------ backend
+    @property
+    def backend(self):
+        if not self._validate_metadata(self.metadata):
+            raise Exception("No database metadata found!")
+        key = (int(self.metadata["kmer_size"]), int(self.metadata["filter_size"]))
+        if self._backend is None:
+            self._backend = get_backend(*key)
+        elif _BACKENDS.get(key) is not self._backend:
+            _BACKENDS[key] = self._backend  # an injected backend also serves the static Database.dist
+        return self._backend
+
+    # ------------------------------------------------------------------ small helpers (core.py:253-368, 3104-3341)
+    @staticmethod
+    def _get_cluster_batch(cluster_id: str) -> str:
+        if not _MSBT_ID.search(cluster_id):
+            raise ValueError("The provided argument is not a valid MSBT cluster id!")
+        return str(int(int(cluster_id[4:]) / 1000)).zfill(6)
+
+    def __contains__(self, genome: str) -> bool:
+        return genome in self.genomes
+
+    def size(self) -> Tuple[int, ...]:
+        return tuple(len(self.clusters[level]) for level in LEVELS)
+
+    def taxonomy_exists(self, taxonomy: str) -> bool:
+        if not self._is_defined(taxonomy):
+            return False
+        return all(level_id in self.clusters[level] for level, level_id in zip(LEVELS, taxonomy.split("|")))
+
+    @classmethod
+    def _is_defined(cls, taxonomy: str) -> bool:
+        if not taxonomy:
+            raise ValueError("No taxonomy provided!")
+        if taxonomy.count("|") != 6:
+            return False
+        for level, level_id in zip(cls.LEVELS, taxonomy.split("|")):
+            if len(level_id) <= 3 or level_id[:3] != f"{level[0]}__":
+                return False
+        return True
+
+    @classmethod
+    def _format_taxonomy(cls, taxonomy: str) -> str:
+        # The reference validates and re-joins the seven prefixed names unchanged (core.py:3137-3199).
+        if not cls._is_defined(taxonomy):
+            raise ValueError(f"Malformed taxonomic label: {taxonomy}")
+        names = [part[3:] for part in taxonomy.split("|")]
+        return "|".join(f"{level[0]}__{name}" for level, name in zip(cls.LEVELS, names))
+
+    @staticmethod
+    def _is_supported(filepath: str) -> bool:
+        if not os.path.isfile(filepath):
+            raise FileNotFoundError(errno.ENOENT, os.strerror(errno.ENOENT), filepath)
+        return os.path.splitext(filepath)[1] in {".fa", ".fasta", ".fna", ".bf"}
+
+    @staticmethod
+    def _validate_metadata(metadata: Dict[str, Any]) -> bool:
+        required = {"clusters_count", "filter_size", "kmer_size", "min_kmer_occurrence", "flat"}
+        return required.issubset(metadata.keys())
+
+    def _dump_metadata(self) -> None:
+        with open(os.path.join(self.root, "metadata.json"), "w+") as metadata_json_file:
+            json.dump(self.metadata, metadata_json_file)
+
+    @staticmethod
+    def _load_report(filepath: str) -> Dict[str, Any]:
+        """clusters.tsv -> {cluster_id: row} (core.py:3233-3321)."""
+        if not os.path.isfile(filepath):
+            raise FileNotFoundError(errno.ENOENT, os.strerror(errno.ENOENT), filepath)
+        table: Dict[str, Any] = OrderedDict()
+        header: List[str] = []
+        with open(filepath) as handle:
+            for line in handle:
+                if not line.strip():
+                    continue
+                if line.startswith("#"):
+                    header = line.strip().split("\t")
+                    header[0] = header[0][1:].strip()
+                    continue
+                cells = line.split("\t")
+                col = {name: cells[pos] for pos, name in enumerate(header) if pos < len(cells)}
+                row: Dict[str, Any] = dict()
+                row["level"] = col["level"]
+                row["density"] = float(col["density"])
+                row["references"] = set(col["references_list"].split(",")) if col["references_list"].strip() else set()
+                row["mags"] = set(col["mags_list"].split(",")) if col["mags_list"].strip() else set()
+                row["centroid"] = col["centroid"]
+                row["known"] = col["known"]
+                row["taxonomy"] = col["taxonomy"]
+                row["internal"] = col["internal"]
+                min_ani = float(col["min_ani"]) if col["min_ani"].strip() else None
+                max_ani = float(col["max_ani"].strip()) if col["max_ani"].strip() else None
+                row["boundaries"] = (min_ani, max_ani)
+                table[col["cluster_id"]] = row
+        return table
+
+    # ------------------------------------------------------------------ configuration (core.py:370-533)
+    def set_configs(self, filepaths: Iterable[str], min_kmer_occurrence: int = None, kmer_size: int = None,
+                    kmer_max: int = None, filter_size: int = None, filter_expand_by: float = None) -> None:
+        if os.path.isfile(os.path.join(self.root, "metadata.json")):
+            raise Exception("A metadata.json file is already defined for this database!")
+        if not filepaths:
+            raise ValueError("One or more genome files must be provided in input!")
+        if not min_kmer_occurrence:
+            raise ValueError("The minimum number of kmer occurrences must be provided in input!")
+        self.metadata["min_kmer_occurrence"] = min_kmer_occurrence
+        if not kmer_size:
+            if not kmer_max:
+                raise ValueError("Max kmer size must be provided!")
+            raise NotImplementedError("k-mer size estimation (kitsune) is outside the B200 hot path: pass kmer_size")
+        self.metadata["kmer_size"] = kmer_size
+        if not filter_size:
+            raise NotImplementedError("filter size estimation (ntcard) is outside the B200 hot path: pass filter_size")
+        self.metadata["filter_size"] = filter_size
+        self._dump_metadata()
+
+    # ------------------------------------------------------------------ add (core.py:845-980)
+    def add(self, filepath: str, reference: bool = False, taxonomy: Optional[str] = None) -> None:
+        self.add_many([(filepath, reference, taxonomy)])
+
+    def add_many(self, items: Sequence[Tuple[str, bool, Optional[str]]]) -> None:
+        """add() for a batch: all sketches are built by ONE makebf batch call, then every genome is
+        registered exactly as the reference's per-genome loop (metasbt.py:542-543) would."""
+        if not self._validate_metadata(self.metadata):
+            raise Exception("No database metadata found!")
+        prepared = []
+        seen = set()
+        for filepath, reference, taxonomy in items:
+            if not self._is_supported(filepath):
+                raise ValueError("Input file format is not supported!")
+            if reference and not taxonomy:
+                raise ValueError("A full taxonomic label must be defined for reference genomes!")
+            if not reference and not self.clusters:
+                raise Exception("The database does not contain any clusters!")
+            filename = os.path.splitext(os.path.basename(filepath))[0]
+            if filename in self.genomes or filename in seen:
+                raise Exception("A genome with the same name already exists in the database!")
+            if not taxonomy:
+                raise NotImplementedError("adding unassigned genomes (the `update` command) is outside the B200 hot path")
+            seen.add(filename)
+            prepared.append((filepath, filename, Entry(self, filename, filename, "genome", taxonomy=taxonomy, known=reference), taxonomy))
+        Entry.sketch_many([p[2] for p in prepared], [p[0] for p in prepared])
+
+        for filepath, filename, genome_obj, taxonomy in prepared:
+            if not self._is_defined(taxonomy):
+                raise ValueError("The assigned taxonomy is malformed or not defined!")
+            taxonomy = self._format_taxonomy(taxonomy)
+            names = taxonomy.split("|")
+            new_clusters = False
+            # species first, kingdom last: new MSBT ids are handed out in this order (core.py:913-932)
+            for position in range(len(names) - 1, -1, -1):
+                level, name = LEVELS[position], names[position]
+                cluster_obj = self.clusters[level].get(name)
+                if cluster_obj is None:
+                    if _MSBT_ID.search(name[3:]):
+                        cluster_id = name[3:]
+                    else:
+                        self.metadata["clusters_count"] += 1
+                        cluster_id = f"MSBT{self.metadata['clusters_count']}"
+                    cluster_folder = os.path.join(self.root, "clusters", self._get_cluster_batch(cluster_id), cluster_id)
+                    os.makedirs(cluster_folder)
+                    parent = None if position == 0 else names[position - 1]
+                    cluster_obj = Entry(self, cluster_id, name, level, folder=cluster_folder, parent=parent)
+                    new_clusters = True
+                if level == "species":
+                    genome_obj.parent = name
+                    self.genomes[filename] = genome_obj
+                    cluster_obj.add_children(filename)
+                else:
+                    cluster_obj.add_children(names[position + 1])
+                self.clusters[level][name] = cluster_obj
+            if new_clusters:
+                self._dump_metadata()
+            self._touched.append(taxonomy)
+
+    # ------------------------------------------------------------------ update (core.py:1388-1459)
+    def update(self) -> None:
+        if not self._touched:
+            raise Exception("There is nothing to update in the database!")
+        if self._unknowns:
+            raise Exception("There are still unknown genomes in cache! Please run `self.characterize()` first")
+        processed = set()
+        for level in reversed(LEVELS):
+            pos = LEVELS.index(level)
+            for taxonomy in self._touched:
+                partial = "|".join(taxonomy.split("|")[: pos + 1])
+                if partial not in processed:
+                    print(f"Update: {partial}")
+                    self.clusters[level][partial.split("|")[-1]].index()
+                    processed.add(partial)
+        db_id = "MSBT0"
+        db_folder = os.path.join(self.root, "clusters", self._get_cluster_batch(db_id), db_id)
+        db_obj = Entry(self, db_id, "db", None, folder=db_folder, parent=None, children=set(self.clusters["kingdom"].keys()))
+        db_obj.index()
+        self._dump_report()
+        self._dump_genomes()
+        self.report = self._load_report(os.path.join(self.root, "clusters.tsv"))
+        self._touched = list()
+
+    def _dump_genomes(self) -> None:
+        """genomes.tsv (core.py:1461-1501)."""
+        count = len(list(Path(self.root).glob("genomes*.tsv")))
+        path = os.path.join(self.root, "genomes.tsv")
+        if os.path.isfile(path):
+            shutil.move(path, os.path.join(self.root, f"genomes_{count + 1}.tsv"))
+        with open(path, "w+") as handle:
+            today = datetime.date.today()
+            handle.write(f"# MetaSBT genomes {today.year}-{today.month}-{today.day}\n")
+            handle.write("# {}\n".format("\t".join(["genome_id", "type", "assignment", "internal"])))
+            for genome, obj in self.genomes.items():
+                handle.write("{}\n".format("\t".join([
+                    genome, "reference" if obj.is_known() else "mag", obj.get_full_taxonomy(), obj.get_full_taxonomy(internal=True)])))
+
+    def _dump_report(self) -> None:
+        """clusters.tsv (core.py:1503-1662): species first, kingdom last; density every time (one batched
+        popcount call); boundaries recomputed unless the membership is unchanged."""
+        count = len(list(Path(self.root).glob("clusters*.tsv")))
+        path = os.path.join(self.root, "clusters.tsv")
+        if os.path.isfile(path):
+            shutil.move(path, os.path.join(self.root, f"clusters_{count + 1}.tsv"))
+        # K3': one batched popcount for every cluster representative
+        all_clusters = [self.clusters[level][name] for level in reversed(LEVELS) for name in self.clusters[level]]
+        densities = Entry.get_density_many(all_clusters)
+        header = ["cluster_id", "level", "density", "references_count", "mags_count", "references_list", "mags_list",
+                  "centroid", "known", "taxonomy", "internal", "min_ani", "max_ani"]
+        with open(path, "w+") as handle:
+            today = datetime.date.today()
+            handle.write(f"# MetaSBT report {today.year}-{today.month}-{today.day}\n")
+            handle.write("# {}\n".format("\t".join(header)))
+            for cluster_obj in all_clusters:
+                level = cluster_obj.level
+                if level == "species":
+                    references = sorted(g for g in cluster_obj.children if self.genomes[g].is_known())
+                else:
+                    lower = LEVELS[LEVELS.index(level) + 1]
+                    references = sorted(c for c in cluster_obj.children if self.clusters[lower][c].is_known())
+                mags = sorted(cluster_obj.children.difference(references))
+                density = densities[cluster_obj.identifier]
+                previous = self.report.get(cluster_obj.identifier)
+                if previous is not None and not previous["references"].difference(references) and not previous["mags"].difference(mags):
+                    min_ani, max_ani = previous["boundaries"]
+                    centroid, known = previous["centroid"], str(previous["known"])
+                    taxonomy, internal = previous["taxonomy"], previous["internal"]
+                else:
+                    is_known = cluster_obj.is_known()
+                    taxonomy = cluster_obj.get_full_taxonomy()
+                    internal = cluster_obj.get_full_taxonomy(internal=True)
+                    min_ani, max_ani, centroid = cluster_obj.get_boundaries()
+                    known = str(is_known)
+                    # the report is updated immediately: higher levels read the species centroids from it
+                    self.report[cluster_obj.identifier] = {
+                        "level": level, "density": density, "references": set(references), "mags": set(mags),
+                        "centroid": centroid, "known": is_known, "taxonomy": taxonomy, "internal": internal,
+                        "boundaries": (min_ani, max_ani)}
+                row = [cluster_obj.identifier, level, str(density), str(len(references)), str(len(mags)),
+                       ",".join(references), ",".join(mags), centroid, known, taxonomy, internal,
+                       "" if min_ani is None else str(min_ani), "" if max_ani is None else str(max_ani)]
+                handle.write("{}\n".format("\t".join(row)))
+
+    # ------------------------------------------------------------------ dist (core.py:1664-1833)
+    @staticmethod
+    def dist(sketch_filepath: str, sketches: List[str], kmer_size: int, tmp: str = None, resume: bool = False
+             ) -> Tuple[str, Dict[str, float]]:
+        """ANI distances between one sketch and a list of sketches.  One AND/OR-popcount pass replaces the
+        two `howdesbt bfdistance` spawns; tmp/resume are accepted for signature compatibility (no
+        intermediate text tables are written)."""
+        if not sketches:
+            return (sketch_filepath, dict())
+        if not os.path.isfile(sketch_filepath):
+            raise FileNotFoundError(errno.ENOENT, os.strerror(errno.ENOENT), sketch_filepath)
+        from . import bffile
+        header = bffile.read_header(sketch_filepath)
+        backend = get_backend(header.kmer_size, header.num_bits)
+        distances: Dict[str, float] = OrderedDict()
+        for target, (intersect, union) in zip(sketches, backend.dist_one_vs_many(sketch_filepath, sketches)):
+            distances[target] = ani_distance(intersect, union, kmer_size)
+        return sketch_filepath, distances
+
+    # ------------------------------------------------------------------ profile (core.py:1836-2211)
+    @staticmethod
+    def _profile(instance: "Database", genome_filepath: str, sketch_filepath: str, uncertainty: float = 50.0,
+                 pruning_threshold: float = 0.0):
+        return (genome_filepath, instance.profile(genome_filepath, sketch_filepath, uncertainty=uncertainty,
+                                                  pruning_threshold=pruning_threshold))
+
+    def _query_tree(self, tree_filepath: str, query, threshold: float) -> "OrderedDict[str, Tuple[int, int]]":
+        """`howdesbt query --sort --distinctkmers --tree=<flat tree> --threshold=T` for one query:
+        {leaf name: (hits, total)} in output order (hits descending, ties in tree order; App. A6)."""
+        leaves = []
+        with open(tree_filepath) as handle:
+            for line in handle:
+                line = line.strip()
+                if line.startswith("*"):
+                    leaves.append(line.lstrip("*"))
+        hits, total = self.backend.query_hits(query, leaves)
+        needed = math.ceil(threshold * total)
+        order = sorted(range(len(leaves)), key=lambda i: -int(hits[i]))
+        out: "OrderedDict[str, Tuple[int, int]]" = OrderedDict()
+        for i in order:
+            if int(hits[i]) >= needed:
+                out[os.path.splitext(os.path.basename(leaves[i]))[0]] = (int(hits[i]), total)
+        return out
+
+    def profile(self, genome_filepath: str, sketch_filepath: str, uncertainty: float = 50.0,
+                pruning_threshold: float = 0.0) -> Dict[str, Dict[str, float]]:
+        levels = ["db"] + LEVELS + ["genome"]
+        profiles: Dict[str, Dict[str, float]] = {level: OrderedDict() for level in levels[1:]}
+        genome_filename = os.path.splitext(os.path.basename(genome_filepath))[0]
+        profiles_dir = os.path.join(self.tmp, "profiles")
+        os.makedirs(profiles_dir, exist_ok=True)
+        result_filepath = os.path.join(profiles_dir, f"{genome_filename}.txt")
+
+        if os.path.isfile(result_filepath):
+            # memoised table (core.py:1932-1960); a corrupted file is removed and recomputed
+            try:
+                with open(result_filepath) as handle:
+                    for line in handle:
+                        line = line.strip()
+                        if line and not line.startswith("#"):
+                            level, label, ani = line.split("\t")[:3]
+                            profiles[level][label] = float(ani)
+                return profiles
+            except Exception:
+                os.unlink(result_filepath)
+                profiles = {level: OrderedDict() for level in levels[1:]}
+
+        # The reference joins multi-record FASTA with "N" (core.py:1974-1996) because howdesbt treats records
+        # as separate queries; k-mers never span records or Ns, so the distinct-position set of the whole
+        # file is the same thing and is computed once for the whole descent.
+        query = self.backend.query_positions(genome_filepath)
+        kmer_size = self.metadata["kmer_size"]
+        dists: Dict[str, float] = dict()
+        first_iter = True
+        clusters: List[str] = []
+        for pos, level in enumerate(levels):
+            if level == "genome":
+                break
+            next_level = levels[pos + 1]
+            if level == "db":
+                clusters = ["db"]
+            best_level_matches: "OrderedDict[str, float]" = OrderedDict()
+            for cluster in clusters:
+                cluster_id = "MSBT0" if level == "db" else self.clusters[level][cluster].identifier
+                tree_filepath = os.path.join(self.root, "clusters", self._get_cluster_batch(cluster_id), cluster_id,
+                                             "tree", "index.detbrief.sbt")
+                if not os.path.isfile(tree_filepath):
+                    raise FileNotFoundError(errno.ENOENT, os.strerror(errno.ENOENT), tree_filepath)
+                threshold = pruning_threshold if level == "kingdom" else 0.0
+                matches = self._query_tree(tree_filepath, query, threshold)
+                if not matches:
+                    continue
+                scores = OrderedDict((node, common / total) for node, (common, total) in matches.items())
+                best_match = sorted(scores.keys(), key=lambda m: scores[m])[-1]
+                best_score = scores[best_match]
+                score_threshold = float((best_score * uncertainty) / 100.0)
+                for node, score in scores.items():
+                    if score >= best_score - score_threshold:
+                        best_level_matches[node] = score
+
+            if level == "db":
+                names = list(best_level_matches.keys())
+                sketches = [self.clusters[next_level][n].sketch_filepath for n in names]
+                _, kingdom_dists = self.dist(sketch_filepath, sketches, kmer_size, tmp=self.tmp, resume=False)
+                for name, sk in zip(names, sketches):
+                    profiles[next_level][self.clusters[next_level][name].get_full_taxonomy()] = round(kingdom_dists[sk], 5)
+            elif level == "species":
+                top = sorted(best_level_matches.keys(), key=lambda m: best_level_matches[m])[-1]
+                top_sketch = self.genomes[top].sketch_filepath
+                _, d = self.dist(sketch_filepath, [top_sketch], kmer_size, tmp=self.tmp, resume=False)
+                best_obj = self.genomes[os.path.splitext(os.path.basename(top_sketch))[0]]
+                label = f"{best_obj.get_full_taxonomy()}|t__{best_obj.name}"
+                profiles[next_level][label] = round(d[best_obj.sketch_filepath], 5)
+            else:
+                for name in best_level_matches:
+                    obj = self.clusters[next_level][name]
+                    species_entries = [obj.name] if next_level == "species" else sorted(obj.get_children(up_to="species"))
+                    centroids = [self.report[self.clusters["species"][s].identifier]["centroid"] for s in species_entries]
+                    centroid_sketches = [self.genomes[c].sketch_filepath for c in centroids]
+                    if first_iter:
+                        _, found = self.dist(sketch_filepath, centroid_sketches, kmer_size, tmp=self.tmp, resume=False)
+                        dists.update(found)
+                    profiles[next_level][obj.get_full_taxonomy()] = round(statistics.mean(dists[s] for s in centroid_sketches), 5)
+                if first_iter:
+                    first_iter = False
+            clusters = list(best_level_matches.keys())
+
+        with open(result_filepath, "w+") as table:
+            table.write("# level\tclosest\tani\n")
+            for level in LEVELS + ["genome"]:
+                for match in profiles[level]:
+                    table.write(f"{level}\t{match}\t{profiles[level][match]}\n")
+        return profiles
+
+    # ------------------------------------------------------------------ outside the hot path
+    def _unsupported(self, *a, **k):
+        raise NotImplementedError("outside the B200 hot path (SURVEY.md 8: index / profile only)")
+
+    qc = dereplicate = characterize = is_known = merge = remove = cluster = _unsupported
+
+
+class Entry(object):
+    """One cluster (MSBT id) or one genome (reference: core.py:3344-4111)."""
+
+    def __init__(self, database: Database, identifier: str, name: str, level: Optional[str], folder: Optional[str] = None,
+                 parent: Optional[str] = None, children: Optional[Set[str]] = None, taxonomy: Optional[str] = None,
+                 known: bool = False):
+        self.database = database
+        if not identifier:
+            raise ValueError("Invalid Entry ID!")
+        self.identifier = identifier
+        if not name:
+            raise ValueError("Invalid Entry name!")
+        self.name = name
+        if level and level not in LEVELS + ["genome"]:
+            raise ValueError("Invalid taxonomic level!")
+        if level == "genome" and children:
+            raise ValueError("A genome cannot contain children!")
+        self.level = level
+        if self.level == "genome" and self.identifier != self.name:
+            raise ValueError("A genome entry ID should match with the entry name!")
+        if self.level in LEVELS and not _MSBT_ID.search(self.identifier):
+            raise ValueError("A cluster entry ID should match with the following regular expression: ^MSBT[0-9]*$")
+        self.folder = folder if folder else os.path.join(os.getcwd(), name)
+        is_cluster = not self.level or self.level in LEVELS
+        if is_cluster:
+            os.makedirs(os.path.join(self.folder, "tree"), exist_ok=True)
+        self.parent = parent
+        self.children: Set[str] = set(children) if children else set()
+        self._known = known
+        self.taxonomy = taxonomy
+        if self.level == "genome" and self._known and not self.taxonomy:
+            raise ValueError("The entry is a reference but no taxonomy is provided!")
+        if self.level == "genome" and self._known and not Database._is_defined(self.taxonomy):
+            raise ValueError("The provided taxonomy is malformed!")
+        self.profile: Dict[str, Any] = dict()
+        self.sketch_filepath: Optional[str] = None
+        candidate = self._sketch_path()
+        if os.path.isfile(candidate):
+            self.sketch_filepath = candidate
+
+    def _sketch_path(self) -> str:
+        if not self.level or self.level in LEVELS:
+            return os.path.join(self.database.root, "clusters", Database._get_cluster_batch(self.identifier),
+                                self.identifier, f"{self.name}.bf")
+        return os.path.join(self.database.root, "sketches", f"{self.name}.bf")
+
+    def __len__(self) -> int:
+        return len(self.children)
+
+    # ------------------------------------------------------------------ navigation (core.py:3509-3712)
+    def add_children(self, child: str) -> None:
+        if self.level == "genome":
+            raise Exception("Genomes cannot have children!")
+        self.children.add(child)
+
+    def get_children(self, up_to: str = None) -> Set[str]:
+        levels = LEVELS + ["genome"]
+        if not up_to:
+            up_to = "genome"
+        elif up_to not in levels:
+            raise Exception(f"{up_to} is not a valid taxonomic level!")
+        elif levels.index(up_to) <= levels.index(self.level):
+            raise Exception(f"There are no {up_to} levels under the {self.level} level!")
+        found: Set[str] = set()
+        stack = [self]
+        while stack:
+            current = stack.pop()
+            if current.level == "genome":
+                raise Exception("The current entry represents a genome!")
+            if current.level == "species":
+                found.update(current.children)
+                continue
+            lower = levels[levels.index(current.level) + 1]
+            if lower == up_to:
+                found.update(current.children)
+                continue
+            stack.extend(self.database.clusters[lower][child] for child in current.children)
+        return found
+
+    def get_full_taxonomy(self, current_entry: "Entry" = None, taxonomy: str = None, internal: bool = False) -> str:
+        entry = current_entry if current_entry else self
+        if not entry.level:
+            return ""
+        if entry.level == "genome":
+            entry = self.database.clusters["species"][entry.parent]
+        parts: List[str] = [taxonomy] if taxonomy else []
+        while True:
+            parts.insert(0, f"{entry.level[0]}__{entry.identifier}" if internal else entry.name)
+            if entry.level == "kingdom":
+                return "|".join(parts)
+            entry = self.database.clusters[LEVELS[LEVELS.index(entry.level) - 1]][entry.parent]
+
+    def is_known(self) -> bool:
+        if not self.level:
+            return False
+        if self.level == "genome" or self._known:
+            return self._known
+        for genome in self.get_children():
+            if genome in self.database.genomes and self.database.genomes[genome].is_known():
+                self._known = True
+                return True
+        return False
+
+    # ------------------------------------------------------------------ K1: sketch (core.py:3880-3943)
+    def sketch(self, filepath: str) -> str:
+        Entry.sketch_many([self], [filepath])
+        return self.sketch_filepath
+
+    @staticmethod
+    def sketch_many(entries: Sequence["Entry"], filepaths: Sequence[str]) -> List[str]:
+        """makebf for many genome entries in one batch; existing sketches are reused (core.py:3915-3918)."""
+        todo_fa, todo_out = [], []
+        database = None
+        for entry, filepath in zip(entries, filepaths):
+            database = entry.database
+            if not Database._validate_metadata(database.metadata):
+                raise Exception("No database metadata found!")
+            if entry.level in LEVELS:
+                raise Exception("This function can be used in case of genome entries only!")
+            if not Database._is_supported(filepath):
+                raise ValueError("Input file format is not supported!")
+            out = os.path.join(database.root, "sketches", f"{entry.name}.bf")
+            if not os.path.isfile(out) and out not in todo_out:
+                todo_fa.append(filepath)
+                todo_out.append(out)
+            entry.sketch_filepath = out
+        if todo_fa:
+            database.backend.sketch_many(todo_fa, todo_out, database.metadata["min_kmer_occurrence"])
+        return [e.sketch_filepath for e in entries]
+
+    # ------------------------------------------------------------------ K2: index (core.py:3714-3878)
+    def index(self) -> None:
+        db = self.database
+        if not Database._validate_metadata(db.metadata):
+            raise Exception("No database metadata found!")
+        if self.level == "genome":
+            raise Exception("Genome entries cannot be indexed!")
+        if not self.children:
+            raise Exception("This entry is empty!")
+        if not db.flat:
+            raise NotImplementedError("flat=False (howdesbt cluster/build) is outside the B200 hot path")
+        if os.path.isdir(self.folder):
+            shutil.rmtree(os.path.join(self.folder, "tree"), ignore_errors=True)
+            os.makedirs(os.path.join(self.folder, "tree"), exist_ok=True)
+        if self.level == "species":
+            sketches = {db.genomes[child].sketch_filepath for child in self.children}
+        else:
+            lower = "kingdom" if not self.level else LEVELS[LEVELS.index(self.level) + 1]
+            sketches = set()
+            for child in self.children:
+                obj = db.clusters[lower][child]
+                sketches.add(os.path.join(obj.folder, f"{obj.name}.bf"))
+        ordered = sorted(sketches)  # the reference iterates the set (hash order)
+        with open(os.path.join(self.folder, f"{self.name}.txt"), "w+") as handle:
+            for path in ordered:
+                handle.write(f"{path}\n")
+        target = os.path.join(self.folder, f"{self.name}.bf")
+        if len(ordered) == 1:
+            db.backend.copy(ordered[0], target)
+        else:
+            db.backend.union(ordered, target)
+        with open(os.path.join(self.folder, "tree", "index.detbrief.sbt"), "w+") as flat_tree:
+            flat_tree.write(f"{target}\n")
+            for path in ordered:
+                flat_tree.write(f"*{path}\n")
+        self.sketch_filepath = target
+
+    # ------------------------------------------------------------------ K3': density (core.py:3576-3607)
+    def get_density(self) -> float:
+        return Entry.get_density_many([self])[self.identifier]
+
+    @staticmethod
+    def get_density_many(entries: Sequence["Entry"]) -> Dict[str, float]:
+        if not entries:
+            return {}
+        db = entries[0].database
+        paths = [os.path.join(e.folder, f"{e.name}.bf") for e in entries]
+        counts = db.backend.popcounts(paths)
+        bits = db.metadata["filter_size"]
+        return {e.identifier: c / bits for e, c in zip(entries, counts)}
+
+    # ------------------------------------------------------------------ K3: boundaries (core.py:3945-4111)
+    def get_boundaries(self, limit_number: int = 0, limit_percentage: float = 100.0):
+        db = self.database
+        if self.level == "genome":
+            raise Exception("Cannot compute boundaries over a genome entry!")
+        if self.level == "species":
+            children = sorted(self.get_children())
+        else:
+            children = []
+            for species in sorted(self.get_children(up_to="species")):
+                identifier = db.clusters["species"][species].identifier
+                if identifier in db.report:
+                    children.append(db.report[identifier]["centroid"])
+                else:
+                    children.append(db.clusters["species"][species].get_boundaries(limit_number, limit_percentage)[2])
+        if limit_percentage < 100.0:
+            limit = math.ceil(len(children) * limit_percentage / 100.0)
+        elif limit_number > 0:
+            limit = min(limit_number, len(children))
+        else:
+            limit = len(children)
+        if 0 < limit < len(children):
+            random.seed(0)
+            children = random.sample(children, limit)
+        if len(children) < 3:
+            return (None, None, sorted(children)[0])
+
+        # all pairs in ONE call: I[i][j] = popc(A_i & A_j), diagonal = popcounts, U = I_ii + I_jj - I_ij
+        paths = [db.genomes[c].sketch_filepath for c in children]
+        inter = db.backend.dist_all_pairs(paths)
+        k = db.metadata["kmer_size"]
+        pairwise: Dict[str, List[float]] = {c: [] for c in children}
+        for i, source in enumerate(children):
+            for j in range(i + 1, len(children)):
+                union = int(inter[i][i]) + int(inter[j][j]) - int(inter[i][j])
+                d = ani_distance(int(inter[i][j]), union, k)
+                pairwise[source].append(d)
+                pairwise[children[j]].append(d)
+        best = sys.float_info.max
+        centroid = None
+        for child in children:
+            mean = statistics.mean(pairwise[child])
+            if mean < best:
+                best, centroid = mean, child
+        min_ani = round(min(pairwise[centroid]), 5)
+        max_ani = round(max(pairwise[centroid]), 5)
+        if self.level != "kingdom" and max_ani == 1.0:
+            return (None, None, centroid)
+        return (round(min_ani, 5), round(max_ani, 5), centroid)

@@ -1,0 +1,58 @@
+"""TEST INFRASTRUCTURE: a checker backend with the interface of metasbt_b200.backend.CudaBackend,
+served by the oracle.  It lets the CPU suite exercise the host logic of metasbt_b200.core (file
+layout, report, profile descent) without a GPU, and lets GPU tests compare whole databases built by
+the two backends.  The shipped package never imports this module."""
+import os
+from typing import List, Sequence, Tuple
+
+import numpy as np
+
+from metasbt_b200 import bffile
+from oracle import oracle as O
+
+
+class OracleBackend:
+    def __init__(self, kmer_size: int, num_bits: int):
+        self.k, self.num_bits = int(kmer_size), int(num_bits)
+        self._cache = {}
+
+    def _load(self, path: str) -> np.ndarray:
+        path = os.path.abspath(path)
+        if path not in self._cache:
+            header, words = bffile.read_bf(path)
+            assert header.num_bits == self.num_bits and header.kmer_size == self.k
+            self._cache[path] = words
+        return self._cache[path]
+
+    def _store(self, path: str, words: np.ndarray) -> None:
+        bffile.write_bf(path, bffile.BloomHeader(kmer_size=self.k, num_bits=self.num_bits), words)
+        self._cache[os.path.abspath(path)] = words
+
+    def sketch_many(self, fasta_paths: Sequence[str], out_paths: Sequence[str], min_abund: int) -> None:
+        for fa, out in zip(fasta_paths, out_paths):
+            self._store(out, O.makebf(open(fa, "rb").read(), self.k, self.num_bits, min_abund))
+
+    def union(self, src_paths: Sequence[str], out_path: str) -> None:
+        self._store(out_path, O.bf_or([self._load(p) for p in src_paths]))
+
+    def copy(self, src_path: str, out_path: str) -> None:
+        self._store(out_path, self._load(src_path).copy())
+
+    def popcounts(self, paths: Sequence[str]) -> List[int]:
+        return [O.bf_popcount(self._load(p)) for p in paths]
+
+    def dist_one_vs_many(self, focus_path: str, target_paths: Sequence[str]) -> List[Tuple[int, int]]:
+        a = self._load(focus_path)
+        return [(O.bf_and_popcount(a, self._load(p)), O.bf_or_popcount(a, self._load(p))) for p in target_paths]
+
+    def dist_all_pairs(self, paths: Sequence[str]) -> np.ndarray:
+        f = [self._load(p) for p in paths]
+        return np.array([[O.bf_and_popcount(a, b) for b in f] for a in f], dtype=np.int64)
+
+    def query_positions(self, fasta_path: str) -> np.ndarray:
+        return O.positions_distinct(open(fasta_path, "rb").read(), self.k, self.num_bits)
+
+    def query_hits(self, positions: np.ndarray, leaf_paths: Sequence[str]):
+        if not leaf_paths:
+            return [], len(positions)
+        return [int(x) for x in O.query_hits(positions, [self._load(p) for p in leaf_paths])], len(positions)

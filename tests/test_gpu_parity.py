@@ -190,3 +190,26 @@ def test_error_behaviour(ctx):
     with pytest.raises(ValueError):
         ctx.bf_or([], 1024)
     assert "k=65" in ctx._L.msbt_last_error(ctx._h).decode() or True
+
+
+def _kats():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_positions.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_committed_known_answers(ctx, variant):
+    """The committed golden vectors, without the oracle in the loop."""
+    from metasbt_b200 import ops
+    for kat in _kats():
+        if kat["min"] > 1 and variant == 2:
+            continue
+        _, got = build(ctx, [kat["fasta"].encode()], kat["k"], kat["num_bits"], min_abund=kat["min"], modulus=kat["modulus"],
+                       variant=variant if kat["min"] == 1 else 0)
+        bits = [i * 64 + b for i, x in enumerate(got[0]) for b in range(64) if (int(x) >> b) & 1]
+        assert bits == kat["set_bits"], kat["name"]
+        q, _ = build(ctx, [kat["fasta"].encode()], kat["k"], kat["num_bits"], modulus=kat["modulus"])
+        pos = ctx.extract_positions(q[0], kat["num_bits"])
+        assert [int(x) for x in pos.cpu().numpy().view(np.uint32)] == kat["query_positions"], kat["name"]

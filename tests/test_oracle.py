@@ -121,3 +121,21 @@ def test_ani_formula(oracle):
     assert oracle.ani_distance(1, 10 ** 9, 3) == 1.0  # jaccard rounds to 0.0
     with pytest.raises(ZeroDivisionError):
         oracle.ani_distance(0, 0, 31)
+
+
+def _kats():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "kat_positions.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("kat", _kats(), ids=lambda c: c["name"])
+def test_committed_known_answers(oracle, kat):
+    """tests/golden/kat_positions.json (made by tests/golden/make_golden.py): both restatements reproduce it."""
+    fa = kat["fasta"].encode()
+    for impl in (oracle.makebf, oracle.py_makebf):
+        w = impl(fa, kat["k"], kat["num_bits"], kat["min"], modulus=kat["modulus"])
+        got = [i * 64 + b for i, x in enumerate(w) for b in range(64) if (int(x) >> b) & 1]
+        assert got == kat["set_bits"]
+    assert [int(p) for p in oracle.positions_distinct(fa, kat["k"], kat["num_bits"], modulus=kat["modulus"])] == kat["query_positions"]
