@@ -76,7 +76,8 @@ typedef struct {
  * inside the genome is >= min_abund (k <= 32 only in this version).
  * The output filters are fully written (zero-filled first) -- callers need not clear them.
  * `h_descs` is host memory and is consumed before the call returns.
- * variant: 0 = auto, 1 = direct (memset + red.or into HBM), 2 = L2-staged regions. */
+ * variant: 0 = auto, 1 = direct (memset + red.or into HBM), 2 = tiled (partition kernel + tile-build kernel),
+ *          3 = fused (one persistent warp-specialised kernel: partition warps + tile-build warps). */
 int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *d_run_ends,
                           const msbt_genome_desc *h_descs, uint32_t n_genomes,
                           uint32_t k, uint64_t seed, uint64_t modulus, uint64_t num_bits,

@@ -11,7 +11,7 @@ from typing import List
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
-SO_PATH = os.path.join(_PKG, "libmsbt.so")
+SO_PATH = os.environ.get("MSBT_LIB") or os.path.join(_PKG, "libmsbt.so")  # MSBT_LIB: kernel-tuning builds only
 SOURCES = [os.path.join(_PKG, "csrc", "msbt_kernels.cu")]
 HEADERS = [os.path.join(_PKG, "csrc", "msbt_spec.h"), os.path.join(_PKG, "csrc", "msbt_kmer.h"), os.path.join(_ROOT, "include", "msbt.h")]
 

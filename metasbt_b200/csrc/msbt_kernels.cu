@@ -41,6 +41,7 @@ struct msbt_ctx {
     cudaEvent_t stage_free;  // recorded after the last H2D that read h_stage
     bool stage_busy;
     bool tiled_attr_set;  // dynamic-smem opt-in done for this device
+    bool fused_attr_set;
 };
 
 static int fail(msbt_ctx *ctx, int code, const char *fmt, ...) {
@@ -259,8 +260,8 @@ struct DevGenome {
     uint64_t filter_word_off;  // in u64 words
     uint32_t n_bases;
     uint32_t n_runs;
-    uint32_t tile_begin;  // first global tile index of this genome
-    uint32_t pad;
+    uint32_t tile_begin;    // first global tile index of this genome (TILE_BASES units)
+    uint32_t fchunk_begin;  // first chunk of this genome in the fused kernel (FU_CHUNK_BASES units)
 };
 
 struct KmerSpec {
@@ -291,11 +292,20 @@ template <int KW, int HV, bool POW2>
 __global__ void __launch_bounds__(TILE_THREADS, 4)
 kmer_bloom_direct_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ run_ends,
                          const DevGenome *__restrict__ genomes, uint32_t n_genomes, uint32_t n_tiles,
-                         KmerSpec spec, uint32_t *__restrict__ filters) {
+                         KmerSpec spec, uint32_t *__restrict__ filters, const uint32_t *__restrict__ only_dirty) {
     const uint32_t k = spec.k, len = (k + 3) >> 2;
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t gi = find_genome(genomes, n_genomes, tile);
         const DevGenome g = genomes[gi];
+        // redo pass after the fused kernel: only genomes whose ring buckets overflowed
+        if (only_dirty) {
+            if (only_dirty[gi] == 0) {
+                const uint32_t nxt = (gi + 1 < n_genomes) ? genomes[gi + 1].tile_begin : n_tiles;  // skip to the next genome
+                const uint32_t skip = (nxt - tile + gridDim.x - 1) / gridDim.x;
+                tile += (skip ? skip - 1 : 0) * gridDim.x;
+                continue;
+            }
+        }
         const uint32_t w = (tile - g.tile_begin) * TILE_THREADS + threadIdx.x;
         const uint32_t s0 = w * 32;
         if (s0 >= g.n_bases) continue;
@@ -577,6 +587,16 @@ overflow_fixup_kernel(const unsigned long long *__restrict__ ovf_count, const ui
     }
 }
 
+#include "msbt_fused.cuh"
+
+#ifdef MSBT_FU_TRACE
+extern "C" int msbt_debug_trace(unsigned long long *out24, int reset) {
+    if (cudaMemcpyFromSymbol(out24, fu_trace, sizeof(unsigned long long) * 24) != cudaSuccess) return -1;
+    if (reset) { unsigned long long z[24] = {0}; cudaMemcpyToSymbol(fu_trace, z, sizeof(z)); }
+    return 0;
+}
+#endif
+
 // ---- exact multiplicity path (min_abund >= 2, k <= 32): open-addressing count table.
 constexpr uint64_t HT_EMPTY = ~0ULL;  // never a canonical k-mer for k <= 32 (all-T's rc is all-A = 0)
 
@@ -776,6 +796,126 @@ static int build_tiled(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *
     return MSBT_OK;
 }
 
+
+static int launch_direct(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *d_run_ends, const DevGenome *d_genomes,
+                         uint32_t n_genomes, uint64_t tiles, const KmerSpec &spec, uint64_t *d_filters,
+                         const uint32_t *only_dirty, cudaStream_t stream) {
+    if (tiles == 0) return MSBT_OK;
+    const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * 8);
+#define MSBT_DIRECT_LAUNCH(KW, HV, P2)                                                                          \
+    kmer_bloom_direct_kernel<KW, HV, P2><<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, d_genomes, n_genomes, \
+                                                                           (uint32_t)tiles, spec, (uint32_t *)d_filters, only_dirty)
+    const int hv = msbt_hash_variant(spec.k);
+    const bool p2 = spec.pos.pow2 != 0;
+    if (hv == 0) { if (p2) MSBT_DIRECT_LAUNCH(1, 0, true); else MSBT_DIRECT_LAUNCH(1, 0, false); }
+    else if (hv == 1) { if (p2) MSBT_DIRECT_LAUNCH(2, 1, true); else MSBT_DIRECT_LAUNCH(2, 1, false); }
+    else { if (p2) MSBT_DIRECT_LAUNCH(2, 2, true); else MSBT_DIRECT_LAUNCH(2, 2, false); }
+#undef MSBT_DIRECT_LAUNCH
+    LAUNCH_CHECK(ctx);
+    return MSBT_OK;
+}
+
+// Variant 3: the fused persistent kernel of msbt_fused.cuh.  Returns 1 if the geometry does not apply.
+static int build_fused(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *d_run_ends, const std::vector<DevGenome> &dg,
+                       uint64_t tiles, uint64_t fchunks, const KmerSpec &spec, uint64_t words, uint64_t *d_filters,
+                       cudaStream_t stream) {
+    const uint32_t n_genomes = (uint32_t)dg.size();
+    const uint64_t num_bits = spec.pos.num_bits;
+    const uint32_t k = spec.k;
+    uint32_t shift = 7;  // a tile is at least 128 bits (one 16-byte bulk store)
+    while (((num_bits + (1ull << shift) - 1) >> shift) > FU_MAX_BUCKETS) shift++;
+    const uint32_t NB = (uint32_t)((num_bits + (1ull << shift) - 1) >> shift);
+    if (fchunks == 0 || (fchunks >> 31) || ((uint64_t)n_genomes * NB >> 28)) return 1;  // counters: 4 B per (genome, bucket)
+
+    FusedParams P;
+    memset(&P, 0, sizeof(P));
+    P.bucket_shift = shift;
+    P.NB = NB;
+    P.cap = (FU_STAGE_WORDS / (NB + 1)) & ~3u;
+    P.quads = P.cap / 4;
+    P.quad_magic = (uint32_t)(((1ull << 32) + P.quads - 1) / P.quads);
+    if ((uint64_t)NB * P.quads * P.quads >= (1ull << 32)) return 1;  // exactness bound of the magic division
+    P.tile_log2 = std::min(shift, FU_TILE_LOG2);
+    P.tiles_per_bucket_log2 = shift - P.tile_log2;
+    P.words = words;
+    P.n_genomes = n_genomes;
+    P.n_chunks_total = (uint32_t)fchunks;
+
+    uint64_t max_kmers = 0;
+    for (const DevGenome &g : dg) max_kmers = std::max<uint64_t>(max_kmers, g.n_bases >= k ? (uint64_t)g.n_bases - k + 1 : 0);
+    {
+        // positions are uniform over [0, modulus): expected entries per bucket + 8 sigma; every chunk that touches a
+        // bucket may add up to 3 pad entries, a full staging row spills 4 entries per k-mer (rare)
+        const double frac = std::min(1.0, (double)(1ull << shift) / (double)spec.pos.modulus);
+        const double e = (double)max_kmers * frac;
+        const double chunks = (double)((max_kmers + FU_CHUNK_BASES - 1) / FU_CHUNK_BASES);
+        const double touched = chunks * std::min(1.0, (double)FU_CHUNK_BASES * frac);
+        uint64_t cap = (uint64_t)(1.02 * e + 8.0 * sqrt(e) + 3.0 * touched + 64.0);
+        cap = std::min<uint64_t>(cap, max_kmers + 3 * (uint64_t)chunks + 8);
+        cap = (cap + 7) / 8 * 8;
+        if ((cap * NB) >> 32) return 1;
+        P.gcap = (uint32_t)cap;
+    }
+    const uint64_t slot_bytes = (uint64_t)NB * P.gcap * 4;
+    P.ring = (uint32_t)std::max<uint64_t>(2, std::min<uint64_t>(4, (72ull << 20) / std::max<uint64_t>(slot_bytes, 1)));
+
+    // scratch: [genome table][sync 64 B][done][consumed][dirty][gcnt n_genomes x NB] | [gbuf ring x NB x gcap]
+    const size_t t_b = align_up(sizeof(DevGenome) * n_genomes, 256);
+    const size_t sync_off = t_b;
+    const size_t done_off = sync_off + 64;
+    const size_t cons_off = done_off + (size_t)n_genomes * 4;
+    const size_t dirty_off = cons_off + (size_t)n_genomes * 4;
+    const size_t gcnt_off = align_up(dirty_off + (size_t)n_genomes * 4, 16);
+    const size_t zero_end = gcnt_off + (size_t)n_genomes * NB * 4;
+    const size_t gbuf_off = align_up(zero_end, 256);
+    const size_t total = gbuf_off + (size_t)P.ring * slot_bytes;
+    int rc = ensure_scratch(ctx, total);
+    if (rc) return rc == MSBT_ENOMEM ? 1 : rc;
+    size_t table_b = 0;
+    rc = stage_genome_table(ctx, dg, &table_b, stream);
+    if (rc) return rc;
+    char *S = (char *)ctx->d_scratch;
+    P.packed = d_packed;
+    P.run_ends = d_run_ends;
+    P.genomes = (const DevGenome *)S;
+    P.sync = (uint32_t *)(S + sync_off);
+    P.done = (uint32_t *)(S + done_off);
+    P.consumed = (uint32_t *)(S + cons_off);
+    P.dirty = (uint32_t *)(S + dirty_off);
+    P.gcnt = (uint32_t *)(S + gcnt_off);
+    P.gbuf = (uint32_t *)(S + gbuf_off);
+    P.filters = d_filters;
+    CU_TRY(ctx, cudaMemsetAsync(S + sync_off, 0, zero_end - sync_off, stream));
+
+    if (!ctx->fused_attr_set) {
+#define MSBT_FU_ATTR(KW, HV) \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_fused_kernel<KW, HV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES)); \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_fused_kernel<KW, HV, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES)); \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_fused_kernel<KW, HV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES)); \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_fused_kernel<KW, HV, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES));
+        MSBT_FU_ATTR(1, 0) MSBT_FU_ATTR(2, 1) MSBT_FU_ATTR(2, 2)
+#undef MSBT_FU_ATTR
+        ctx->fused_attr_set = true;
+    }
+    const int grid = ctx->num_sms;
+#define MSBT_FU_LAUNCH(KW, HV)                                                                                     \
+    {                                                                                                              \
+        if (p2 && full) kmer_bloom_fused_kernel<KW, HV, true, true><<<grid, FU_THREADS, FU_SMEM_BYTES, stream>>>(P, spec);   \
+        else if (p2) kmer_bloom_fused_kernel<KW, HV, true, false><<<grid, FU_THREADS, FU_SMEM_BYTES, stream>>>(P, spec);     \
+        else if (full) kmer_bloom_fused_kernel<KW, HV, false, true><<<grid, FU_THREADS, FU_SMEM_BYTES, stream>>>(P, spec);   \
+        else kmer_bloom_fused_kernel<KW, HV, false, false><<<grid, FU_THREADS, FU_SMEM_BYTES, stream>>>(P, spec);            \
+    }
+    const int hv = msbt_hash_variant(k);
+    const bool p2 = spec.pos.pow2 != 0, full = spec.pos.modulus <= spec.pos.num_bits;
+    if (hv == 0) MSBT_FU_LAUNCH(1, 0)
+    else if (hv == 1) MSBT_FU_LAUNCH(2, 1)
+    else MSBT_FU_LAUNCH(2, 2)
+#undef MSBT_FU_LAUNCH
+    LAUNCH_CHECK(ctx);
+    // genomes whose ring buckets overflowed (skewed inputs) are completed by the direct kernel
+    return launch_direct(ctx, d_packed, d_run_ends, P.genomes, n_genomes, tiles, spec, d_filters, P.dirty, stream);
+}
+
 extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *d_run_ends,
                                      const msbt_genome_desc *h_descs, uint32_t n_genomes, uint32_t k,
                                      uint64_t seed, uint64_t modulus, uint64_t num_bits, uint32_t min_abund,
@@ -790,7 +930,7 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
     if (n_genomes == 0) return MSBT_OK;
     if (!d_packed || !d_run_ends || !h_descs || !d_filters) return fail(ctx, MSBT_EINVAL, "null pointer argument");
     if (min_abund >= 2 && k > 32) return fail(ctx, MSBT_EINVAL, "min_abund >= 2 supports k <= 32 only (k=%u)", k);
-    if (variant < 0 || variant > 2) return fail(ctx, MSBT_EINVAL, "unknown variant %d", variant);
+    if (variant < 0 || variant > 3) return fail(ctx, MSBT_EINVAL, "unknown variant %d", variant);
     CU_TRY(ctx, cudaSetDevice(ctx->device));
 
     KmerSpec spec;
@@ -799,7 +939,7 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
 
     // device genome table with tile prefix
     std::vector<DevGenome> dg(n_genomes);
-    uint64_t tiles = 0;
+    uint64_t tiles = 0, fchunks = 0;
     uint64_t max_bases = 0;
     for (uint32_t i = 0; i < n_genomes; i++) {
         const msbt_genome_desc &d = h_descs[i];
@@ -810,8 +950,9 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
         dg[i].n_bases = (uint32_t)d.n_bases;
         dg[i].n_runs = d.n_runs;
         dg[i].tile_begin = (uint32_t)tiles;
-        dg[i].pad = 0;
+        dg[i].fchunk_begin = (uint32_t)fchunks;
         tiles += (d.n_bases + TILE_BASES - 1) / TILE_BASES;
+        fchunks += (d.n_bases + FU_CHUNK_BASES - 1) / FU_CHUNK_BASES;
         max_bases = std::max<uint64_t>(max_bases, d.n_bases);
         if (tiles >> 31) return fail(ctx, MSBT_EINVAL, "batch too large (%llu tiles)", (unsigned long long)tiles);
     }
@@ -825,8 +966,15 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
         for (uint32_t i = 1; i < n_genomes; i++) distinct = distinct && offs[i] != offs[i - 1];
     }
     const bool tiled_ok = distinct && min_abund <= 1 && num_bits <= (1ull << 32);
-    if (variant == 2 && !tiled_ok)
-        return fail(ctx, MSBT_EINVAL, "variant 2 needs distinct filter_index values, min_abund <= 1 and num_bits <= 2^32");
+    if (variant >= 2 && !tiled_ok)
+        return fail(ctx, MSBT_EINVAL, "variant %d needs distinct filter_index values, min_abund <= 1 and num_bits <= 2^32", variant);
+    const bool fused_ok = tiled_ok && num_bits >= (1ull << 17);
+    if (variant == 3 && !fused_ok) return fail(ctx, MSBT_EINVAL, "variant 3 needs num_bits >= 2^17");
+    if (fused_ok && (variant == 3 || (variant == 0 && num_bits >= (1ull << 26)))) {
+        const int rc = build_fused(ctx, d_packed, d_run_ends, dg, tiles, fchunks, spec, words, d_filters, stream);
+        if (rc <= 0) return rc;
+        if (variant == 3 && fchunks) return fail(ctx, MSBT_EINVAL, "variant 3: geometry not applicable to this batch");
+    }
     const bool tiled = tiled_ok && (variant == 2 || (variant == 0 && num_bits >= (1ull << TB_TILE_LOG2)));
     if (tiled) {
         const int rc = build_tiled(ctx, d_packed, d_run_ends, dg, tiles, spec, words, d_filters, stream);
@@ -885,19 +1033,8 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
     rc = stage_end(ctx, stream);
     if (rc) return rc;
 
-    int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * 8);
-#define MSBT_DIRECT_LAUNCH(KW, HV, P2)                                                                                   \
-    kmer_bloom_direct_kernel<KW, HV, P2><<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, (const DevGenome *)ctx->d_scratch, \
-                                                                           n_genomes, (uint32_t)tiles, spec, (uint32_t *)d_filters)
-    {
-        const int hv = msbt_hash_variant(k);
-        const bool p2 = spec.pos.pow2 != 0;
-        if (hv == 0) { if (p2) MSBT_DIRECT_LAUNCH(1, 0, true); else MSBT_DIRECT_LAUNCH(1, 0, false); }
-        else if (hv == 1) { if (p2) MSBT_DIRECT_LAUNCH(2, 1, true); else MSBT_DIRECT_LAUNCH(2, 1, false); }
-        else { if (p2) MSBT_DIRECT_LAUNCH(2, 2, true); else MSBT_DIRECT_LAUNCH(2, 2, false); }
-    }
-#undef MSBT_DIRECT_LAUNCH
-    LAUNCH_CHECK(ctx);
+    rc = launch_direct(ctx, d_packed, d_run_ends, (const DevGenome *)ctx->d_scratch, n_genomes, tiles, spec, d_filters, nullptr, stream);
+    if (rc) return rc;
     return MSBT_OK;
 }
 
