@@ -301,6 +301,8 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
         const uint32_t tile_mask = (1u << P.tile_log2) - 1u;
         const uint32_t tiles_here = 1u << P.tiles_per_bucket_log2;
         bool store_pending = false;
+        uint64_t evict_first;
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(evict_first));
         uint4 e[FU_REG_QUADS];  // every ring reservation is a whole quad, so validity is per 16-byte group
         uint32_t n_raw = 0, first = 0;
 
@@ -393,7 +395,8 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
                 const uint32_t bytes = (uint32_t)(nw * 8);
                 if (((bytes & 15) == 0) && ((((uintptr_t)dst) & 15) == 0)) {
                     if (tid == 0) {
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(saddr), "r"(bytes) : "memory");
+                        // evict_first: the finished tile streams to HBM and must not push the ring out of L2
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(saddr), "r"(bytes), "l"(evict_first) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
                     store_pending = true;
