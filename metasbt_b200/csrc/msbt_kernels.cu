@@ -42,6 +42,7 @@ struct msbt_ctx {
     bool stage_busy;
     bool tiled_attr_set;  // dynamic-smem opt-in done for this device
     bool fused_attr_set;
+    bool phased_attr_set;
 };
 
 static int fail(msbt_ctx *ctx, int code, const char *fmt, ...) {
@@ -588,6 +589,7 @@ overflow_fixup_kernel(const unsigned long long *__restrict__ ovf_count, const ui
 }
 
 #include "msbt_fused.cuh"
+#include "msbt_phased.cuh"
 
 #ifdef MSBT_FU_TRACE
 extern "C" int msbt_debug_trace(unsigned long long *out24, int reset) {
@@ -816,9 +818,15 @@ static int launch_direct(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t
 }
 
 // Variant 3: the fused persistent kernel of msbt_fused.cuh.  Returns 1 if the geometry does not apply.
-static int build_fused(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *d_run_ends, const std::vector<DevGenome> &dg,
-                       uint64_t tiles, uint64_t fchunks, const KmerSpec &spec, uint64_t words, uint64_t *d_filters,
-                       cudaStream_t stream) {
+static int build_fused(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *d_run_ends, const std::vector<DevGenome> &dg_in,
+                       uint64_t tiles, const KmerSpec &spec, uint64_t words, uint64_t *d_filters, cudaStream_t stream) {
+    std::vector<DevGenome> dg(dg_in);
+    uint64_t fchunks = 0;
+    for (DevGenome &g : dg) {
+        g.fchunk_begin = (uint32_t)fchunks;
+        fchunks += ((uint64_t)g.n_bases + FU_CHUNK_BASES - 1) / FU_CHUNK_BASES;
+        if (fchunks >> 31) return 1;
+    }
     const uint32_t n_genomes = (uint32_t)dg.size();
     const uint64_t num_bits = spec.pos.num_bits;
     const uint32_t k = spec.k;
@@ -916,6 +924,112 @@ static int build_fused(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *
     return launch_direct(ctx, d_packed, d_run_ends, P.genomes, n_genomes, tiles, spec, d_filters, P.dirty, stream);
 }
 
+// Variant 4: the phased persistent kernel of msbt_phased.cuh.  Returns 1 if the geometry does not apply.
+static int build_phased(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *d_run_ends, const std::vector<DevGenome> &dg_in,
+                        uint64_t tiles, const KmerSpec &spec, uint64_t words, uint64_t *d_filters, cudaStream_t stream) {
+    std::vector<DevGenome> dg(dg_in);
+    uint64_t chunks = 0;
+    for (DevGenome &g : dg) {
+        g.fchunk_begin = (uint32_t)chunks;
+        chunks += ((uint64_t)g.n_bases + PH_CHUNK_BASES - 1) / PH_CHUNK_BASES;
+        if (chunks >> 31) return 1;
+    }
+    const uint32_t n_genomes = (uint32_t)dg.size();
+    const uint64_t num_bits = spec.pos.num_bits;
+    const uint32_t k = spec.k;
+    uint32_t shift = 7;  // a tile is at least 128 bits (one 16-byte bulk store)
+    while (((num_bits + (1ull << shift) - 1) >> shift) > PH_MAX_BUCKETS) shift++;
+    const uint32_t NB = (uint32_t)((num_bits + (1ull << shift) - 1) >> shift);
+    if (chunks == 0 || ((uint64_t)n_genomes * NB >> 28)) return 1;  // counters: 4 B per (genome, bucket)
+
+    PhasedParams P;
+    memset(&P, 0, sizeof(P));
+    P.bucket_shift = shift;
+    P.NB = NB;
+    P.cap = (PH_AREA_WORDS / (NB + 1)) & ~3u;
+    P.quads = P.cap / 4;
+    P.tile_log2 = std::min(shift, PH_TILE_LOG2);
+    P.tiles_per_bucket_log2 = shift - P.tile_log2;
+    P.words = words;
+    P.n_genomes = n_genomes;
+    P.n_chunks_total = (uint32_t)chunks;
+    P.n_items = n_genomes * NB;
+
+    uint64_t max_kmers = 0;
+    for (const DevGenome &g : dg) max_kmers = std::max<uint64_t>(max_kmers, g.n_bases >= k ? (uint64_t)g.n_bases - k + 1 : 0);
+    {
+        // positions are uniform over [0, modulus): expected entries per bucket + 8 sigma; every chunk that touches a
+        // bucket may add up to 3 pad entries, a full staging row spills 4 entries per k-mer (rare)
+        const double frac = std::min(1.0, (double)(1ull << shift) / (double)spec.pos.modulus);
+        const double e = (double)max_kmers * frac;
+        const double nch = (double)((max_kmers + PH_CHUNK_BASES - 1) / PH_CHUNK_BASES);
+        const double touched = nch * std::min(1.0, (double)PH_CHUNK_BASES * frac);
+        uint64_t cap = (uint64_t)(1.03 * e + 8.0 * sqrt(e) + 3.0 * touched + 64.0);
+        cap = std::min<uint64_t>(cap, max_kmers + 3 * (uint64_t)nch + 8);
+        cap = (cap + 7) / 8 * 8;
+        if ((cap * NB) >> 32) return 1;
+        P.gcap = (uint32_t)cap;
+    }
+    const uint64_t slot_bytes = (uint64_t)NB * P.gcap * 4;
+    P.ring = (uint32_t)std::max<uint64_t>(2, std::min<uint64_t>(4, (72ull << 20) / std::max<uint64_t>(slot_bytes, 1)));
+
+    // scratch: [genome table][sync 256 B][done][consumed][dirty][gcnt n_genomes x NB] | [gbuf ring x NB x gcap]
+    const size_t t_b = align_up(sizeof(DevGenome) * n_genomes, 256);
+    const size_t sync_off = t_b;
+    const size_t done_off = sync_off + 256;
+    const size_t cons_off = done_off + (size_t)n_genomes * 4;
+    const size_t dirty_off = cons_off + (size_t)n_genomes * 4;
+    const size_t gcnt_off = align_up(dirty_off + (size_t)n_genomes * 4, 16);
+    const size_t zero_end = gcnt_off + (size_t)n_genomes * NB * 4;
+    const size_t gbuf_off = align_up(zero_end, 256);
+    const size_t total = gbuf_off + (size_t)P.ring * slot_bytes;
+    int rc = ensure_scratch(ctx, total);
+    if (rc) return rc == MSBT_ENOMEM ? 1 : rc;
+    size_t table_b = 0;
+    rc = stage_genome_table(ctx, dg, &table_b, stream);
+    if (rc) return rc;
+    char *S = (char *)ctx->d_scratch;
+    P.packed = d_packed;
+    P.run_ends = d_run_ends;
+    P.genomes = (const DevGenome *)S;
+    P.sync = (uint32_t *)(S + sync_off);
+    P.done = (uint32_t *)(S + done_off);
+    P.consumed = (uint32_t *)(S + cons_off);
+    P.dirty = (uint32_t *)(S + dirty_off);
+    P.gcnt = (uint32_t *)(S + gcnt_off);
+    P.gbuf = (uint32_t *)(S + gbuf_off);
+    P.filters = d_filters;
+    CU_TRY(ctx, cudaMemsetAsync(S + sync_off, 0, zero_end - sync_off, stream));
+
+    if (!ctx->phased_attr_set) {
+#define MSBT_PH_ATTR(KW, HV) \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_phased_kernel<KW, HV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PH_SMEM_BYTES)); \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_phased_kernel<KW, HV, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PH_SMEM_BYTES)); \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_phased_kernel<KW, HV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PH_SMEM_BYTES)); \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_phased_kernel<KW, HV, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PH_SMEM_BYTES));
+        MSBT_PH_ATTR(1, 0) MSBT_PH_ATTR(2, 1) MSBT_PH_ATTR(2, 2)
+#undef MSBT_PH_ATTR
+        ctx->phased_attr_set = true;
+    }
+    const int grid = ctx->num_sms;
+#define MSBT_PH_LAUNCH(KW, HV)                                                                                     \
+    {                                                                                                              \
+        if (p2 && full) kmer_bloom_phased_kernel<KW, HV, true, true><<<grid, PH_THREADS, PH_SMEM_BYTES, stream>>>(P, spec);   \
+        else if (p2) kmer_bloom_phased_kernel<KW, HV, true, false><<<grid, PH_THREADS, PH_SMEM_BYTES, stream>>>(P, spec);     \
+        else if (full) kmer_bloom_phased_kernel<KW, HV, false, true><<<grid, PH_THREADS, PH_SMEM_BYTES, stream>>>(P, spec);   \
+        else kmer_bloom_phased_kernel<KW, HV, false, false><<<grid, PH_THREADS, PH_SMEM_BYTES, stream>>>(P, spec);            \
+    }
+    const int hv = msbt_hash_variant(k);
+    const bool p2 = spec.pos.pow2 != 0, full = spec.pos.modulus <= spec.pos.num_bits;
+    if (hv == 0) MSBT_PH_LAUNCH(1, 0)
+    else if (hv == 1) MSBT_PH_LAUNCH(2, 1)
+    else MSBT_PH_LAUNCH(2, 2)
+#undef MSBT_PH_LAUNCH
+    LAUNCH_CHECK(ctx);
+    // genomes whose ring buckets overflowed (skewed inputs) are completed by the direct kernel
+    return launch_direct(ctx, d_packed, d_run_ends, P.genomes, n_genomes, tiles, spec, d_filters, P.dirty, stream);
+}
+
 extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *d_run_ends,
                                      const msbt_genome_desc *h_descs, uint32_t n_genomes, uint32_t k,
                                      uint64_t seed, uint64_t modulus, uint64_t num_bits, uint32_t min_abund,
@@ -930,7 +1044,7 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
     if (n_genomes == 0) return MSBT_OK;
     if (!d_packed || !d_run_ends || !h_descs || !d_filters) return fail(ctx, MSBT_EINVAL, "null pointer argument");
     if (min_abund >= 2 && k > 32) return fail(ctx, MSBT_EINVAL, "min_abund >= 2 supports k <= 32 only (k=%u)", k);
-    if (variant < 0 || variant > 3) return fail(ctx, MSBT_EINVAL, "unknown variant %d", variant);
+    if (variant < 0 || variant > 4) return fail(ctx, MSBT_EINVAL, "unknown variant %d", variant);
     CU_TRY(ctx, cudaSetDevice(ctx->device));
 
     KmerSpec spec;
@@ -939,7 +1053,7 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
 
     // device genome table with tile prefix
     std::vector<DevGenome> dg(n_genomes);
-    uint64_t tiles = 0, fchunks = 0;
+    uint64_t tiles = 0;
     uint64_t max_bases = 0;
     for (uint32_t i = 0; i < n_genomes; i++) {
         const msbt_genome_desc &d = h_descs[i];
@@ -950,9 +1064,8 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
         dg[i].n_bases = (uint32_t)d.n_bases;
         dg[i].n_runs = d.n_runs;
         dg[i].tile_begin = (uint32_t)tiles;
-        dg[i].fchunk_begin = (uint32_t)fchunks;
+        dg[i].fchunk_begin = 0;
         tiles += (d.n_bases + TILE_BASES - 1) / TILE_BASES;
-        fchunks += (d.n_bases + FU_CHUNK_BASES - 1) / FU_CHUNK_BASES;
         max_bases = std::max<uint64_t>(max_bases, d.n_bases);
         if (tiles >> 31) return fail(ctx, MSBT_EINVAL, "batch too large (%llu tiles)", (unsigned long long)tiles);
     }
@@ -969,11 +1082,16 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
     if (variant >= 2 && !tiled_ok)
         return fail(ctx, MSBT_EINVAL, "variant %d needs distinct filter_index values, min_abund <= 1 and num_bits <= 2^32", variant);
     const bool fused_ok = tiled_ok && num_bits >= (1ull << 17);
-    if (variant == 3 && !fused_ok) return fail(ctx, MSBT_EINVAL, "variant 3 needs num_bits >= 2^17");
-    if (fused_ok && (variant == 3 || (variant == 0 && num_bits >= (1ull << 26)))) {
-        const int rc = build_fused(ctx, d_packed, d_run_ends, dg, tiles, fchunks, spec, words, d_filters, stream);
+    if (variant >= 3 && !fused_ok) return fail(ctx, MSBT_EINVAL, "variant %d needs num_bits >= 2^17", variant);
+    if (fused_ok && variant == 4) {
+        const int rc = build_phased(ctx, d_packed, d_run_ends, dg, tiles, spec, words, d_filters, stream);
         if (rc <= 0) return rc;
-        if (variant == 3 && fchunks) return fail(ctx, MSBT_EINVAL, "variant 3: geometry not applicable to this batch");
+        if (tiles) return fail(ctx, MSBT_EINVAL, "variant 4: geometry not applicable to this batch");
+    }
+    if (fused_ok && (variant == 3 || (variant == 0 && num_bits >= (1ull << 26)))) {
+        const int rc = build_fused(ctx, d_packed, d_run_ends, dg, tiles, spec, words, d_filters, stream);
+        if (rc <= 0) return rc;
+        if (variant == 3 && tiles) return fail(ctx, MSBT_EINVAL, "variant 3: geometry not applicable to this batch");
     }
     const bool tiled = tiled_ok && (variant == 2 || (variant == 0 && num_bits >= (1ull << TB_TILE_LOG2)));
     if (tiled) {

@@ -25,7 +25,7 @@ def build(ctx, fastas, k, num_bits, min_abund=1, modulus=None, variant=0):
     return out, [to_np(out[i, :w]) for i in range(len(fastas))]
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("k", [1, 9, 21, 31, 32, 33, 51, 64])
 def test_makebf_messy_batches(ctx, oracle, k, variant):
     rng = random.Random(k)
@@ -33,7 +33,7 @@ def test_makebf_messy_batches(ctx, oracle, k, variant):
               for _ in range(9)]
     fastas += [b"", b">empty\n", b">short\nACG\n"]
     sizes = ((1 << 16, None), (100003, None), (1 << 14, 20011), (20011, 1 << 14))
-    if variant == 3:  # the fused kernel needs num_bits >= 2^17
+    if variant >= 3:  # the fused / phased kernels need num_bits >= 2^17
         sizes = ((1 << 17, None), (200003, None), (1 << 18, 300007), (300007, 1 << 18))
     for num_bits, modulus in sizes:
         _, got = build(ctx, fastas, k, num_bits, modulus=modulus, variant=variant)
@@ -41,12 +41,12 @@ def test_makebf_messy_batches(ctx, oracle, k, variant):
             assert np.array_equal(g, oracle.makebf(f, k, num_bits, 1, 0, modulus))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("num_bits", [64, 1000, (1 << 19) - 64, 1 << 19, (1 << 19) + 64, (1 << 21) + 192, 3 * (1 << 20) + 8])
 def test_makebf_filter_sizes_and_tile_edges(ctx, oracle, num_bits, variant):
     """Filter sizes around the 64 KiB tile boundary, odd word counts, tiny filters."""
-    if variant == 3 and num_bits < (1 << 17):
-        pytest.skip("the fused kernel needs num_bits >= 2^17")
+    if variant >= 3 and num_bits < (1 << 17):
+        pytest.skip("the fused / phased kernels need num_bits >= 2^17")
     rng = random.Random(num_bits)
     fastas = [util.messy_fasta(rng, 3, 4000, "ACGTN") for _ in range(5)]
     _, got = build(ctx, fastas, 21, num_bits, variant=variant)
@@ -54,7 +54,7 @@ def test_makebf_filter_sizes_and_tile_edges(ctx, oracle, num_bits, variant):
         assert np.array_equal(g, oracle.makebf(f, 21, num_bits))
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_makebf_skewed_inputs_overflow_path(ctx, oracle, variant):
     """Low-complexity genomes put (almost) every k-mer into a few buckets: the staging slots and the
     scratch buckets overflow and the fix-up pass must restore every bit."""
@@ -83,7 +83,7 @@ def test_makebf_min_abundance_k_gt_32_rejected(ctx):
         build(ctx, [b">r\n" + b"ACGT" * 50 + b"\n"], 33, 1 << 12, min_abund=2)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 @pytest.mark.parametrize("k,num_bits", [(31, 1 << 22), (21, 1 << 24), (51, 1 << 22), (31, 1 << 27)])
 def test_makebf_synthetic_genomes(ctx, oracle, k, num_bits, variant):
     from metasbt_b200 import ops
@@ -101,11 +101,11 @@ def test_makebf_synthetic_genomes(ctx, oracle, k, num_bits, variant):
         assert np.array_equal(ops.pack_fasta(fa, k).words, packed[g].words)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_makebf_filter_index_and_rebuild(ctx, oracle, variant):
     """Filters are fully rewritten (stale bits cleared) and filter_index routes outputs."""
     from metasbt_b200 import ops
-    k, num_bits = 15, (1 << 17) + 64 if variant == 3 else 1 << 14
+    k, num_bits = 15, (1 << 17) + 64 if variant >= 3 else 1 << 14
     rng = random.Random(2)
     fastas = [util.messy_fasta(rng, 2, 800, "ACGT") for _ in range(3)]
     packed = [ops.pack_fasta(f, k) for f in fastas]
@@ -204,12 +204,12 @@ def _kats():
         return json.load(f)
 
 
-@pytest.mark.parametrize("variant", [1, 2, 3])
+@pytest.mark.parametrize("variant", [1, 2, 3, 4])
 def test_committed_known_answers(ctx, variant):
     """The committed golden vectors, without the oracle in the loop."""
     from metasbt_b200 import ops
     for kat in _kats():
-        if (kat["min"] > 1 and variant >= 2) or (variant == 3 and kat["num_bits"] < (1 << 17)):
+        if (kat["min"] > 1 and variant >= 2) or (variant >= 3 and kat["num_bits"] < (1 << 17)):
             continue
         _, got = build(ctx, [kat["fasta"].encode()], kat["k"], kat["num_bits"], min_abund=kat["min"], modulus=kat["modulus"],
                        variant=variant if kat["min"] == 1 else 0)

@@ -2,9 +2,9 @@
 # usage: tools/gpu_round.sh <tag>   (runs on the GPU box from the repo root)
 tag=${1:-x}
 mkdir -p gpurun_out
-timeout 150 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_$tag.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_$tag.log
-for v in 3 2; do
-  timeout 60 python bench.py --genomes 200 --steps 3 --warmup 3 --variant $v --no-e2e --no-cpu-baseline > gpurun_out/bench_${tag}_v$v.log 2> gpurun_out/bench_${tag}_v$v.err; echo "bench v$v rc=$?"
+timeout -k 5 ${PYTEST_TIMEOUT:-150} python -m pytest tests -m gpu -x -q ${PYTEST_ARGS:-} > gpurun_out/pytest_$tag.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_$tag.log
+for v in ${VARIANTS:-4 3}; do
+  timeout -k 5 60 python bench.py --genomes 200 --steps 3 --warmup 3 --variant $v --no-e2e --no-cpu-baseline > gpurun_out/bench_${tag}_v$v.log 2> gpurun_out/bench_${tag}_v$v.err; echo "bench v$v rc=$?"
   python - <<PY
 import json
 try:
