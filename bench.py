@@ -48,11 +48,12 @@ def parse_args():
     ap.add_argument("--genome-bp", type=int, default=GENOME_BP)
     ap.add_argument("--filter-bits", type=int, default=FILTER_BITS)
     ap.add_argument("--kmer", type=int, default=K)
-    ap.add_argument("--variant", type=int, default=0, help="K1 kernel variant (0 auto, 1 direct, 2 L2-staged)")
+    ap.add_argument("--variant", type=int, default=0, help="K1 kernel variant (0 auto, 1 direct, 2 tiled, 3 fused, 4 phased)")
     ap.add_argument("--e2e-genomes", type=int, default=32, help="genomes per end-to-end step (host buffers)")
     ap.add_argument("--cpu-genomes", type=int, default=0, help="genomes in the CPU-baseline sample (0 = 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the K2/K3/K4 measurements (tools/bench_ops.py)")
     return ap.parse_args()
 
 
@@ -180,6 +181,17 @@ class ClockSampler:
 # ------------------------------------------------------------------ our arm
 
 
+def ncu_traffic_per_genome():
+    """DRAM bytes (read + write) per genome of the K1 kernel from the committed `ncu --set full` capture
+    (profiles/k1_ncu_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep), or None."""
+    p = os.path.join(ROOT, "profiles", "k1_ncu_traffic.json")
+    try:
+        d = json.load(open(p))
+        return float(d["dram_bytes_per_genome"]), d.get("source", "")
+    except Exception:
+        return None, ""
+
+
 def measured_peak_gbs():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -275,8 +287,9 @@ def run_ours(args):
         e2e = {"value": ne * G * world * e2e_steps / float(te.item()) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(sub.h2d_bytes), "d2h_bytes_per_step": int(h_out.numel() * 8),
                "genomes_per_step": ne, "steps": e2e_steps,
-               "note": "packed genomes H2D + build + full filters D2H each step; bounded by the %d MiB/filter PCIe copy"
-                       % (m // 8 // 2 ** 20)}
+               "pcie_gbs": (int(sub.h2d_bytes) + int(h_out.numel() * 8)) * e2e_steps / float(te.item()) / 1e9,
+               "note": "packed genomes pinned-host->device + build + every filter device->pinned-host each step; "
+                       "PCIe-bound by the %d MiB/filter output (27x the input)" % (m // 8 // 2 ** 20)}
         assert int(h_out[0, 0].item()) == int(filters[0, 0].item()) or rank != 0 or True
         del d_out, h_out, sub
 
@@ -289,19 +302,34 @@ def run_ours(args):
     algo_bytes_genome = (G + 3) // 4 + m // 8
     per_genome_us = ms / args.steps / N * 1e3
     achieved = algo_bytes_genome / (per_genome_us * 1e-6) / 1e9
+    traffic_genome, traffic_src = ncu_traffic_per_genome()
+    launches_per_step = max(1, launches // max(args.steps, 1))
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": config_dict(args, world),
         "e2e": e2e, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
-                     "kernel": "kmer_bloom build (memset + scatter kernels of msbt_kmer_bloom_build)",
-                     "algorithmic_bytes_per_genome": algo_bytes_genome, "us_per_genome": per_genome_us},
+                     "traffic": (traffic_genome * N if traffic_genome else None), "peak_source": peak_src,
+                     "kernel": "kmer_bloom_fused_kernel (msbt_kmer_bloom_build, one launch per %d-genome batch; "
+                               "%d launches per step incl. the early-exit redo pass)" % (N, launches_per_step),
+                     "algorithmic_bytes_per_launch": algo_bytes_genome * N,
+                     "algorithmic_bytes_per_genome": algo_bytes_genome, "us_per_genome": per_genome_us,
+                     "traffic_source": traffic_src},
         "clocks": clocks.summary(),
         "lib": os.path.relpath(_lib.loaded_path(), ROOT),
         "check": {"filter0_popcount": pc},
     }
+    if not args.no_secondary and world == 1:
+        # the other rows of SURVEY.md 8a (union, popcount distances, MAG queries/s) at 1,024 leaves, 2^28-bit filters
+        try:
+            del filters, batch
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_ops
+            line["secondary"] = bench_ops.run(ctx, peak_gbs=peak)
+        except Exception as exc:  # the headline line must survive a failure here
+            line["secondary"] = {"error": repr(exc)}
     if not args.no_cpu_baseline and world == 1:
         cores = os.cpu_count() or 1
         n_cpu = args.cpu_genomes or 8 * cores

@@ -1647,43 +1647,94 @@ bitslice_kernel(const uint64_t *const *__restrict__ leaves, uint32_t n_leaves, u
     }
 }
 
-// Sliced probe: CTA = (leaf-word group, query).  Thread owns one u32 column word (32 leaves) and
-// walks the query's positions; vertical (bit-plane) counters absorb 15 rows between flushes.
-__global__ void __launch_bounds__(128)
+// Sliced probe.  CTA (x = block of QS_WARPS sub-chunks of positions, y = group of 32 column words = 1024 leaves,
+// z = query).  A warp walks one sub-chunk of the query's (ascending) positions that fall into [row_begin, row_end):
+// per position the 32 lanes read one 128-byte row segment (coalesced), and each lane adds its 32 one-bit leaf
+// columns into 12 vertical (bit-plane) counters -- seven rows are first compressed 7 -> 3 planes with four
+// LOP3 full adders, then rippled into the planes (32 LOP3 per 7 rows per 32 leaves).  Planes are unpacked once
+// per sub-chunk into shared-memory leaf counters, and once per CTA into hits[] with global atomics.
+// HBM traffic = one row segment per (position, leaf group): the algorithmic nP * ceil(L/8) bytes of SURVEY 8d.
+constexpr int QS_WARPS = 8;
+constexpr uint32_t QS_SUB = 4088;  // positions per warp sub-chunk: 7 * 584 <= 4095 (12 planes)
+
+__device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t &sum, uint32_t &carry) {
+    uint32_t s_, c_;  // the outputs may alias the inputs
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s_) : "r"(a), "r"(b), "r"(c));  // a ^ b ^ c
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(c_) : "r"(a), "r"(b), "r"(c));  // majority
+    sum = s_;
+    carry = c_;
+}
+
+__global__ void __launch_bounds__(QS_WARPS * 32)
 query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint32_t lw, uint64_t row_begin, uint64_t row_end,
                     const uint32_t *__restrict__ positions, const unsigned long long *__restrict__ q_off,
                     uint32_t *__restrict__ hits) {
-    const uint32_t q = blockIdx.y;
-    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (col >= lw) return;
-    const uint64_t b = q_off[q], e = q_off[q + 1];
-    uint32_t cnt[32];
+    __shared__ uint32_t sm_hits[1024];
+    __shared__ unsigned long long sm_range[2];
+    const uint32_t q = blockIdx.z;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t col = blockIdx.y * 32 + lane;
+    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) sm_hits[i] = 0;
+    if (threadIdx.x == 0) {
+        // positions are ascending: the ones inside [row_begin, row_end) form one contiguous range
+        const unsigned long long b = q_off[q], e = q_off[q + 1];
+        unsigned long long lo = b, hi = e;
+        while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1; if (positions[mid] < row_begin) lo = mid + 1; else hi = mid; }
+        sm_range[0] = lo;
+        hi = e;
+        while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1; if (positions[mid] < row_end) lo = mid + 1; else hi = mid; }
+        sm_range[1] = lo;
+    }
+    __syncthreads();
+    const unsigned long long rb = sm_range[0], re = sm_range[1];
+    const unsigned long long sub_b = rb + ((unsigned long long)blockIdx.x * QS_WARPS + warp) * QS_SUB;
+    if (sub_b < re) {
+        const unsigned long long sub_e = min(sub_b + (unsigned long long)QS_SUB, re);
+        const uint32_t *__restrict__ colp = sliced + (col < lw ? col : 0);
+        const bool live = col < lw;
+        uint32_t P[12];
 #pragma unroll
-    for (int i = 0; i < 32; i++) cnt[i] = 0;
-    uint32_t p0 = 0, p1 = 0, p2 = 0, p3 = 0;  // bit planes of a 4-bit vertical counter
-    uint32_t pending = 0;
-    for (uint64_t i = b; i < e; i++) {
-        const uint64_t p = positions[i];
-        if (p < row_begin || p >= row_end) continue;
-        uint32_t x = __ldg(sliced + (p - row_begin) * lw + col);
-        // ripple-carry add of the 1-bit row x into planes p0..p3
-        uint32_t c0 = p0 & x; p0 ^= x;
-        uint32_t c1 = p1 & c0; p1 ^= c0;
-        uint32_t c2 = p2 & c1; p2 ^= c1;
-        p3 ^= c2;
-        if (++pending == 15) {
+        for (int i = 0; i < 12; i++) P[i] = 0;
+        for (unsigned long long base = sub_b; base < sub_e; base += 28) {
+            // 28 positions per round: one coalesced load of positions, then 4 groups of 7 independent row reads
+            const unsigned long long idx = base + lane;
+            const uint32_t mypos = (lane < 28 && idx < sub_e) ? positions[idx] : 0xFFFFFFFFu;
 #pragma unroll
-            for (int l = 0; l < 32; l++)
-                cnt[l] += ((p0 >> l) & 1u) + 2u * ((p1 >> l) & 1u) + 4u * ((p2 >> l) & 1u) + 8u * ((p3 >> l) & 1u);
-            p0 = p1 = p2 = p3 = 0;
-            pending = 0;
+            for (int g7 = 0; g7 < 4; g7++) {
+                uint32_t x[7];
+#pragma unroll
+                for (int j = 0; j < 7; j++) {
+                    const uint32_t p = __shfl_sync(0xffffffffu, mypos, g7 * 7 + j);
+                    x[j] = (p != 0xFFFFFFFFu && live) ? __ldg(colp + ((uint64_t)p - row_begin) * lw) : 0u;
+                }
+                uint32_t sa, ca, sb, cb, ones, cc, twos, fours;
+                full_add(x[0], x[1], x[2], sa, ca);
+                full_add(x[3], x[4], x[5], sb, cb);
+                full_add(sa, sb, x[6], ones, cc);
+                full_add(ca, cb, cc, twos, fours);
+                uint32_t k;
+                k = P[0] & ones; P[0] ^= ones;
+                full_add(P[1], twos, k, P[1], k);
+                full_add(P[2], fours, k, P[2], k);
+#pragma unroll
+                for (int i = 3; i < 12; i++) { const uint32_t t = P[i] & k; P[i] ^= k; k = t; }
+            }
+        }
+        if (live) {
+#pragma unroll 4
+            for (int l = 0; l < 32; l++) {
+                uint32_t c = 0;
+#pragma unroll
+                for (int i = 0; i < 12; i++) c |= ((P[i] >> l) & 1u) << i;
+                if (c) atomicAdd(sm_hits + lane * 32 + l, c);
+            }
         }
     }
-#pragma unroll
-    for (int l = 0; l < 32; l++) {
-        uint32_t c = cnt[l] + ((p0 >> l) & 1u) + 2u * ((p1 >> l) & 1u) + 4u * ((p2 >> l) & 1u) + 8u * ((p3 >> l) & 1u);
-        const uint32_t leaf = col * 32 + l;
-        if (leaf < n_leaves) hits[(uint64_t)q * n_leaves + leaf] = c;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) {
+        const uint32_t leaf = blockIdx.y * 1024 + i;
+        const uint32_t c = sm_hits[i];
+        if (c && leaf < n_leaves) atomicAdd(hits + (uint64_t)q * n_leaves + leaf, c);
     }
 }
 
@@ -1731,8 +1782,16 @@ extern "C" int msbt_query_batch_sliced(msbt_ctx *ctx, const uint32_t *d_sliced, 
     rc = stage_end(ctx, stream);
     if (rc) return rc;
     const uint32_t lw = (n_leaves + 31) / 32;
-    query_sliced_kernel<<<dim3((lw + 127) / 128, n_queries), 128, 0, stream>>>(d_sliced, n_leaves, lw, row_begin, row_end,
-                                                                             d_positions, d_off, d_hits);
+    uint64_t max_pos = 0;
+    for (uint32_t q = 0; q < n_queries; q++) max_pos = std::max<uint64_t>(max_pos, h_query_offsets[q + 1] - h_query_offsets[q]);
+    if (max_pos == 0) { CU_TRY(ctx, cudaMemsetAsync(d_hits, 0, (size_t)n_queries * n_leaves * 4, stream)); return MSBT_OK; }
+    // hits accumulate with atomics: clear first (partial results of other bit ranges are summed by the caller)
+    CU_TRY(ctx, cudaMemsetAsync(d_hits, 0, (size_t)n_queries * n_leaves * 4, stream));
+    const uint64_t per_cta = (uint64_t)QS_WARPS * QS_SUB;
+    const uint32_t gx = (uint32_t)((max_pos + per_cta - 1) / per_cta), gy = (lw + 31) / 32;
+    if (gy > 65535) return fail(ctx, MSBT_EINVAL, "query_batch_sliced: too many leaves");
+    query_sliced_kernel<<<dim3(gx, gy, n_queries), QS_WARPS * 32, 0, stream>>>(d_sliced, n_leaves, lw, row_begin, row_end,
+                                                                                 d_positions, d_off, d_hits);
     LAUNCH_CHECK(ctx);
     return MSBT_OK;
 }

@@ -218,3 +218,29 @@ def test_committed_known_answers(ctx, variant):
         q, _ = build(ctx, [kat["fasta"].encode()], kat["k"], kat["num_bits"], modulus=kat["modulus"])
         pos = ctx.extract_positions(q[0], kat["num_bits"])
         assert [int(x) for x in pos.cpu().numpy().view(np.uint32)] == kat["query_positions"], kat["name"]
+
+
+def test_query_sliced_many_leaves_and_chunks(ctx, oracle):
+    """Bit-sliced probe with > 1024 leaves (several column groups), queries long enough for several warp sub-chunks
+    and CTAs, an empty query, and a split into three bit-range shards that must add up."""
+    from metasbt_b200 import ops
+    num_bits, n_leaves = 1 << 17, 1100
+    rng = np.random.default_rng(7)
+    w = ops.filter_words(num_bits)
+    host = rng.integers(0, 1 << 63, size=(n_leaves, w), dtype=np.int64) & rng.integers(0, 1 << 63, size=(n_leaves, w), dtype=np.int64)
+    dev = torch.from_numpy(host).to(ctx.device)
+    leaves = [dev[i] for i in range(n_leaves)]
+    leaf_np = [host[i].view(np.uint64) for i in range(n_leaves)]
+    queries = [np.sort(rng.choice(num_bits, size=n, replace=False)).astype(np.uint64) for n in (70000, 9000, 0, 33)]
+    positions = [torch.from_numpy(q.astype(np.uint32).view(np.int32)).to(ctx.device) for q in queries]
+    want = np.stack([oracle.query_hits(q, leaf_np) for q in queries])
+    sliced = ctx.bitslice(leaves, 0, num_bits)
+    got = ctx.query_batch_sliced(sliced, n_leaves, 0, num_bits, positions).cpu().numpy()
+    assert np.array_equal(got.astype(np.uint64), want)
+    cuts = [0, 40000 // 32 * 32, 90000 // 32 * 32, num_bits]
+    total = None
+    for b, e in zip(cuts, cuts[1:]):
+        part = ctx.query_batch_sliced(ctx.bitslice(leaves, b, e), n_leaves, b, e, positions)
+        total = part if total is None else total + part
+    assert np.array_equal(total.cpu().numpy().astype(np.uint64), want)
+    assert np.array_equal(ctx.query_batch(leaves[:37], positions).cpu().numpy().astype(np.uint64), want[:, :37])

@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""Secondary measurements for the other rows of SURVEY.md 8a (K2 union, K3/K3' popcounts, K4 query) on one GPU.
+Used by bench.py (key "secondary" of its JSON line) and runnable alone:
+
+    python tools/bench_ops.py [--leaves 1024] [--filter-bits 268435456] [--mags 64]
+
+Every number is timed with CUDA events on the launching stream after a warm-up call; inputs are far larger
+than L2.  `frac` = algorithmic bytes / time / measured HBM peak.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def _time(fn, reps=3):
+    import torch
+    fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps * 1e-3  # seconds
+
+
+def run(ctx, n_leaves=1024, filter_bits=1 << 28, n_mags=64, genome_bp=5_000_000, mag_bp=2_000_000, k=31, peak_gbs=6537.6):
+    import torch
+    from metasbt_b200 import ops, synth
+    dev = ctx.device
+    m, L = filter_bits, n_leaves
+    fbytes = m // 8
+    out = {"config": {"leaves": L, "filter_bits": m, "mags": n_mags, "genome_bp": genome_bp, "mag_bp": mag_bp, "kmer_size": k}}
+
+    def entry(seconds, algo_bytes, **extra):
+        d = {"ms": seconds * 1e3, "algorithmic_GB": algo_bytes / 1e9, "GBps": algo_bytes / seconds / 1e9,
+             "frac_of_hbm_peak": algo_bytes / seconds / 1e9 / peak_gbs}
+        d.update(extra)
+        return d
+
+    # leaves: related genomes (species ancestor + 1 % SNPs), so that similarities and hits are non-trivial
+    words = []
+    for g in range(L):
+        codes = synth.genome_codes(0xA11CE000 + g // 8, genome_bp, dev)
+        r = synth.splitmix64(((0x5EED0000 + g) << 32) ^ torch.arange(genome_bp, dtype=torch.int64, device=dev))
+        snp = (synth._lsr(r, 8) % 1000) < 10
+        codes = torch.where(snp, (codes + 1 + synth._lsr(r, 40) % 3) % 4, codes)
+        words.append(synth.pack_codes_device(codes))
+    batch = ops.GenomeBatch.from_device_words(words, [genome_bp] * L, dev)
+    del words
+    leaves = ctx.alloc_filters(L, m)
+    t = _time(lambda: ctx.build_filters(batch, k, m, out=leaves), reps=2)
+    out["K1_build_leaves"] = entry(t, L * ((genome_bp + 3) // 4 + fbytes), Mbp_per_s=L * genome_bp / t / 1e6)
+    rows = [leaves[i] for i in range(L)]
+
+    # K2: cluster filter = OR of C children
+    C = min(100, L)
+    t = _time(lambda: ctx.bf_or(rows[:C], m))
+    out["K2_or_%d" % C] = entry(t, (C + 1) * fbytes)
+    # K3': density numerators of all leaves
+    t = _time(lambda: ctx.bf_popcount(rows, m))
+    out["K3p_popcount_%d" % L] = entry(t, L * fbytes)
+    # K3: one focus against all others (intersection and union in one pass)
+    t = _time(lambda: ctx.bf_dist(rows[0], rows[1:], m))
+    out["K3_dist_1v%d" % (L - 1)] = entry(t, L * fbytes, pairs_per_s=(L - 1) / t)
+    # K3 all pairs inside one species-sized cluster
+    A = min(64, L)
+    t = _time(lambda: ctx.bf_allpairs(rows[:A], m))
+    out["K3_allpairs_%d" % A] = entry(t, A * fbytes, pairs_per_s=A * (A - 1) / 2 / t,
+                                      note="bytes = each filter read once (lower bound); the kernel re-reads tiles")
+
+    # K4: MAGs = 5 % mutated prefixes of leaves
+    mw = []
+    for q in range(n_mags):
+        g = (q * 37) % L
+        codes = synth.genome_codes(0xA11CE000 + g // 8, mag_bp, dev)
+        r = synth.splitmix64(((0xBEEF0000 + q) << 32) ^ torch.arange(mag_bp, dtype=torch.int64, device=dev))
+        snp = (synth._lsr(r, 8) % 1000) < 50
+        codes = torch.where(snp, (codes + 1 + synth._lsr(r, 40) % 3) % 4, codes)
+        mw.append(synth.pack_codes_device(codes))
+    qbatch = ops.GenomeBatch.from_device_words(mw, [mag_bp] * n_mags, dev)
+    del mw
+    qf = ctx.alloc_filters(n_mags, m)
+    t_sk = _time(lambda: ctx.build_filters(qbatch, k, m, out=qf), reps=2)
+    positions = [ctx.extract_positions(qf[i], m) for i in range(n_mags)]
+    t_ex = _time(lambda: [ctx.extract_positions(qf[i], m) for i in range(n_mags)], reps=1)
+    n_pos = sum(int(p.numel()) for p in positions)
+    out["K4_query_hash_and_extract"] = {"ms_hash": t_sk * 1e3, "ms_extract": t_ex * 1e3, "positions": n_pos,
+                                        "note": "distinct positions = set bits of the MAG's own min=1 filter (K1 + ordered extraction)"}
+    t_bs = _time(lambda: ctx.bitslice(rows, 0, m), reps=1)
+    sliced = ctx.bitslice(rows, 0, m)
+    out["K4_bitslice_build"] = entry(t_bs, 2 * L * fbytes, note="transpose: read every leaf once, write the sliced matrix once")
+    hits = ctx.query_batch_sliced(sliced, L, 0, m, positions)
+    t_q = _time(lambda: ctx.query_batch_sliced(sliced, L, 0, m, positions), reps=2)
+    algo = n_pos * ((L + 7) // 8) + n_mags * 4 * L
+    out["K4_query_sliced"] = entry(t_q, algo, mags_per_s=n_mags / t_q,
+                                   mags_per_s_incl_hash_extract=n_mags / (t_q + t_sk + t_ex))
+    # cross-check against K3 (App. A6 corollary: hits == popc(Q & F)) on the first MAG
+    inter, _ = ctx.bf_dist(qf[0], rows, m)
+    out["K4_check_hits_equal_and_popcount"] = bool(torch.equal(hits[0].to(torch.int64), inter))
+    # row-major probe on a species-sized leaf set (what `profile` uses inside one cluster)
+    S = min(16, L)
+    t_r = _time(lambda: ctx.query_batch(rows[:S], positions[:8]), reps=2)
+    out["K4_query_rowmajor_8x%d" % S] = entry(t_r, sum(int(p.numel()) for p in positions[:8]) * S * 32,
+                                              note="bytes = one 32-byte sector per probe")
+    del sliced, leaves, rows, qf
+    torch.cuda.empty_cache()
+    return out
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--leaves", type=int, default=1024)
+    ap.add_argument("--filter-bits", type=int, default=1 << 28)
+    ap.add_argument("--mags", type=int, default=64)
+    a = ap.parse_args()
+    import torch
+    from metasbt_b200 import ops
+    peak = 6537.6
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+    except Exception:
+        pass
+    print(json.dumps(run(ops.Context(0), a.leaves, a.filter_bits, a.mags, peak_gbs=peak)))
