@@ -215,6 +215,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner out of stdout: one JSON line only
         dist.init_process_group("nccl", device_id=device)
 
     ctx = ops.Context(local_rank)

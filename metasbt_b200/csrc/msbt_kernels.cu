@@ -295,6 +295,11 @@ kmer_bloom_direct_kernel(const uint64_t *__restrict__ packed, const uint32_t *__
                          const DevGenome *__restrict__ genomes, uint32_t n_genomes, uint32_t n_tiles,
                          KmerSpec spec, uint32_t *__restrict__ filters, const uint32_t *__restrict__ only_dirty) {
     const uint32_t k = spec.k, len = (k + 3) >> 2;
+    if (only_dirty) {  // redo pass: leave at once when no genome is marked (the normal case)
+        int any = 0;
+        for (uint32_t i = threadIdx.x; i < n_genomes; i += blockDim.x) any |= (only_dirty[i] != 0);
+        if (!__syncthreads_or(any)) return;
+    }
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t gi = find_genome(genomes, n_genomes, tile);
         const DevGenome g = genomes[gi];
