@@ -215,8 +215,19 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ.setdefault("NCCL_DEBUG", "WARN")  # keep NCCL's version banner out of stdout: one JSON line only
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL may print a version banner on stdout at its first collective: route fd 1 to stderr until then, so that
+        # stdout carries the one JSON line only
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     ctx = ops.Context(local_rank)
     k, m, G, N = args.kmer, args.filter_bits, args.genome_bp, args.genomes

@@ -28,17 +28,17 @@
 #pragma once
 
 #ifndef MSBT_FU_P_THREADS
-#define MSBT_FU_P_THREADS 640
+#define MSBT_FU_P_THREADS 576
 #endif
 constexpr int FU_P_THREADS = MSBT_FU_P_THREADS;      // partition warps (role P)
 constexpr int FU_THREADS = 1024;
 constexpr int FU_B_THREADS = FU_THREADS - FU_P_THREADS;  // tile-build warps (role B)
 constexpr uint32_t FU_CHUNK_BASES = FU_P_THREADS * 32;  // k-mer starts per chunk
-constexpr uint32_t FU_MAX_BUCKETS = 1024;
-constexpr uint32_t FU_STAGE_WORDS = 36 * (FU_MAX_BUCKETS + 1);  // staging rows: (NB + 1) x cap
+constexpr uint32_t FU_MAX_BUCKETS = 2048;               // at 2^30 bits: bucket == one 64 KiB tile, B needs a single pass
+constexpr uint32_t FU_STAGE_WORDS = 16 * (FU_MAX_BUCKETS + 1);  // staging rows: (NB + 1) x cap
 constexpr uint32_t FU_TILE_LOG2 = 19;                   // <= 2^19 bits = 64 KiB per tile
 constexpr uint32_t FU_TILE_BYTES = 1u << (FU_TILE_LOG2 - 3);
-constexpr int FU_REG_QUADS = 1536 / FU_B_THREADS;       // 16-byte groups of bucket positions a B thread keeps in registers
+constexpr int FU_REG_QUADS = 768 / FU_B_THREADS;        // 16-byte groups of bucket positions a B thread keeps in registers
 constexpr int FU_REG_ENTRIES = 4 * FU_REG_QUADS;
 // dynamic shared memory: [tile 64 KiB][cnt NB][stage][claims]
 constexpr size_t FU_SMEM_BYTES = FU_TILE_BYTES + FU_MAX_BUCKETS * 4 + (size_t)FU_STAGE_WORDS * 4 + 64;
@@ -65,6 +65,7 @@ struct FusedParams {
     uint32_t NB;             // buckets per filter (<= FU_MAX_BUCKETS)
     uint32_t cap;            // staging entries per bucket per chunk (multiple of 4)
     uint32_t quads;          // cap / 4
+    uint32_t lanes_per_row;  // flush: power of two >= min(quads, 32)
     uint32_t quad_magic;     // ceil(2^32 / quads): idx / quads == umulhi(idx, quad_magic) for idx < NB * quads
     uint32_t tile_log2;      // min(bucket_shift, FU_TILE_LOG2)
     uint32_t tiles_per_bucket_log2;
@@ -231,49 +232,75 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
                 nxt_gi = gi;  // claims are monotonic: scan forward from the current genome
                 if (nxt < P.n_chunks_total) {
                     while (nxt_gi + 1 < P.n_genomes && P.genomes[nxt_gi + 1].fchunk_begin <= nxt) nxt_gi++;
-                    nxt_free = (nxt_gi >= P.ring) ? fu_ld_acquire(P.consumed + (nxt_gi - P.ring)) : NB;
+                    // relaxed is enough: P only WRITES the slot after seeing the count, and B bumped it after its reads
+                    if (nxt_gi >= P.ring) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(nxt_free) : "l"(P.consumed + (nxt_gi - P.ring)) : "memory");
+                    else nxt_free = NB;
                 }
             }
-            // Flush: a thread owns whole staging rows.  One ring reservation per (chunk, bucket), rounded up to whole
-            // quads; the reservations of all its rows are issued before the first is consumed.  The row is copied
-            // with aligned 16-byte loads/stores (row stride = cap words keeps the 128-bit smem reads conflict-free);
-            // pad slots repeat the row's first entry (OR is idempotent).  The counter is zeroed for the next chunk.
+            // Flush, warp by warp (each warp owns a contiguous range of staging rows, so no CTA barrier is needed):
+            //  A  one lane per row: one ring reservation per (chunk, bucket), rounded up to whole quads; the result is
+            //     packed back into the row's counter as (offset << 8) | n;
+            //  B  `lpr` adjacent lanes per row copy its quads with aligned 16-byte loads/stores: a quarter warp reads
+            //     consecutive quads of consecutive rows (bank-conflict free) and a row's quads leave in one instruction
+            //     as one contiguous run (fewer L1 sector requests than one lane per row).  Pad slots repeat the row's
+            //     first entry (OR is idempotent).  The counter is zeroed for the next chunk.
             {
-                constexpr int ROWS = (FU_MAX_BUCKETS + FU_P_THREADS - 1) / FU_P_THREADS;
-                uint32_t nrow[ROWS], orow[ROWS];
+                const uint32_t lane = tid & 31u, warp = tid >> 5;
+                constexpr uint32_t P_WARPS = FU_P_THREADS / 32;
+                const uint32_t rpw = (NB + P_WARPS - 1) / P_WARPS;
+                const uint32_t r0 = warp * rpw, r1 = min(r0 + rpw, NB);
+                // all reservations of a lane are issued before the first result is used (one L2 round trip, not four)
+                for (uint32_t rb = r0; rb < r1; rb += 128) {
+                    uint32_t nn[4], oo[4];
 #pragma unroll
-                for (int j = 0; j < ROWS; j++) {
-                    const uint32_t b = tid + j * FU_P_THREADS;
-                    uint32_t n = 0;
-                    if (b < NB) { n = min(cnt[b], P.cap); cnt[b] = 0; }
-                    nrow[j] = n;
-                    orow[j] = n ? atomicAdd(gc + b, (n + 3u) & ~3u) : 0u;
-                }
-                const uint4 *stage4 = (const uint4 *)stage;
-                uint4 *gb4 = (uint4 *)gb;
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t b = rb + lane + 32 * j;
+                        nn[j] = (b < r1) ? min(cnt[b], P.cap) : 0u;
+                        oo[j] = nn[j] ? atomicAdd(gc + b, (nn[j] + 3u) & ~3u) : 0u;
+                    }
 #pragma unroll
-                for (int j = 0; j < ROWS; j++) {
-                    const uint32_t n = nrow[j];
-                    if (n) {
-                        const uint32_t b = tid + j * FU_P_THREADS;
-                        const uint32_t nq = (n + 3u) >> 2;
-                        if (orow[j] + nq * 4u <= P.gcap) {
-                            const uint4 *src4 = stage4 + b * P.quads;
-                            uint4 *dst4 = gb4 + (((uint64_t)b * P.gcap + orow[j]) >> 2);
-                            const uint32_t first = src4[0].x;
-                            for (uint32_t q = 0; q + 1 < nq; q++) dst4[q] = src4[q];
-                            uint4 v = src4[nq - 1];
-                            const uint32_t have = n - (nq - 1) * 4u;
-                            if (have < 2) v.y = first;
-                            if (have < 3) v.z = first;
-                            if (have < 4) v.w = first;
-                            dst4[nq - 1] = v;
-                        } else {
-                            *dirty_g = 1u;  // ring bucket full (skewed input): the direct kernel redoes this genome
+                    for (int j = 0; j < 4; j++) {
+                        const uint32_t b = rb + lane + 32 * j;
+                        if (b < r1) {
+                            uint32_t n = nn[j];
+                            if (n && oo[j] + ((n + 3u) & ~3u) > P.gcap) { *dirty_g = 1u; n = 0; }  // ring bucket full: redone by the direct kernel
+                            cnt[b] = (oo[j] << 8) | n;
                         }
                     }
                 }
+                __syncwarp();
+                FU_T(tf1)
+                if (tid == 0) { FU_ACC(5, tp2, tf1) }
+                const uint4 *stage4 = (const uint4 *)stage;
+                uint4 *gb4 = (uint4 *)gb;
+                const uint32_t lpr = P.lanes_per_row, rows_per_it = 32u / lpr;
+                const uint32_t q0 = lane & (lpr - 1u), sub = lane / lpr;
+                for (uint32_t rb = r0; rb < r1; rb += rows_per_it) {
+                    const uint32_t b = rb + sub;
+                    if (b < r1) {
+                        const uint32_t info = cnt[b];
+                        const uint32_t n = info & 0xFFu, o = info >> 8;
+                        const uint32_t nq = (n + 3u) >> 2;
+                        const uint4 *src4 = stage4 + b * P.quads;
+                        uint4 *dst4 = gb4 + (((uint64_t)b * P.gcap + o) >> 2);
+                        for (uint32_t q = q0; q < nq; q += lpr) {
+                            uint4 v = src4[q];
+                            if (q + 1 == nq) {
+                                const uint32_t first = stage[b * P.cap];
+                                const uint32_t have = n - q * 4u;
+                                if (have < 2) v.y = first;
+                                if (have < 3) v.z = first;
+                                if (have < 4) v.w = first;
+                            }
+                            dst4[q] = v;
+                        }
+                    }
+                    __syncwarp();
+                    if (b < r1 && q0 == 0) cnt[b] = 0;
+                }
             }
+            FU_T(tf2)
+            if (tid == 0) { FU_ACC(6, tp2, tf2) }
             // Publish per warp (done[g] counts warps, not chunks): no CTA barrier between the flush and the publish, and
             // the publish never waits behind tid 0's ring wait below (B needs it to free that very ring slot).
             __threadfence();
@@ -378,11 +405,22 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
                 FU_T(tb3)
                 if (n) {
                     const uint32_t word_mask = (tile_mask >> 3) & ~3u;
+                    if (tiles_here == 1) {  // bucket == tile: every position belongs here, no test at all
+#define FU_B_OR1(x) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(saddr + (((x) >> 3) & word_mask)), "r"(1u << ((x) & 31)) : "memory");
 #pragma unroll
-                    for (int u = 0; u < FU_REG_QUADS; u++) { FU_B_OR(e[u].x) FU_B_OR(e[u].y) FU_B_OR(e[u].z) FU_B_OR(e[u].w) }
-                    for (uint32_t i = FU_REG_ENTRIES * FU_B_THREADS + tid; i < n; i += FU_B_THREADS) {  // oversized buckets
-                        const uint32_t p = __ldcg(src + i);
-                        FU_B_OR(p)
+                        for (int u = 0; u < FU_REG_QUADS; u++) { FU_B_OR1(e[u].x) FU_B_OR1(e[u].y) FU_B_OR1(e[u].z) FU_B_OR1(e[u].w) }
+                        for (uint32_t i = FU_REG_ENTRIES * FU_B_THREADS + tid; i < n; i += FU_B_THREADS) {  // oversized buckets
+                            const uint32_t p = __ldcg(src + i);
+                            FU_B_OR1(p)
+                        }
+#undef FU_B_OR1
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < FU_REG_QUADS; u++) { FU_B_OR(e[u].x) FU_B_OR(e[u].y) FU_B_OR(e[u].z) FU_B_OR(e[u].w) }
+                        for (uint32_t i = FU_REG_ENTRIES * FU_B_THREADS + tid; i < n; i += FU_B_THREADS) {  // oversized buckets
+                            const uint32_t p = __ldcg(src + i);
+                            FU_B_OR(p)
+                        }
                     }
                 }
                 FU_T(tb4)

@@ -844,8 +844,10 @@ static int build_fused(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *
     memset(&P, 0, sizeof(P));
     P.bucket_shift = shift;
     P.NB = NB;
-    P.cap = (FU_STAGE_WORDS / (NB + 1)) & ~3u;
+    P.cap = std::min<uint32_t>((FU_STAGE_WORDS / (NB + 1)) & ~3u, 252u);  // n is packed into 8 bits by the flush
     P.quads = P.cap / 4;
+    P.lanes_per_row = 1;
+    while (P.lanes_per_row < P.quads && P.lanes_per_row < 32) P.lanes_per_row <<= 1;
     P.quad_magic = (uint32_t)(((1ull << 32) + P.quads - 1) / P.quads);
     if ((uint64_t)NB * P.quads * P.quads >= (1ull << 32)) return 1;  // exactness bound of the magic division
     P.tile_log2 = std::min(shift, FU_TILE_LOG2);

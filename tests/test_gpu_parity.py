@@ -244,3 +244,37 @@ def test_query_sliced_many_leaves_and_chunks(ctx, oracle):
         total = part if total is None else total + part
     assert np.array_equal(total.cpu().numpy().astype(np.uint64), want)
     assert np.array_equal(ctx.query_batch(leaves[:37], positions).cpu().numpy().astype(np.uint64), want[:, :37])
+
+
+@pytest.mark.parametrize("variant", [0, 2, 4])
+def test_full_size_genomes_bit_exact_and_properties(ctx, oracle, variant):
+    """BASELINE.json configs[1] shape at full size (5 Mbp genomes, k=31, 2^30-bit filters) for three genomes:
+    bit-exact against the oracle, plus the size-independent properties the domain offers --
+    popcount == number of distinct positions, OR of two filters == filter of the concatenated FASTA (k-mers never span
+    records), union/intersection counts consistent, and the query of a genome against its own filter hits every position."""
+    from metasbt_b200 import ops
+    k, m, n = 31, 1 << 30, 5_000_000
+    codes = [util.synthetic_codes(0x5EED0000 + g, n) for g in range(2)]
+    codes.append(util.mutate(codes[0], 0.01, 99))
+    fastas = [util.codes_to_fasta(c, "g%d" % i, 80) for i, c in enumerate(codes)]
+    batch = ops.GenomeBatch([ops.pack_codes(c) for c in codes], ctx.device)
+    out = ctx.build_filters(batch, k, m, variant=variant)
+    torch.cuda.synchronize()
+    w = ops.filter_words(m)
+    want = [oracle.makebf(f, k, m, rolling=True) for f in fastas]
+    for i in range(3):
+        assert torch.equal(out[i, :w].cpu(), torch.from_numpy(want[i].view(np.int64))), "genome %d differs" % i
+    rows = [out[i] for i in range(3)]
+    pc = [int(x) for x in ctx.bf_popcount(rows, m).cpu()]
+    pos0 = ctx.extract_positions(rows[0], m)
+    assert pc[0] == pos0.numel() == len(oracle.positions_distinct(fastas[0], k, m))
+    both = ctx.build_filters(ops.GenomeBatch([ops.pack_fasta(fastas[0] + fastas[1], k)], ctx.device), k, m, variant=variant)
+    union = ctx.bf_or(rows[:2], m)
+    assert torch.equal(both[0, :w], union[:w])
+    inter, uni = ctx.bf_dist(rows[0], rows[1:], m)
+    for j in (1, 2):
+        assert int(inter[j - 1]) + int(uni[j - 1]) == pc[0] + pc[j]
+    assert int(uni[0]) == int(ctx.bf_popcount([union], m)[0])
+    hits = ctx.query_batch(rows, [pos0]).cpu().numpy()[0]
+    assert int(hits[0]) == pc[0] and int(hits[2]) == int(inter[1]) and int(hits[1]) == int(inter[0])
+    assert 0.6 * pc[0] < int(hits[2]) < 0.85 * pc[0]  # a 1 % mutant shares about 0.99^31 = 73 % of its 31-mers

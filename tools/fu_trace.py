@@ -20,6 +20,7 @@ e0.record(); ctx.build_filters(batch, 31, 1 << 30, out=out, variant=3); e1.recor
 L.msbt_debug_trace(buf, 0)
 ms = e0.elapsed_time(e1)
 print("total %.1f us/genome" % (ms * 1e3 / n))
+print("flush (warp 0): reservations done after %.2f us, copy done after %.2f us per chunk" % (buf[5] / 1.965e3 / max(buf[7], 1), buf[6] / 1.965e3 / max(buf[7], 1)))
 names = ["P barA (wait claim)", "P hash+barB", "(unused)", "P flush+fence", "P ring wait/claim", "", "", "P chunks",
          "B wait_group.read (tid0)", "B barrier after wait", "B zero+select+bar", "B atomics", "B fence+bar", "B claim wait+bar", "B issue loads", "B tiles",
          "B store issue (tid0)", "B loop top (tid0)", "B loop top (tid32)"]
