@@ -38,7 +38,7 @@ constexpr uint32_t FU_MAX_BUCKETS = 2048;               // at 2^30 bits: bucket 
 constexpr uint32_t FU_STAGE_WORDS = 16 * (FU_MAX_BUCKETS + 1);  // staging rows: (NB + 1) x cap
 constexpr uint32_t FU_TILE_LOG2 = 19;                   // <= 2^19 bits = 64 KiB per tile
 constexpr uint32_t FU_TILE_BYTES = 1u << (FU_TILE_LOG2 - 3);
-constexpr int FU_REG_QUADS = 768 / FU_B_THREADS;        // 16-byte groups of bucket positions a B thread keeps in registers
+constexpr int FU_REG_QUADS = (768 + FU_B_THREADS - 1) / FU_B_THREADS;  // 16-byte groups of bucket positions per B thread in registers
 constexpr int FU_REG_ENTRIES = 4 * FU_REG_QUADS;
 // dynamic shared memory: [tile 64 KiB][cnt NB][stage][claims]
 constexpr size_t FU_SMEM_BYTES = FU_TILE_BYTES + FU_MAX_BUCKETS * 4 + (size_t)FU_STAGE_WORDS * 4 + 64;
@@ -138,6 +138,9 @@ __device__ __noinline__ void fu_append_cold(uint32_t *gc, uint32_t *gb, uint32_t
     }
 }
 
+// One half step = 4 k-mers: four independent hash chains, then the four rank atomics, then the four staged stores.
+// (Software-pipelining the stores one half step behind the atomics was measured and is slower: 12 more live registers
+// spill at the 64-register budget of a 1024-thread CTA.)
 template <int KW, int HV, bool POW2, bool FULL, bool AV, int H>
 __device__ __forceinline__ void fu_half_step(const KmerBlock<KW> &kb, uint32_t vg, const KmerSpec &spec, const FusedParams &P,
                                              uint32_t len, uint32_t cnt_s, uint32_t stage_s, uint32_t *gc, uint32_t *gb,
@@ -149,6 +152,18 @@ __device__ __forceinline__ void fu_half_step(const KmerBlock<KW> &kb, uint32_t v
     bool over = false;
     FU_STORE(0) FU_STORE(1) FU_STORE(2) FU_STORE(3)
     if (over) { FU_COLD(0) FU_COLD(1) FU_COLD(2) FU_COLD(3) }
+}
+// the 32 k-mers of one packed word
+template <int KW, int HV, bool POW2, bool FULL, bool AV>
+__device__ __forceinline__ void fu_word(KmerBlock<KW> &kb, uint32_t vm, const KmerSpec &spec, const FusedParams &P, uint32_t len,
+                                        uint32_t cnt_s, uint32_t stage_s, uint32_t *gc, uint32_t *gb, uint32_t *dirty_g) {
+#pragma unroll 1
+    for (uint32_t grp = 0; grp < 4; grp++) {
+        const uint32_t vg = AV ? 0xFFu : ((vm >> (8 * grp)) & 0xFFu);
+        fu_half_step<KW, HV, POW2, FULL, AV, 0>(kb, vg, spec, P, len, cnt_s, stage_s, gc, gb, dirty_g);
+        fu_half_step<KW, HV, POW2, FULL, AV, 1>(kb, vg, spec, P, len, cnt_s, stage_s, gc, gb, dirty_g);
+        kb.advance8();
+    }
 }
 
 template <int KW, int HV, bool POW2, bool FULL>
@@ -207,22 +222,11 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
             if (vm == 0xFFFFFFFFu) {
                 KmerBlock<KW> kb;
                 kb.init(P.packed + g.packed_word_off + w, k);
-#pragma unroll 1
-                for (uint32_t grp = 0; grp < 4; grp++) {
-                    fu_half_step<KW, HV, POW2, FULL, true, 0>(kb, 0xFFu, spec, P, len, cnt_s, stage_s, gc, gb, dirty_g);
-                    fu_half_step<KW, HV, POW2, FULL, true, 1>(kb, 0xFFu, spec, P, len, cnt_s, stage_s, gc, gb, dirty_g);
-                    kb.advance8();
-                }
+                fu_word<KW, HV, POW2, FULL, true>(kb, vm, spec, P, len, cnt_s, stage_s, gc, gb, dirty_g);
             } else if (vm) {
                 KmerBlock<KW> kb;
                 kb.init(P.packed + g.packed_word_off + w, k);
-#pragma unroll 1
-                for (uint32_t grp = 0; grp < 4; grp++) {
-                    const uint32_t vg = (vm >> (8 * grp)) & 0xFFu;
-                    fu_half_step<KW, HV, POW2, FULL, false, 0>(kb, vg, spec, P, len, cnt_s, stage_s, gc, gb, dirty_g);
-                    fu_half_step<KW, HV, POW2, FULL, false, 1>(kb, vg, spec, P, len, cnt_s, stage_s, gc, gb, dirty_g);
-                    kb.advance8();
-                }
+                fu_word<KW, HV, POW2, FULL, false>(kb, vm, spec, P, len, cnt_s, stage_s, gc, gb, dirty_g);
             }
             fu_bar(1, FU_P_THREADS);  // barrier B: the chunk is staged
             FU_T(tp2)
@@ -303,9 +307,13 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
             if (tid == 0) { FU_ACC(6, tp2, tf2) }
             // Publish per warp (done[g] counts warps, not chunks): no CTA barrier between the flush and the publish, and
             // the publish never waits behind tid 0's ring wait below (B needs it to free that very ring slot).
-            __threadfence();
+            // bar.warp.sync orders the lanes' ring writes before lane 0's fence, and the fence is cumulative: one
+            // MEMBAR per warp instead of 32
             __syncwarp();
-            if ((tid & 31u) == 0) atomicAdd(P.done + gi, 1u);
+            if ((tid & 31u) == 0) {
+                __threadfence();
+                atomicAdd(P.done + gi, 1u);
+            }
             FU_T(tp4)
             if (tid == 0) {
                 if (nxt < P.n_chunks_total && nxt_free < NB) fu_wait_ge(P.consumed + (nxt_gi - P.ring), NB);
@@ -331,7 +339,7 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
         uint64_t evict_first;
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(evict_first));
         uint4 e[FU_REG_QUADS];  // every ring reservation is a whole quad, so validity is per 16-byte group
-        uint32_t n_raw = 0, first = 0;
+        uint32_t n_raw = 0;
 
 #define FU_B_WANT(it) (((P.genomes[(it) / NB].n_bases + FU_CHUNK_BASES - 1) / FU_CHUNK_BASES) * (FU_P_THREADS / 32))
 #define FU_B_ISSUE_LOADS(it)                                                                       \
@@ -339,7 +347,6 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
         const uint32_t gi_ = claim[5], b_ = (it) - gi_ * NB, slot_ = claim[6];                     \
         const uint4 *src_ = (const uint4 *)(P.gbuf + ((uint64_t)slot_ * NB + b_) * P.gcap);        \
         n_raw = __ldcg(P.gcnt + (uint64_t)gi_ * NB + b_);                                          \
-        first = __ldcg((const uint32_t *)src_);                                                    \
         _Pragma("unroll") for (int u = 0; u < FU_REG_QUADS; u++)                                   \
             e[u] = __ldcg(src_ + min(u * FU_B_THREADS + tid, (P.gcap >> 2) - 1u));                 \
     }
@@ -395,20 +402,18 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
                 uint4 *tv = (uint4 *)tile;
                 for (uint32_t i = tid; i < (tile_words32 + 3) / 4; i += FU_B_THREADS) tv[i] = make_uint4(0, 0, 0, 0);
                 if (sub == 0) {
-                    // the prefetched loads land here; groups past the end repeat the bucket's first position
-                    n = min(n_raw, P.gcap);
-#pragma unroll
-                    for (int u = 0; u < FU_REG_QUADS; u++)
-                        if ((u * FU_B_THREADS + tid) * 4u >= n) e[u] = make_uint4(first, first, first, first);
+                    n = min(n_raw, P.gcap);  // the prefetched loads land here
                 }
                 fu_bar(2, FU_B_THREADS);
                 FU_T(tb3)
                 if (n) {
                     const uint32_t word_mask = (tile_mask >> 3) & ~3u;
+                    // groups past the end of the bucket are skipped (a thread-uniform branch per 16-byte group)
                     if (tiles_here == 1) {  // bucket == tile: every position belongs here, no test at all
 #define FU_B_OR1(x) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(saddr + (((x) >> 3) & word_mask)), "r"(1u << ((x) & 31)) : "memory");
 #pragma unroll
-                        for (int u = 0; u < FU_REG_QUADS; u++) { FU_B_OR1(e[u].x) FU_B_OR1(e[u].y) FU_B_OR1(e[u].z) FU_B_OR1(e[u].w) }
+                        for (int u = 0; u < FU_REG_QUADS; u++)
+                            if ((u * FU_B_THREADS + tid) * 4u < n) { FU_B_OR1(e[u].x) FU_B_OR1(e[u].y) FU_B_OR1(e[u].z) FU_B_OR1(e[u].w) }
                         for (uint32_t i = FU_REG_ENTRIES * FU_B_THREADS + tid; i < n; i += FU_B_THREADS) {  // oversized buckets
                             const uint32_t p = __ldcg(src + i);
                             FU_B_OR1(p)
@@ -416,7 +421,8 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
 #undef FU_B_OR1
                     } else {
 #pragma unroll
-                        for (int u = 0; u < FU_REG_QUADS; u++) { FU_B_OR(e[u].x) FU_B_OR(e[u].y) FU_B_OR(e[u].z) FU_B_OR(e[u].w) }
+                        for (int u = 0; u < FU_REG_QUADS; u++)
+                            if ((u * FU_B_THREADS + tid) * 4u < n) { FU_B_OR(e[u].x) FU_B_OR(e[u].y) FU_B_OR(e[u].z) FU_B_OR(e[u].w) }
                         for (uint32_t i = FU_REG_ENTRIES * FU_B_THREADS + tid; i < n; i += FU_B_THREADS) {  // oversized buckets
                             const uint32_t p = __ldcg(src + i);
                             FU_B_OR(p)

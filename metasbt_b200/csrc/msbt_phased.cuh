@@ -300,12 +300,11 @@ kmer_bloom_phased_kernel(PhasedParams P, KmerSpec spec) {
             const uint32_t tiles_here = 1u << P.tiles_per_bucket_log2;
             const uint32_t tile_vec = (tile_words32 + 3) / 4;  // uint4 per tile
             uint4 e[PH_REG_QUADS];
-            uint32_t n_raw, first;
+            uint32_t n_raw;
 #define PH_ISSUE_LOADS(gi_, b_)                                                                        \
     {                                                                                                  \
         const uint4 *src_ = (const uint4 *)(P.gbuf + ((uint64_t)((gi_) % P.ring) * NB + (b_)) * P.gcap); \
         n_raw = __ldcg(P.gcnt + (uint64_t)(gi_) * NB + (b_));                                          \
-        first = __ldcg((const uint32_t *)src_);                                                        \
         _Pragma("unroll") for (int u = 0; u < PH_REG_QUADS; u++)                                       \
             e[u] = __ldcg(src_ + min(u * PH_THREADS + tid, (P.gcap >> 2) - 1u));                       \
     }
@@ -324,10 +323,9 @@ kmer_bloom_phased_kernel(PhasedParams P, KmerSpec spec) {
             if (tid == 0) { FU_ACC(8, td1, tb0) FU_ACC(13, 0, 1) }
             for (uint32_t item = a0; item < a1; item++) {
                 const uint32_t n = min(n_raw, P.gcap);
-                // groups past the end repeat the bucket's first position (setting a bit twice is harmless)
-#pragma unroll
-                for (int u = 0; u < PH_REG_QUADS; u++)
-                    if ((u * PH_THREADS + tid) * 4u >= n) e[u] = make_uint4(first, first, first, first);
+                // groups past the end of the bucket are skipped below (never OR a repeated position: REDs of one warp
+                // instruction to the same word serialise)
+                const bool v0 = tid * 4u < n, v1 = (PH_THREADS + tid) * 4u < n;
                 const uint4 e0 = e[0], e1 = e[1];
                 const uint32_t cur_gi = gi, cur_b = b;
                 const uint32_t *src = P.gbuf + ((uint64_t)(cur_gi % P.ring) * NB + cur_b) * P.gcap;
@@ -352,8 +350,8 @@ kmer_bloom_phased_kernel(PhasedParams P, KmerSpec spec) {
                     if (n) {
                         if (tiles_here > 1) {
                             constexpr bool MULTI = true;
-                            PH_OR(e0.x, buf_s) PH_OR(e0.y, buf_s) PH_OR(e0.z, buf_s) PH_OR(e0.w, buf_s)
-                            PH_OR(e1.x, buf_s) PH_OR(e1.y, buf_s) PH_OR(e1.z, buf_s) PH_OR(e1.w, buf_s)
+                            if (v0) { PH_OR(e0.x, buf_s) PH_OR(e0.y, buf_s) PH_OR(e0.z, buf_s) PH_OR(e0.w, buf_s) }
+                            if (v1) { PH_OR(e1.x, buf_s) PH_OR(e1.y, buf_s) PH_OR(e1.z, buf_s) PH_OR(e1.w, buf_s) }
                             for (uint32_t i = PH_REG_QUADS * 4 * PH_THREADS + tid; i < n; i += PH_THREADS) {  // oversized buckets
                                 const uint32_t p = __ldcg(src + i);
                                 PH_OR(p, buf_s)
@@ -362,8 +360,8 @@ kmer_bloom_phased_kernel(PhasedParams P, KmerSpec spec) {
                             constexpr bool MULTI = false;
                             const uint32_t tf = 0;
                             (void)tf;
-                            PH_OR(e0.x, buf_s) PH_OR(e0.y, buf_s) PH_OR(e0.z, buf_s) PH_OR(e0.w, buf_s)
-                            if (n > 4 * PH_THREADS) { PH_OR(e1.x, buf_s) PH_OR(e1.y, buf_s) PH_OR(e1.z, buf_s) PH_OR(e1.w, buf_s) }
+                            if (v0) { PH_OR(e0.x, buf_s) PH_OR(e0.y, buf_s) PH_OR(e0.z, buf_s) PH_OR(e0.w, buf_s) }
+                            if (v1) { PH_OR(e1.x, buf_s) PH_OR(e1.y, buf_s) PH_OR(e1.z, buf_s) PH_OR(e1.w, buf_s) }
                             for (uint32_t i = PH_REG_QUADS * 4 * PH_THREADS + tid; i < n; i += PH_THREADS) {
                                 const uint32_t p = __ldcg(src + i);
                                 PH_OR(p, buf_s)
