@@ -117,6 +117,12 @@ int msbt_bf_and_popcount_allpairs(msbt_ctx *ctx, const uint64_t *const *h_filter
 int msbt_bf_extract_positions(msbt_ctx *ctx, const uint64_t *d_filter, uint64_t words,
                               uint32_t *d_positions, uint64_t cap, uint64_t *d_count, void *stream);
 
+/* The same for a batch of n query filters in one call and without a host round trip: d_offsets (u64, n + 1 entries)
+ * receives the start of every query inside d_positions (offsets[n] = total count); positions beyond `cap` are dropped
+ * (call once with cap = 0 to size the buffer, or pass an upper bound such as the summed k-mer counts). */
+int msbt_bf_extract_positions_batch(msbt_ctx *ctx, const uint64_t *const *h_filters, uint32_t n, uint64_t words,
+                                    uint32_t *d_positions, uint64_t cap, uint64_t *d_offsets, void *stream);
+
 /* Step 2: hits[q][l] = #{p in positions of query q : bit p of leaf filter l is set}.
  * d_positions holds all queries back to back; h_query_offsets (host, n_queries+1 entries)
  * delimits them.  d_hits is n_queries * n_leaves u32, row-major. */

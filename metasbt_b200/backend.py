@@ -153,7 +153,7 @@ class CudaBackend:
     def query_many(self, query_filters: Sequence[torch.Tensor], leaf_paths: Sequence[str]):
         """hits[q][l] and totals[q] for device-resident query filters against the given leaves."""
         leaves = [self.filter(p) for p in leaf_paths]
-        positions = [self.ctx.extract_positions(q, self.num_bits) for q in query_filters]
+        positions = self.ctx.extract_positions_batch(list(query_filters), self.num_bits)
         hits = self.ctx.query_batch(leaves, positions)
         totals = [int(p.numel()) for p in positions]
         return hits.cpu().numpy(), totals

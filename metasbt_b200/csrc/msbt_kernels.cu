@@ -1558,6 +1558,137 @@ extern "C" int msbt_bf_extract_positions(msbt_ctx *ctx, const uint64_t *d_filter
     return MSBT_OK;
 }
 
+// ---- batched extraction: all query filters of a batch in three launches, no host round trip in between.
+// grid (chunks, filters): per-chunk popcounts
+__global__ void __launch_bounds__(EX_THREADS)
+bf_extract_count_batch_kernel(const uint64_t *const *__restrict__ filters, uint64_t words, uint32_t n_chunks,
+                              uint32_t *__restrict__ chunk_counts) {
+    const uint64_t *__restrict__ f = filters[blockIdx.y];
+    const uint64_t base = (uint64_t)blockIdx.x * EX_CHUNK + (uint64_t)threadIdx.x * EX_WORDS_PER_THREAD;
+    uint64_t c = 0;
+#pragma unroll
+    for (int i = 0; i < EX_WORDS_PER_THREAD; i++)
+        if (base + i < words) c += __popcll(f[base + i]);
+    c = block_sum_u64(c);
+    if (threadIdx.x == 0) chunk_counts[(uint64_t)blockIdx.y * n_chunks + blockIdx.x] = (uint32_t)c;
+}
+
+// one CTA per filter: exclusive scan of its chunk counts in place, total -> totals[f]
+__global__ void __launch_bounds__(1024)
+bf_extract_scan_batch_kernel(uint32_t *__restrict__ chunk_counts, uint32_t n_chunks, unsigned long long *__restrict__ totals) {
+    __shared__ unsigned long long part[1024];
+    uint32_t *cc = chunk_counts + (uint64_t)blockIdx.x * n_chunks;
+    const uint32_t per = (n_chunks + 1023) / 1024;
+    const uint32_t b = threadIdx.x * per, e = min(b + per, n_chunks);
+    unsigned long long s = 0;
+    for (uint32_t i = b; i < e; i++) s += cc[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < 1024; i++) { const unsigned long long t = part[i]; part[i] = run; run += t; }
+        totals[blockIdx.x] = run;
+    }
+    __syncthreads();
+    unsigned long long run = part[threadIdx.x];
+    for (uint32_t i = b; i < e; i++) { const uint32_t t = cc[i]; cc[i] = (uint32_t)run; run += t; }  // per-filter offsets < 2^32
+}
+
+// single CTA: offsets[f] = sum of totals[0..f), offsets[n] = grand total
+__global__ void __launch_bounds__(1024)
+bf_extract_offsets_kernel(const unsigned long long *__restrict__ totals, uint32_t n, unsigned long long *__restrict__ offsets) {
+    __shared__ unsigned long long part[1024];
+    const uint32_t per = (n + 1023) / 1024;
+    const uint32_t b = threadIdx.x * per, e = min(b + per, n);
+    unsigned long long s = 0;
+    for (uint32_t i = b; i < e; i++) s += totals[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (int i = 0; i < 1024; i++) { const unsigned long long t = part[i]; part[i] = run; run += t; }
+        offsets[n] = run;
+    }
+    __syncthreads();
+    unsigned long long run = part[threadIdx.x];
+    for (uint32_t i = b; i < e; i++) { offsets[i] = run; run += totals[i]; }
+}
+
+// grid (chunks, filters): ordered emission into the concatenated output
+__global__ void __launch_bounds__(EX_THREADS)
+bf_extract_emit_batch_kernel(const uint64_t *const *__restrict__ filters, uint64_t words, uint32_t n_chunks,
+                             const uint32_t *__restrict__ chunk_offsets, const unsigned long long *__restrict__ offsets,
+                             uint32_t *__restrict__ out, uint64_t cap) {
+    __shared__ uint32_t warp_tot[EX_THREADS / 32];
+    const uint64_t *__restrict__ f = filters[blockIdx.y];
+    const uint64_t base = (uint64_t)blockIdx.x * EX_CHUNK + (uint64_t)threadIdx.x * EX_WORDS_PER_THREAD;
+    uint64_t v[EX_WORDS_PER_THREAD];
+    uint32_t mine = 0;
+#pragma unroll
+    for (int i = 0; i < EX_WORDS_PER_THREAD; i++) {
+        v[i] = (base + i < words) ? f[base + i] : 0;
+        mine += __popcll(v[i]);
+    }
+    uint32_t incl = mine;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w2 = 0; w2 < wid; w2++) woff += warp_tot[w2];
+    uint64_t o = offsets[blockIdx.y] + chunk_offsets[(uint64_t)blockIdx.y * n_chunks + blockIdx.x] + woff + (incl - mine);
+#pragma unroll
+    for (int i = 0; i < EX_WORDS_PER_THREAD; i++) {
+        uint64_t x = v[i];
+        while (x) {
+            const int bit = __ffsll((long long)x) - 1;
+            x &= x - 1;
+            if (o < cap) out[o] = (uint32_t)(((base + i) << 6) + bit);
+            o++;
+        }
+    }
+}
+
+extern "C" int msbt_bf_extract_positions_batch(msbt_ctx *ctx, const uint64_t *const *h_filters, uint32_t n, uint64_t words,
+                                               uint32_t *d_positions, uint64_t cap, uint64_t *d_offsets, void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n == 0) return MSBT_OK;
+    if (!d_offsets || words == 0) return fail(ctx, MSBT_EINVAL, "bf_extract_positions_batch: null/empty input");
+    if (words > (1ull << 26)) return fail(ctx, MSBT_EINVAL, "bf_extract_positions_batch: positions are u32 (num_bits <= 2^32)");
+    if (n > 65535) return fail(ctx, MSBT_EINVAL, "bf_extract_positions_batch: at most 65535 filters per call");
+    if (cap && !d_positions) return fail(ctx, MSBT_EINVAL, "bf_extract_positions_batch: null output");
+    int rc = check_ptrs(ctx, h_filters, n);
+    if (rc) return rc;
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    const uint32_t n_chunks = (uint32_t)((words + EX_CHUNK - 1) / EX_CHUNK);
+    // scratch: [pointer table][totals n x u64][chunk counts n x n_chunks x u32]
+    const size_t ptr_b = align_up((size_t)n * sizeof(void *), 256);
+    const size_t tot_b = align_up((size_t)n * 8, 256);
+    rc = ensure_scratch(ctx, ptr_b + tot_b + (size_t)n * n_chunks * 4);
+    if (rc) return rc;
+    const uint64_t *const *d_f;
+    rc = upload_ptrs(ctx, h_filters, n, stream, &d_f);
+    if (rc) return rc;
+    unsigned long long *totals = (unsigned long long *)((char *)ctx->d_scratch + ptr_b);
+    uint32_t *chunks = (uint32_t *)((char *)ctx->d_scratch + ptr_b + tot_b);
+    bf_extract_count_batch_kernel<<<dim3(n_chunks, n), EX_THREADS, 0, stream>>>(d_f, words, n_chunks, chunks);
+    LAUNCH_CHECK(ctx);
+    bf_extract_scan_batch_kernel<<<n, 1024, 0, stream>>>(chunks, n_chunks, totals);
+    LAUNCH_CHECK(ctx);
+    bf_extract_offsets_kernel<<<1, 1024, 0, stream>>>(totals, n, (unsigned long long *)d_offsets);
+    LAUNCH_CHECK(ctx);
+    if (cap) {
+        bf_extract_emit_batch_kernel<<<dim3(n_chunks, n), EX_THREADS, 0, stream>>>(d_f, words, n_chunks, chunks,
+                                                                                  (const unsigned long long *)d_offsets, d_positions, cap);
+        LAUNCH_CHECK(ctx);
+    }
+    return MSBT_OK;
+}
+
 // Row-major probe: CTA (leaf-group, query).  Each thread walks positions with stride and
 // tests QL leaves per position so the position stream is read once per QL leaves.
 constexpr int QL = 4;
@@ -1628,29 +1759,63 @@ extern "C" int msbt_query_batch(msbt_ctx *ctx, const uint64_t *const *h_leaves, 
     return MSBT_OK;
 }
 
-// Bit-slice transpose: thread block handles 32 rows x 32 leaves at a time through shared memory.
-// sliced[(p - row_begin) * lw + (l >> 5)] bit (l & 31) = bit p of leaf l.
+// Bit-slice transpose.  sliced[(p - row_begin) * lw + (l >> 5)] bit (l & 31) = bit p of leaf l.
+// CTA tile = up to 1024 leaves x 256 rows: every leaf contributes one 32-byte run (sector-efficient reads), the
+// 32 x 32 bit blocks are transposed in registers with a 5-stage shuffle butterfly, and the tile leaves as full
+// 128-byte row segments (coalesced writes) -- read every leaf once, write the sliced matrix once.
+constexpr int BS_WORDS = 8;                       // u32 words (= 256 rows) of every leaf per CTA
+constexpr int BS_LEAVES = 1024;                   // leaves per CTA (32 column words)
+constexpr int BS_IN_STRIDE = BS_WORDS + 1;        // smem padding: conflict-free column reads
+constexpr int BS_OUT_STRIDE = 33;
+constexpr size_t BS_SMEM_BYTES = ((size_t)BS_LEAVES * BS_IN_STRIDE + (size_t)BS_WORDS * 32 * BS_OUT_STRIDE) * 4;
+
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
+    // lane r holds row r of a 32 x 32 bit matrix; returns column r (bit c = old row c, bit r)
+#define MSBT_T32_STAGE(J, M)                                                                   \
+    {                                                                                          \
+        const uint32_t t = __shfl_xor_sync(0xffffffffu, x, J);                                 \
+        x = (lane & J) ? ((x & ~M) | ((t & ~M) >> J)) : ((x & M) | ((t & M) << J));            \
+    }
+    MSBT_T32_STAGE(16, 0x0000FFFFu) MSBT_T32_STAGE(8, 0x00FF00FFu) MSBT_T32_STAGE(4, 0x0F0F0F0Fu)
+    MSBT_T32_STAGE(2, 0x33333333u) MSBT_T32_STAGE(1, 0x55555555u)
+#undef MSBT_T32_STAGE
+    return x;
+}
+
 __global__ void __launch_bounds__(256)
 bitslice_kernel(const uint64_t *const *__restrict__ leaves, uint32_t n_leaves, uint64_t row_begin, uint64_t row_end,
                 uint32_t lw, uint32_t *__restrict__ sliced) {
-    // CTA: 8 warps; warp handles one 32-row block (one u32 word of each of 32 leaves) for a leaf group.
+    extern __shared__ uint32_t bs_smem[];
+    uint32_t *in = bs_smem;                                     // [BS_LEAVES][BS_IN_STRIDE]
+    uint32_t *out = bs_smem + BS_LEAVES * BS_IN_STRIDE;         // [BS_WORDS * 32][BS_OUT_STRIDE]
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint64_t first_word = row_begin >> 5;                 // row_begin is a multiple of 32
+    const uint32_t leaf0 = blockIdx.y * BS_LEAVES;
+    const uint32_t lg0 = leaf0 >> 5;
+    const uint32_t cols = min(32u, lw - lg0);                   // column words of this tile
     const uint64_t n_rowwords = (row_end - row_begin + 31) >> 5;
-    const uint32_t lg = blockIdx.y;                              // leaf group (32 leaves)
-    const uint32_t leaf = lg * 32 + lane;
-    const uint32_t *lf = (leaf < n_leaves) ? (const uint32_t *)leaves[leaf] : nullptr;
-    for (uint64_t rw = (uint64_t)blockIdx.x * 8 + warp; rw < n_rowwords; rw += (uint64_t)gridDim.x * 8) {
-        uint32_t v = lf ? lf[first_word + rw] : 0u;  // lane = leaf: word holding rows rw*32..+31
-        // 32x32 bit transpose across the warp: out lane r gets bit r of every lane's v
-        uint32_t outw = 0;
-#pragma unroll
-        for (int r = 0; r < 32; r++) {
-            uint32_t bal = __ballot_sync(0xffffffffu, (v >> r) & 1u);
-            if (lane == r) outw = bal;
+    const uint64_t first_word = row_begin >> 5;                 // row_begin is a multiple of 32
+    for (uint64_t wb = (uint64_t)blockIdx.x * BS_WORDS; wb < n_rowwords; wb += (uint64_t)gridDim.x * BS_WORDS) {
+        __syncthreads();
+        // load: 8 lanes per leaf read its 8 consecutive words, 32 leaves per pass
+        for (uint32_t l = threadIdx.x >> 3; l < cols * 32; l += 32) {
+            const uint32_t leaf = leaf0 + l, ww = threadIdx.x & 7;
+            uint32_t v = 0;
+            if (leaf < n_leaves && wb + ww < n_rowwords) v = __ldg((const uint32_t *)leaves[leaf] + first_word + wb + ww);
+            in[l * BS_IN_STRIDE + ww] = v;
         }
-        const uint64_t row = rw * 32 + lane;  // relative row
-        if (row_begin + row < row_end) sliced[row * lw + lg] = outw;
+        __syncthreads();
+        // transpose: warp ww handles row word ww of every leaf group
+        for (uint32_t lg = 0; lg < cols; lg++) {
+            const uint32_t x = transpose32(in[(lg * 32 + lane) * BS_IN_STRIDE + warp], lane);
+            out[(warp * 32 + lane) * BS_OUT_STRIDE + lg] = x;  // row (wb + warp) * 32 + lane, column word lg0 + lg
+        }
+        __syncthreads();
+        // store: full row segments
+        for (uint32_t idx = threadIdx.x; idx < BS_WORDS * 32 * cols; idx += 256) {
+            const uint32_t r = idx / cols, c = idx - r * cols;
+            const uint64_t row = wb * 32 + r;  // relative row
+            if (row_begin + row < row_end) sliced[row * lw + lg0 + c] = out[r * BS_OUT_STRIDE + c];
+        }
     }
 }
 
@@ -1761,8 +1926,11 @@ extern "C" int msbt_bitslice_build(msbt_ctx *ctx, const uint64_t *const *h_leave
     const uint32_t lw = (n_leaves + 31) / 32;
     if (lw > 65535) return fail(ctx, MSBT_EINVAL, "bitslice_build: too many leaves");
     const uint64_t n_rowwords = (row_end - row_begin + 31) >> 5;
-    uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((n_rowwords + 7) / 8, (uint64_t)ctx->num_sms * 32));
-    bitslice_kernel<<<dim3((unsigned)gx, lw), 256, 0, stream>>>(d_l, n_leaves, row_begin, row_end, lw, d_sliced);
+    CU_TRY(ctx, cudaFuncSetAttribute(bitslice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES));
+    const uint32_t gy = (lw + 31) / 32;
+    const uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((n_rowwords + BS_WORDS - 1) / BS_WORDS,
+                                                                  std::max<uint64_t>(1, (uint64_t)ctx->num_sms * 12 / gy)));
+    bitslice_kernel<<<dim3((unsigned)gx, gy), 256, BS_SMEM_BYTES, stream>>>(d_l, n_leaves, row_begin, row_end, lw, d_sliced);
     LAUNCH_CHECK(ctx);
     return MSBT_OK;
 }

@@ -276,6 +276,26 @@ class Context:
         n = min(int(count.item()), cap)
         return pos[:n]
 
+    def extract_positions_batch(self, filters: Sequence[torch.Tensor], num_bits: int, cap: Optional[int] = None) -> List[torch.Tensor]:
+        """Ascending set-bit positions of every filter of a batch (three launches for the whole batch).
+        `cap`: upper bound on the total count (e.g. the summed k-mer counts); None sizes the buffer with one
+        extra counting pass.  Returns one int32 view (uint32 bit patterns) per filter."""
+        n = len(filters)
+        if n == 0:
+            return []
+        words = filter_words(num_bits)
+        ptrs = _ptr_array(filters)
+        offs = torch.empty(n + 1, dtype=torch.int64, device=self.device)
+        if cap is None:
+            rc = self._L.msbt_bf_extract_positions_batch(self._h, ptrs, n, words, None, 0, offs.data_ptr(), self._stream())
+            self._check(rc, "msbt_bf_extract_positions_batch")
+            cap = int(offs[n].item())
+        pos = torch.empty(max(cap, 1), dtype=torch.int32, device=self.device)
+        rc = self._L.msbt_bf_extract_positions_batch(self._h, ptrs, n, words, pos.data_ptr(), cap, offs.data_ptr(), self._stream())
+        self._check(rc, "msbt_bf_extract_positions_batch")
+        h = offs.cpu().tolist()
+        return [pos[min(h[i], cap): min(h[i + 1], cap)] for i in range(n)]
+
     def query_batch(self, leaves: Sequence[torch.Tensor], positions: Sequence[torch.Tensor]) -> torch.Tensor:
         """hits[q][l] = number of query q's positions set in leaf l (row-major probe) -> int32[q, l]."""
         nq, nl = len(positions), len(leaves)

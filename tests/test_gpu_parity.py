@@ -164,9 +164,12 @@ def test_query_paths_agree_with_oracle(ctx, oracle):
     q_mat, q_np = build(ctx, queries_fa, k, num_bits)
     leaves = [leaf_mat[i] for i in range(len(leaves_fa))]
     positions = [ctx.extract_positions(q_mat[i], num_bits) for i in range(len(queries_fa))]
-    for qf, p in zip(queries_fa, positions):
+    batched = ctx.extract_positions_batch([q_mat[i] for i in range(len(queries_fa))], num_bits)
+    capped = ctx.extract_positions_batch([q_mat[i] for i in range(len(queries_fa))], num_bits, cap=10 ** 6)
+    for qf, p, pb, pc in zip(queries_fa, positions, batched, capped):
         ref = oracle.positions_distinct(qf, k, num_bits)
         assert np.array_equal(p.cpu().numpy().view(np.uint32).astype(np.uint64), ref)
+        assert torch.equal(p, pb) and torch.equal(p, pc)
     want = np.stack([oracle.query_hits(oracle.positions_distinct(qf, k, num_bits), leaf_np) for qf in queries_fa])
     hits = ctx.query_batch(leaves, positions).cpu().numpy()
     assert np.array_equal(hits.astype(np.uint64), want)
