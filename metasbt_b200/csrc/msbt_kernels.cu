@@ -1871,6 +1871,7 @@ query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint
             // 28 positions per round: one coalesced load of positions, then 4 groups of 7 independent row reads
             const unsigned long long idx = base + lane;
             const uint32_t mypos = (lane < 28 && idx < sub_e) ? positions[idx] : 0xFFFFFFFFu;
+            // (issuing all 28 row reads before the first use was measured: 76 registers, lower occupancy, 1.5x slower)
 #pragma unroll
             for (int g7 = 0; g7 < 4; g7++) {
                 uint32_t x[7];
