@@ -139,8 +139,9 @@ __device__ __noinline__ void fu_append_cold(uint32_t *gc, uint32_t *gb, uint32_t
 }
 
 // One half step = 4 k-mers: four independent hash chains, then the four rank atomics, then the four staged stores.
-// (Software-pipelining the stores one half step behind the atomics was measured and is slower: 12 more live registers
-// spill at the 64-register budget of a 1024-thread CTA.)
+// Measured alternatives that did not help: software-pipelining the stores one half step behind the atomics (12 more
+// live registers spill at the 64-register budget of a 1024-thread CTA), and eight chains per step with registers
+// moved from the B to the P warps by setmaxnreg (-DMSBT_FU_SETMAXNREG): the loop is already issue/IMAD-pipe bound.
 template <int KW, int HV, bool POW2, bool FULL, bool AV, int H>
 __device__ __forceinline__ void fu_half_step(const KmerBlock<KW> &kb, uint32_t vg, const KmerSpec &spec, const FusedParams &P,
                                              uint32_t len, uint32_t cnt_s, uint32_t stage_s, uint32_t *gc, uint32_t *gb,
@@ -178,6 +179,9 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
 
     if (threadIdx.x < FU_P_THREADS) {
         // ------------------------------------------------------------------ P: partition
+#ifdef MSBT_FU_SETMAXNREG
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MSBT_FU_P_REGS));  // registers handed over by the B warps
+#endif
         const uint32_t tid = threadIdx.x;
         const uint32_t cnt_s = (uint32_t)__cvta_generic_to_shared(cnt);
         const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
@@ -326,6 +330,9 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
         }
     } else {
         // ------------------------------------------------------------------ B: build tiles
+#ifdef MSBT_FU_SETMAXNREG
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(MSBT_FU_B_REGS));
+#endif
         // Software-pipelined by one item: the claim of item i+1 and the L2 loads of its positions are issued
         // while item i's last tile drains, so that the only exposed latency per tile is the smem read-out of
         // the previous bulk store.
