@@ -137,26 +137,60 @@ def run_reference(args):
 
 
 class ClockSampler:
+    """Samples SM clock and throttle reasons DURING the timed region: NVML (pynvml) every ~10 ms when available,
+    else `nvidia-smi` every ~100 ms."""
     QUERY = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index: int):
         self.index = index
-        self.samples = []
+        self.samples = []   # (sm_mhz, max_mhz, [reason names])
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml = pynvml
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        mhz = n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM)
+        r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+        names = []
+        for bit, name in ((getattr(n, "nvmlClocksThrottleReasonHwSlowdown", 0x8), "hw_slowdown"),
+                          (getattr(n, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40), "hw_thermal_slowdown"),
+                          (getattr(n, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20), "sw_thermal_slowdown"),
+                          (getattr(n, "nvmlClocksThrottleReasonSwPowerCap", 0x4), "sw_power_cap")):
+            if r & bit:
+                names.append(name)
+        self.samples.append((int(mhz), int(mx), names))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        if len(parts) >= 6 and parts[0].isdigit():
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            self.samples.append((int(parts[0]), int(parts[1]) if parts[1].isdigit() else None,
+                                 [nm for i, nm in enumerate(names) if parts[2 + i].lower().startswith("active")]))
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
-                    self.samples.append(parts)
+                if self._nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.01 if self._nvml is not None else 0.1)
 
     def __enter__(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -170,12 +204,10 @@ class ClockSampler:
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        mhz = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": mhz[len(mhz) // 2] if mhz else None,
-                "sm_max_mhz": int(self.samples[0][1]) if self.samples[0][1].isdigit() else None,
-                "reasons": reasons, "samples": len(self.samples)}
+        mhz = sorted(s[0] for s in self.samples)
+        reasons = sorted({r for s in self.samples for r in s[2]})
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons,
+                "samples": len(self.samples), "source": "nvml" if self._nvml is not None else "nvidia-smi"}
 
 
 # ------------------------------------------------------------------ our arm

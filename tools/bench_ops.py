@@ -59,6 +59,15 @@ def run(ctx, n_leaves=1024, filter_bits=1 << 28, n_mags=64, genome_bp=5_000_000,
     t = _time(lambda: ctx.build_filters(batch, k, m, out=leaves), reps=2)
     out["K1_build_leaves"] = entry(t, L * ((genome_bp + 3) // 4 + fbytes), Mbp_per_s=L * genome_bp / t / 1e6)
     rows = [leaves[i] for i in range(L)]
+    # K1 with --min-kmer-occurrences 2 (MetaSBT's CLI default): exact multiplicity path, a bounded sample of the batch
+    n2 = min(32, L)
+    sub = ops.GenomeBatch.from_device_words([batch.d_words[i * (batch.d_words.numel() // L):(i + 1) * (batch.d_words.numel() // L)] for i in range(n2)],
+                                            [genome_bp] * n2, dev)
+    tmp = ctx.alloc_filters(n2, m)
+    t2 = _time(lambda: ctx.build_filters(sub, k, m, min_abund=2, out=tmp), reps=1)
+    out["K1_build_min2_%d" % n2] = entry(t2, n2 * ((genome_bp + 3) // 4 + fbytes), Mbp_per_s=n2 * genome_bp / t2 / 1e6,
+                                         note="exact canonical k-mer multiplicity per genome (hash table), not a bandwidth-roofline path")
+    del tmp, sub
 
     # K2: cluster filter = OR of C children
     C = min(100, L)
@@ -112,7 +121,35 @@ def run(ctx, n_leaves=1024, filter_bits=1 << 28, n_mags=64, genome_bp=5_000_000,
     t_r = _time(lambda: ctx.query_batch(rows[:S], positions[:8]), reps=2)
     out["K4_query_rowmajor_8x%d" % S] = entry(t_r, sum(int(p.numel()) for p in positions[:8]) * S * 32,
                                               note="bytes = one 32-byte sector per probe")
-    del sliced, leaves, rows, qf
+    del sliced, leaves, rows
+    torch.cuda.empty_cache()
+    # BASELINE configs[3] shape on ONE bit-range shard: 10,000 leaves, rows [0, m/8) of a 2^28-bit filter space
+    # (what each of 8 GPUs holds).  The leaf bits are random words (building 10,000 real leaves needs 8 GPUs);
+    # the queries are the real MAG positions above, so the gather pattern and the traffic are the real ones.
+    try:
+        L4, shard_rows = 10_000, m // 8
+        lw4 = (L4 + 31) // 32
+        big = torch.empty((shard_rows, lw4), dtype=torch.int32, device=dev)
+        step = 1 << 20
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(1)
+        for r0 in range(0, shard_rows, step):
+            big[r0:r0 + step] = torch.randint(-2 ** 31, 2 ** 31 - 1, (min(step, shard_rows - r0), lw4), dtype=torch.int32, device=dev, generator=gen)
+        h4 = ctx.query_batch_sliced(big, L4, 0, shard_rows, positions)
+        t4 = _time(lambda: ctx.query_batch_sliced(big, L4, 0, shard_rows, positions), reps=2)
+        n_in = sum(int((p.view(torch.int32) >= 0).logical_and(p < shard_rows).sum()) for p in positions)
+        algo4 = n_in * ((L4 + 7) // 8) + n_mags * 4 * L4
+        # spot check of one (query, leaf) count against a direct gather
+        p0 = positions[0]
+        p0 = p0[(p0 >= 0) & (p0 < shard_rows)].long()
+        want = int(((big[p0, 7] >> 3) & 1).sum())
+        out["K4_query_sliced_10000_leaves_one_of_8_shards"] = entry(
+            t4, algo4, mags_per_s_per_shard=n_mags / t4, positions_in_shard=n_in, spot_check=bool(int(h4[0, 7 * 32 + 3]) == want),
+            note="row = 1,250 B per position; with 8 GPUs each holding one shard the batch rate is this rate (partial hits are summed by all_reduce)")
+        del big, h4
+    except Exception as exc:
+        out["K4_query_sliced_10000_leaves_one_of_8_shards"] = {"error": repr(exc)}
+    del qf
     torch.cuda.empty_cache()
     return out
 
