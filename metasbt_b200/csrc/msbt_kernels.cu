@@ -651,6 +651,68 @@ kmer_count_emit_kernel(const unsigned long long *__restrict__ keys, const uint32
     }
 }
 
+// ---- exact multiplicity, compact form (k <= 31, min_abund <= 3): the canonical k-mer occupies 62 bits, so its saturating
+// count (1..3) rides in the two top bits of the same 64-bit slot: one table of 8 bytes per slot at load factor <= 2/3
+// (64 MiB for a 5 Mbp genome: L2-resident), 0 = empty (an occupied slot always has a non-zero count), one CAS for a
+// new k-mer and one more for a repeat.  Keys come from the same unrolled KmerBlock extraction as the other kernels.
+constexpr uint64_t HT2_KEY_MASK = (1ull << 62) - 1;
+
+__device__ __forceinline__ void ht2_insert(unsigned long long *__restrict__ tab, uint64_t mask, uint64_t key) {
+    uint64_t slot = ht_slot(key, mask);
+    const unsigned long long fresh = key | (1ull << 62);
+    while (true) {
+        unsigned long long old = atomicCAS(tab + slot, 0ull, fresh);
+        if (old == 0ull) return;
+        if ((old & HT2_KEY_MASK) == key) {
+            while ((old >> 62) < 3ull) {  // saturating increment
+                const unsigned long long prev = atomicCAS(tab + slot, old, old + (1ull << 62));
+                if (prev == old) return;
+                old = prev;
+            }
+            return;
+        }
+        slot = (slot + 1) & mask;
+    }
+}
+
+#define MSBT_HT2_STEP(J)                                              \
+    {                                                                 \
+        uint64_t lo_, hi_;                                            \
+        kb.template get<J>(lo_, hi_);                                 \
+        if ((vg >> J) & 1u) ht2_insert(tab, slot_mask, lo_);          \
+    }
+
+__global__ void __launch_bounds__(TILE_THREADS, 4)
+kmer_count2_insert_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ run_ends, DevGenome g,
+                          uint32_t k, unsigned long long *__restrict__ tab, uint64_t slot_mask) {
+    const uint32_t n_words = (g.n_bases + 31) / 32;
+    for (uint32_t w = blockIdx.x * TILE_THREADS + threadIdx.x; w < n_words; w += gridDim.x * TILE_THREADS) {
+        const uint32_t vm = valid_mask(run_ends + g.run_off, g.n_runs, w * 32, k);
+        if (vm == 0) continue;
+        KmerBlock<1> kb;
+        kb.init(packed + g.packed_word_off + w, k);
+#pragma unroll 1
+        for (uint32_t grp = 0; grp < 4; grp++) {
+            const uint32_t vg = (vm >> (8 * grp)) & 0xFFu;
+            MSBT_HT2_STEP(0) MSBT_HT2_STEP(1) MSBT_HT2_STEP(2) MSBT_HT2_STEP(3)
+            MSBT_HT2_STEP(4) MSBT_HT2_STEP(5) MSBT_HT2_STEP(6) MSBT_HT2_STEP(7)
+            kb.advance8();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+kmer_count2_emit_kernel(const unsigned long long *__restrict__ tab, uint64_t n_slots, uint32_t min_abund, KmerSpec spec,
+                        uint32_t *__restrict__ out) {
+    for (uint64_t s = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; s < n_slots; s += (uint64_t)gridDim.x * blockDim.x) {
+        const unsigned long long w = tab[s];
+        if (w != 0ull && (w >> 62) >= min_abund) {
+            const uint64_t pos = msbt_position(msbt_kmer_hash(w & HT2_KEY_MASK, 0, spec.k, spec.pos.seed), spec.pos);
+            if (pos < spec.pos.num_bits) atomicOr(out + (pos >> 5), 1u << (pos & 31));
+        }
+    }
+}
+
 static uint32_t ceil_log2_u64(uint64_t x) {
     uint32_t l = 0;
     while ((1ull << l) < x && l < 63) l++;
@@ -1121,6 +1183,29 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
         }
     }
 
+    if (min_abund >= 2 && min_abund <= 3 && k <= 31) {
+        // compact table: 8 bytes per slot, load factor <= 2/3
+        uint64_t max_slots = 1024;
+        while (2 * max_slots < 3 * max_bases) max_slots <<= 1;
+        int rc = ensure_scratch(ctx, max_slots * 8);
+        if (rc) return rc;
+        unsigned long long *tab = (unsigned long long *)ctx->d_scratch;
+        for (uint32_t i = 0; i < n_genomes; i++) {
+            if (dg[i].n_bases < k) continue;
+            uint64_t slots = 1024;
+            while (2 * slots < 3ull * dg[i].n_bases) slots <<= 1;
+            CU_TRY(ctx, cudaMemsetAsync(tab, 0, slots * 8, stream));
+            const uint32_t n_words = (dg[i].n_bases + 31) / 32;
+            const int grid = (int)std::min<uint64_t>((n_words + TILE_THREADS - 1) / TILE_THREADS, (uint64_t)ctx->num_sms * 8);
+            kmer_count2_insert_kernel<<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, dg[i], k, tab, slots - 1);
+            LAUNCH_CHECK(ctx);
+            const int grid2 = (int)std::min<uint64_t>((slots + 255) / 256, (uint64_t)ctx->num_sms * 8);
+            kmer_count2_emit_kernel<<<grid2, 256, 0, stream>>>(tab, slots, min_abund, spec,
+                                                               (uint32_t *)(d_filters + dg[i].filter_word_off));
+            LAUNCH_CHECK(ctx);
+        }
+        return MSBT_OK;
+    }
     if (min_abund >= 2) {
         uint64_t n_slots = 1024;
         while (n_slots < 2 * max_bases) n_slots <<= 1;

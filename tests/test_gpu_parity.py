@@ -68,7 +68,7 @@ def test_makebf_skewed_inputs_overflow_path(ctx, oracle, variant):
         assert np.array_equal(g, oracle.makebf(f, k, num_bits, rolling=True))
 
 
-@pytest.mark.parametrize("k,min_abund", [(9, 2), (21, 2), (31, 3), (32, 2)])
+@pytest.mark.parametrize("k,min_abund", [(5, 2), (9, 2), (9, 3), (21, 2), (31, 2), (31, 3), (31, 4), (32, 2), (32, 3)])
 def test_makebf_min_abundance(ctx, oracle, k, min_abund):
     rng = random.Random(k * 7 + min_abund)
     base = util.messy_fasta(rng, 2, 3000, "ACGT")
@@ -281,3 +281,19 @@ def test_full_size_genomes_bit_exact_and_properties(ctx, oracle, variant):
     hits = ctx.query_batch(rows, [pos0]).cpu().numpy()[0]
     assert int(hits[0]) == pc[0] and int(hits[2]) == int(inter[1]) and int(hits[1]) == int(inter[0])
     assert 0.6 * pc[0] < int(hits[2]) < 0.85 * pc[0]  # a 1 % mutant shares about 0.99^31 = 73 % of its 31-mers
+
+
+@pytest.mark.parametrize("min_abund", [2, 3])
+def test_makebf_min_abundance_large_genome(ctx, oracle, min_abund):
+    """MetaSBT's CLI default (--min-kmer-occurrences 2) on a 1.2 Mbp genome with repeated segments, a low-complexity
+    stretch and an N run: exact canonical multiplicity (forward and reverse-complement copies count together)."""
+    from metasbt_b200 import ops
+    k, m = 31, 1 << 26
+    base = util.synthetic_codes(77, 1_000_000)
+    rc = (3 - base[200_000:260_000])[::-1]
+    codes = np.concatenate([base, base[100_000:180_000], rc, base[100_000:130_000], np.zeros(5000, dtype=np.uint8)])
+    fa = util.codes_to_fasta(codes, "rep", 80) + b">n\nACGT" + b"N" * 50 + b"ACGTACGTACGTACGTACGTACGTACGTACGTACGTAC" * 3 + b"\n"
+    _, got = build(ctx, [fa, b">tiny\nACGT\n"], k, m, min_abund=min_abund)
+    want = oracle.makebf(fa, k, m, min_abund)
+    assert np.array_equal(got[0], want)
+    assert oracle.bf_popcount(want) > 20_000 and oracle.bf_popcount(got[1]) == 0
