@@ -59,8 +59,20 @@ int msbt_fasta_pack(const char *text, size_t n, uint32_t min_run,
                     uint32_t *run_ends, size_t run_cap,
                     uint64_t *n_bases_out, uint64_t *n_runs_out);
 
+/* The same packing ON THE DEVICE for a batch of FASTA files: `d_text` holds the files back to back,
+ * h_offsets (host, n_files + 1 entries) delimits them.  Genome i is written at a position derived from the file sizes
+ * only (every byte counted as a base, so nothing depends on the parse): packed words from
+ * sum_{j<i} (ceil(len_j / 32) + MSBT_PACK_PAD_WORDS), run ends from sum_{j<i} (len_j / max(min_run, 1) + 1); the caller
+ * sizes d_packed / d_run_ends accordingly (MSBT_ENOSPC otherwise).  h_descs (host, n_files entries) receives the
+ * descriptors msbt_kmer_bloom_build takes (filter_index = i).  Result identical to msbt_fasta_pack per file.
+ * Synchronises `stream` twice (the parse decides how many runs exist). */
+struct msbt_genome_desc_s;
+int msbt_fasta_pack_device(msbt_ctx *ctx, const char *d_text, const uint64_t *h_offsets, uint32_t n_files, uint32_t min_run,
+                           uint64_t *d_packed, uint64_t packed_cap_words, uint32_t *d_run_ends, uint64_t run_cap,
+                           struct msbt_genome_desc_s *h_descs, void *stream);
+
 /* One genome of a construction / query batch. */
-typedef struct {
+typedef struct msbt_genome_desc_s {
     uint64_t packed_word_off; /* first word of this genome inside d_packed */
     uint64_t n_bases;         /* valid bases (< 2^32) */
     uint64_t run_off;         /* first entry of this genome inside d_run_ends */

@@ -24,7 +24,7 @@ NVCC_FLAGS = [
 # every symbol include/msbt.h declares; tests check that the library exports all of them
 SYMBOLS = [
     "msbt_abi_version", "msbt_ctx_create", "msbt_ctx_destroy", "msbt_last_error", "msbt_sync",
-    "msbt_launch_count", "msbt_fasta_pack", "msbt_kmer_bloom_build", "msbt_bf_or_reduce",
+    "msbt_launch_count", "msbt_fasta_pack", "msbt_fasta_pack_device", "msbt_kmer_bloom_build", "msbt_bf_or_reduce",
     "msbt_bf_popcount", "msbt_bf_and_popcount_1vN", "msbt_bf_and_popcount_allpairs",
     "msbt_bf_extract_positions", "msbt_bf_extract_positions_batch", "msbt_query_batch", "msbt_bitslice_build", "msbt_query_batch_sliced",
 ]
@@ -90,6 +90,8 @@ def lib() -> ctypes.CDLL:
     L.msbt_launch_count.restype = u64
     L.msbt_fasta_pack.argtypes = [ctypes.c_char_p, sz, u32, vp, sz, vp, sz, P(u64), P(u64)]
     L.msbt_fasta_pack.restype = i32
+    L.msbt_fasta_pack_device.argtypes = [vp, vp, P(u64), u32, u32, vp, u64, vp, u64, P(GenomeDesc), vp]
+    L.msbt_fasta_pack_device.restype = i32
     L.msbt_kmer_bloom_build.argtypes = [vp, vp, vp, P(GenomeDesc), u32, u32, u64, u64, u64, u32, vp, u64, i32, vp]
     L.msbt_kmer_bloom_build.restype = i32
     L.msbt_bf_or_reduce.argtypes = [vp, P(vp), u32, u64, vp, vp]

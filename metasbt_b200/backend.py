@@ -30,15 +30,14 @@ def read_fasta_bytes(path: str) -> bytes:
         return f.read()
 
 
-def pack_files(paths: Sequence[str], kmer_size: int, threads: Optional[int] = None) -> List["ops.PackedGenome"]:
-    """Read and 2-bit pack many FASTA files on a thread pool (msbt_fasta_pack releases the GIL): the host-side
-    ingest is the slowest stage in front of K1 (about 175 MB/s per core), so it is spread over the host cores."""
+def read_files(paths: Sequence[str], threads: Optional[int] = None) -> List[bytes]:
+    """Read many FASTA files on a thread pool (file reads release the GIL)."""
     from concurrent.futures import ThreadPoolExecutor
     threads = threads or min(32, os.cpu_count() or 1)
     if len(paths) <= 1 or threads <= 1:
-        return [ops.pack_fasta(read_fasta_bytes(p), kmer_size) for p in paths]
+        return [read_fasta_bytes(p) for p in paths]
     with ThreadPoolExecutor(max_workers=threads) as ex:
-        return list(ex.map(lambda p: ops.pack_fasta(read_fasta_bytes(p), kmer_size), paths))
+        return list(ex.map(read_fasta_bytes, paths))
 
 
 class CudaBackend:
@@ -96,8 +95,8 @@ class CudaBackend:
         """howdesbt makebf --k --min --bits --hashes=1 --seed=0,0 <fasta> --out=<bf> for every pair."""
         for lo in range(0, len(fasta_paths), self.sketch_batch):
             fa = fasta_paths[lo: lo + self.sketch_batch]
-            packed = pack_files(fa, self.k)
-            batch = ops.GenomeBatch(packed, self.ctx.device)
+            # raw FASTA text goes host -> device once; parsing and 2-bit packing happen on the GPU (msbt_fasta_pack_device)
+            batch = self.ctx.pack_fasta_device(read_files(fa), self.k)
             filt = self.ctx.build_filters(batch, self.k, self.num_bits, min_abund=min_abund)
             for i, out in enumerate(out_paths[lo: lo + self.sketch_batch]):
                 row = filt[i].clone()
@@ -106,8 +105,7 @@ class CudaBackend:
 
     def sketch_resident(self, fasta_paths: Sequence[str], min_abund: int = 1) -> torch.Tensor:
         """Filters of the given FASTA files left on the device only (query side of `profile`)."""
-        packed = pack_files(fasta_paths, self.k)
-        batch = ops.GenomeBatch(packed, self.ctx.device)
+        batch = self.ctx.pack_fasta_device(read_files(fasta_paths), self.k)
         return self.ctx.build_filters(batch, self.k, self.num_bits, min_abund=min_abund)
 
     # ------------------------------------------------------------------ bfoperate --or

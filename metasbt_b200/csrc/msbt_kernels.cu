@@ -1248,6 +1248,97 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
     return MSBT_OK;
 }
 
+// --------------------------------------------------------------------------- device FASTA ingest (msbt_ingest.cuh)
+#include "msbt_ingest.cuh"
+
+extern "C" int msbt_fasta_pack_device(msbt_ctx *ctx, const char *d_text, const uint64_t *h_offsets, uint32_t n_files,
+                                      uint32_t min_run, uint64_t *d_packed, uint64_t packed_cap_words, uint32_t *d_run_ends,
+                                      uint64_t run_cap, msbt_genome_desc *h_descs, void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_files == 0) return MSBT_OK;
+    if (!h_offsets || !h_descs || !d_packed || !d_run_ends) return fail(ctx, MSBT_EINVAL, "fasta_pack_device: null argument");
+    if (min_run > 64) return fail(ctx, MSBT_EINVAL, "fasta_pack_device: min_run > 64");
+    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    std::vector<FpFile> files(n_files);
+    uint64_t chunks = 0, words = 0, runs = 0;
+    const uint64_t need = std::max<uint32_t>(min_run, 1);
+    for (uint32_t i = 0; i < n_files; i++) {
+        if (h_offsets[i + 1] < h_offsets[i]) return fail(ctx, MSBT_EINVAL, "fasta_pack_device: offsets must be non-decreasing");
+        const uint64_t len = h_offsets[i + 1] - h_offsets[i];
+        if (len >> 32) return fail(ctx, MSBT_EINVAL, "fasta_pack_device: file %u has >= 2^32 bytes", i);
+        files[i].text_off = h_offsets[i];
+        files[i].text_len = len;
+        files[i].chunk_begin = (uint32_t)chunks;
+        files[i].n_chunks = (uint32_t)((len + FP_CHUNK - 1) / FP_CHUNK);
+        files[i].packed_word_off = words;
+        files[i].run_off = runs;
+        files[i].bt_off = 0;
+        chunks += files[i].n_chunks;
+        words += (len + 31) / 32 + MSBT_PACK_PAD_WORDS;  // upper bound: every byte a base
+        runs += len / need + 1;
+        if (chunks >> 31) return fail(ctx, MSBT_EINVAL, "fasta_pack_device: batch too large");
+    }
+    if (words > packed_cap_words) return fail(ctx, MSBT_ENOSPC, "fasta_pack_device: packed buffer needs %llu words", (unsigned long long)words);
+    if (runs > run_cap) return fail(ctx, MSBT_ENOSPC, "fasta_pack_device: run table needs %llu entries", (unsigned long long)runs);
+    if (chunks && !d_text) return fail(ctx, MSBT_EINVAL, "fasta_pack_device: null text");
+    const uint32_t n_chunks = (uint32_t)chunks;
+    // scratch: [files][summary][state][chunk_bases][chunk_breaks][totals 2 x u64][out_totals 2 x u64]
+    const size_t f_b = align_up(sizeof(FpFile) * n_files, 256), c_b = align_up((size_t)n_chunks * 4 + 4, 256), t_b = align_up((size_t)n_files * 16, 256);
+    int rc = ensure_scratch(ctx, f_b + 4 * c_b + 2 * t_b);
+    if (rc) return rc;
+    char *S = (char *)ctx->d_scratch;
+    FpFile *d_files = (FpFile *)S;
+    uint32_t *d_sum = (uint32_t *)(S + f_b), *d_state = (uint32_t *)(S + f_b + c_b);
+    uint32_t *d_cb = (uint32_t *)(S + f_b + 2 * c_b), *d_ck = (uint32_t *)(S + f_b + 3 * c_b);
+    unsigned long long *d_tot = (unsigned long long *)(S + f_b + 4 * c_b), *d_out = (unsigned long long *)(S + f_b + 4 * c_b + t_b);
+    CU_TRY(ctx, cudaMemcpyAsync(d_files, files.data(), sizeof(FpFile) * n_files, cudaMemcpyHostToDevice, stream));
+    CU_TRY(ctx, cudaMemsetAsync(d_packed, 0, words * 8, stream));
+    const uint8_t *text = (const uint8_t *)d_text;
+    std::vector<unsigned long long> tot(2 * (size_t)n_files, 0), out(2 * (size_t)n_files, 0);
+    uint32_t *d_bt = nullptr;
+    if (n_chunks) {
+        fp_line_summary_kernel<<<n_chunks, FP_THREADS, 0, stream>>>(text, d_files, n_files, n_chunks, d_sum);
+        LAUNCH_CHECK(ctx);
+        fp_line_state_kernel<<<n_files, 1024, 0, stream>>>(d_files, d_sum, d_state);
+        LAUNCH_CHECK(ctx);
+        fp_count_kernel<<<n_chunks, FP_THREADS, 0, stream>>>(text, d_files, n_files, n_chunks, d_state, d_cb, d_ck);
+        LAUNCH_CHECK(ctx);
+        fp_chunk_scan_kernel<<<n_files, 1024, 0, stream>>>(d_files, d_cb, d_ck, d_tot);
+        LAUNCH_CHECK(ctx);
+        CU_TRY(ctx, cudaMemcpyAsync(tot.data(), d_tot, sizeof(unsigned long long) * 2 * n_files, cudaMemcpyDeviceToHost, stream));
+        CU_TRY(ctx, cudaStreamSynchronize(stream));
+        uint64_t breaks = 0;
+        for (uint32_t i = 0; i < n_files; i++) { files[i].bt_off = breaks; breaks += tot[2 * i + 1]; }
+        // break table (breaks entries) and kp table (breaks + n_files entries)
+        if (cudaMalloc(&d_bt, (2 * breaks + n_files + 1) * 4) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(ctx, MSBT_ENOMEM, "fasta_pack_device: cudaMalloc of the run tables failed");
+        }
+        uint32_t *d_kp = d_bt + breaks;
+        CU_TRY(ctx, cudaMemcpyAsync(d_files, files.data(), sizeof(FpFile) * n_files, cudaMemcpyHostToDevice, stream));
+        fp_break_table_kernel<<<n_chunks, FP_THREADS, 0, stream>>>(text, d_files, n_files, n_chunks, d_state, d_cb, d_ck, d_bt);
+        LAUNCH_CHECK(ctx);
+        fp_run_scan_kernel<<<n_files, 1024, 0, stream>>>(d_files, d_tot, d_bt, min_run, d_kp, d_run_ends, d_out);
+        LAUNCH_CHECK(ctx);
+        fp_emit_kernel<<<n_chunks, FP_THREADS, 0, stream>>>(text, d_files, n_files, n_chunks, d_state, d_cb, d_ck, d_tot, d_bt, d_kp,
+                                                          min_run, (unsigned long long *)d_packed);
+        LAUNCH_CHECK(ctx);
+        CU_TRY(ctx, cudaMemcpyAsync(out.data(), d_out, sizeof(unsigned long long) * 2 * n_files, cudaMemcpyDeviceToHost, stream));
+        const cudaError_t e = cudaStreamSynchronize(stream);
+        cudaFree(d_bt);
+        if (e != cudaSuccess) return fail(ctx, MSBT_ECUDA, "fasta_pack_device: %s", cudaGetErrorString(e));
+    }
+    for (uint32_t i = 0; i < n_files; i++) {
+        h_descs[i].packed_word_off = files[i].packed_word_off;
+        h_descs[i].n_bases = files[i].n_chunks ? out[2 * i] : 0;
+        h_descs[i].run_off = files[i].run_off;
+        h_descs[i].n_runs = files[i].n_chunks ? (uint32_t)out[2 * i + 1] : 0;
+        h_descs[i].filter_index = i;
+    }
+    return MSBT_OK;
+}
+
 // --------------------------------------------------------------------------- K2 / K3 filter algebra
 
 __device__ __forceinline__ uint4 ld_stream(const uint4 *p) {

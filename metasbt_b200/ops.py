@@ -138,6 +138,20 @@ class GenomeBatch:
         self.h2d_bytes = self.d_words.numel() * 8 + self.d_runs.numel() * 4
         return self
 
+    @classmethod
+    def from_device_pack(cls, d_words: torch.Tensor, d_runs: torch.Tensor, descs, n: int, device: torch.device,
+                         h2d_bytes: int = 0) -> "GenomeBatch":
+        """Batch whose packed words / run table were produced on the device (Context.pack_fasta_device)."""
+        self = cls.__new__(cls)
+        self.n = n
+        self.descs = descs
+        self.total_bases = int(sum(descs[i].n_bases for i in range(n)))
+        self.device = device
+        self.d_words, self.d_runs = d_words, d_runs
+        self.h_words = self.h_runs = None
+        self.h2d_bytes = h2d_bytes
+        return self
+
     def to_device(self, non_blocking: bool = True) -> "GenomeBatch":
         self.d_words = self.h_words.to(self.device, non_blocking=non_blocking)
         self.d_runs = self.h_runs.to(self.device, non_blocking=non_blocking)
@@ -198,6 +212,33 @@ class Context:
     def alloc_filters(self, n: int, num_bits: int) -> torch.Tensor:
         """Uninitialised [n, stride] int64 matrix; row i is filter i (first filter_words(num_bits) words)."""
         return torch.empty((n, filter_stride_words(num_bits)), dtype=torch.int64, device=self.device)
+
+    # ------------------------------------------------------------------ FASTA ingest on the device (N1)
+    def pack_fasta_device(self, texts: Sequence[bytes], min_run: int) -> GenomeBatch:
+        """FASTA texts (one per genome) -> GenomeBatch, parsed and 2-bit packed ON THE DEVICE (msbt_fasta_pack_device):
+        the raw text is copied host -> device once and never touched by the CPU.  Same result as pack_fasta()."""
+        n = len(texts)
+        sizes = [len(t) for t in texts]
+        offs = (ctypes.c_uint64 * (n + 1))()
+        for i, sz in enumerate(sizes):
+            offs[i + 1] = offs[i] + sz
+        total = int(offs[n])
+        h_text = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=True)
+        hv = h_text.numpy()
+        for i, t in enumerate(texts):
+            if sizes[i]:
+                hv[offs[i]: offs[i + 1]] = np.frombuffer(t, dtype=np.uint8)
+        d_text = h_text.to(self.device, non_blocking=True)
+        need = max(int(min_run), 1)
+        n_words = sum((sz + 31) // 32 + _lib.PACK_PAD_WORDS for sz in sizes)
+        n_runs = sum(sz // need + 1 for sz in sizes)
+        d_words = torch.empty(max(n_words, 1), dtype=torch.int64, device=self.device)
+        d_runs = torch.empty(max(n_runs, 1), dtype=torch.int32, device=self.device)
+        descs = (_lib.GenomeDesc * max(n, 1))()
+        rc = self._L.msbt_fasta_pack_device(self._h, d_text.data_ptr(), offs, n, int(min_run), d_words.data_ptr(), d_words.numel(),
+                                            d_runs.data_ptr(), d_runs.numel(), descs, self._stream())
+        self._check(rc, "msbt_fasta_pack_device")
+        return GenomeBatch.from_device_pack(d_words, d_runs, descs, n, self.device, h2d_bytes=total)
 
     # ------------------------------------------------------------------ K1
     def build_filters(self, batch: GenomeBatch, k: int, num_bits: int, min_abund: int = 1, seed: int = 0,

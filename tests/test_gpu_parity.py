@@ -297,3 +297,52 @@ def test_makebf_min_abundance_large_genome(ctx, oracle, min_abund):
     want = oracle.makebf(fa, k, m, min_abund)
     assert np.array_equal(got[0], want)
     assert oracle.bf_popcount(want) > 20_000 and oracle.bf_popcount(got[1]) == 0
+
+
+def _ingest_cases():
+    rng = random.Random(42)
+    big_line = b">one_line\n" + util.codes_to_fasta(util.synthetic_codes(5, 20000), "x", 0).split(b"\n", 1)[1]
+    long_header = b">" + b"h" * 9000 + b"\nACGTACGTACGTAAACCCGGGTTT\n"
+    return [
+        util.messy_fasta(rng, 4, 3000),
+        util.messy_fasta(rng, 2, 9000, "ACGTacgtNn"),
+        b"", b">only_header", b">only_header\n", b"\n\n\n", b"ACGT", b"ACGTACGTACGTACGTACGTACGTACGTACGTACG",   # no header, no newline
+        b">a\r\nACGTACGTAC\r\nGGGTTTAAAC\r\n>b\r\nTTTT\r\n",
+        b">a\nACGT>ACGTNACGT\n >notheader\nACGTACGTACGT\n",
+        big_line, long_header,
+        b">x\n" + b"ACGTTGCA" * 512 + b"\n" + b"ACGTTGCA" * 511 + b"ACGTTG\n",            # lines ending exactly on a chunk boundary
+        b">x\n" + b"A" * 4093 + b"\n>" + b"y" * 4095 + b"\nCCCCCCCCCCGGGGGGGGGG\n",       # header starting at a chunk's first byte
+        util.codes_to_fasta(util.synthetic_codes(9, 300_000), "big", 80),
+        b">n\n" + b"N" * 10000 + b"ACGTACGTACGTACGTAGCTAGCTAGCTAGCATCGATCAGCTAC" + b"N" * 5000 + b"\n",
+    ]
+
+
+@pytest.mark.parametrize("min_run", [0, 1, 5, 31, 64])
+def test_fasta_pack_device_matches_host_packer(ctx, min_run):
+    """Device FASTA ingest (msbt_fasta_pack_device) == host packer (msbt_fasta_pack), file by file: packed words incl. the
+    zero padding, run table, base and run counts -- messy records, CRLF, '>' inside a line, headers and lines longer than
+    a chunk, chunk-aligned line ends, empty files, N runs."""
+    from metasbt_b200 import ops
+    texts = _ingest_cases()
+    batch = ctx.pack_fasta_device(texts, min_run)
+    torch.cuda.synchronize()
+    words = batch.d_words.cpu().numpy().view(np.uint64)
+    runs = batch.d_runs.cpu().numpy().view(np.uint32)
+    for i, t in enumerate(texts):
+        ref = ops.pack_fasta(t, min_run)
+        d = batch.descs[i]
+        assert int(d.n_bases) == ref.n_bases, (i, int(d.n_bases), ref.n_bases)
+        assert int(d.n_runs) == len(ref.run_ends), i
+        assert np.array_equal(words[d.packed_word_off: d.packed_word_off + len(ref.words)], ref.words), i
+        assert np.array_equal(runs[d.run_off: d.run_off + d.n_runs], ref.run_ends), i
+
+
+def test_fasta_pack_device_feeds_k1(ctx, oracle):
+    texts = _ingest_cases()
+    k, m = 21, 1 << 20
+    batch = ctx.pack_fasta_device(texts, k)
+    out = ctx.build_filters(batch, k, m)
+    torch.cuda.synchronize()
+    w = 1 << 14
+    for i, t in enumerate(texts):
+        assert np.array_equal(to_np(out[i, :w]), oracle.makebf(t, k, m)), i

@@ -69,6 +69,31 @@ def run(ctx, n_leaves=1024, filter_bits=1 << 28, n_mags=64, genome_bp=5_000_000,
                                          note="exact canonical k-mer multiplicity per genome (hash table), not a bandwidth-roofline path")
     del tmp, sub
 
+    # N1: FASTA text -> packed genomes on the device (the stage in front of K1), from host bytes, H2D included
+    try:
+        from tests import util
+        n_fa = 32
+        texts = [util.codes_to_fasta(util.synthetic_codes(0x5EED0000 + g, genome_bp), "g%d" % g, 80) for g in range(4)]
+        texts = [texts[i % 4] for i in range(n_fa)]
+        nbytes = sum(len(t) for t in texts)
+        import time as _time_mod
+        ctx.pack_fasta_device(texts, k)
+        torch.cuda.synchronize()
+        t0 = _time_mod.perf_counter()
+        fb = ctx.pack_fasta_device(texts, k)
+        torch.cuda.synchronize()
+        dt = _time_mod.perf_counter() - t0
+        out["N1_fasta_ingest_device_%d" % n_fa] = {"ms": dt * 1e3, "text_GB": nbytes / 1e9, "GBps_text": nbytes / dt / 1e9,
+                                                   "Mbp_per_s": fb.total_bases / dt / 1e6, "genomes_per_s": n_fa / dt,
+                                                   "note": "wall clock from host bytes: copy into pinned memory + H2D + 7 kernels + 2 syncs"}
+        t0 = _time_mod.perf_counter()
+        ops.pack_fasta(texts[0], k)
+        dth = _time_mod.perf_counter() - t0
+        out["N1_fasta_ingest_host_1thread"] = {"ms_per_genome": dth * 1e3, "Mbp_per_s": genome_bp / dth / 1e6}
+        del fb
+    except Exception as exc:
+        out["N1_fasta_ingest_device"] = {"error": repr(exc)}
+
     # K2: cluster filter = OR of C children
     C = min(100, L)
     t = _time(lambda: ctx.bf_or(rows[:C], m))
