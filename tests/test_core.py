@@ -34,6 +34,34 @@ def _diff(a, b, path=""):
     return []
 
 
+def _reference_golden():
+    with open(os.path.join(GOLDEN, "config1_reference.json")) as f:
+        return json.load(f)
+
+
+def _order_insensitive(snap):
+    """The reference writes child lists by iterating a Python set (core.py:3746-3776, 3870-3875: order depends on
+    PYTHONHASHSEED); this code writes them sorted.  Compare `<name>.txt` and `index.detbrief.sbt` as: first line of the
+    tree (the cluster's own filter) + the multiset of the remaining lines."""
+    out = json.loads(json.dumps(snap))
+    for rel, lines in out["text"].items():
+        if rel.endswith(".sbt"):
+            out["text"][rel] = [lines[0]] + sorted(lines[1:])
+        elif rel.endswith(".txt") and rel.startswith("clusters"):
+            out["text"][rel] = sorted(lines)
+    return out
+
+
+def test_config1_matches_reference_python(tmp_path, oracle):
+    """Tier-2 parity: tests/golden/config1_reference.json was produced by the UNMODIFIED reference
+    metasbt/core.py (Database.set_configs/add/update/_profile, Entry.sketch/index/get_density/get_boundaries, Database.dist)
+    driving a stand-in `howdesbt` served by the oracle (tests/golden/make_reference_golden.py).  This repo's own
+    Database/Entry/CLI must give the same database: every .bf byte, clusters.tsv (densities, centroids, ANI boundaries),
+    genomes.tsv, metadata.json and every profile table -- identical up to the order of child lines."""
+    snap = snapshot.run_config1(str(tmp_path), backend=cpu_backend.OracleBackend(dataset.K, dataset.FILTER_BITS))
+    assert _diff(_order_insensitive(snap), _order_insensitive(_reference_golden())) == []
+
+
 def test_config1_oracle_backend_matches_golden(tmp_path, oracle):
     snap = snapshot.run_config1(str(tmp_path), backend=cpu_backend.OracleBackend(dataset.K, dataset.FILTER_BITS))
     assert _diff(snap, _golden()) == []
@@ -107,3 +135,4 @@ def test_config1_cuda_backend_matches_golden(tmp_path, ctx):
     from metasbt_b200 import ops
     assert ops.default_context().launch_count > 0  # the CUDA kernels really ran
     assert _diff(snap, _golden()) == []
+    assert _diff(_order_insensitive(snap), _order_insensitive(_reference_golden())) == []  # == the reference's own Python
