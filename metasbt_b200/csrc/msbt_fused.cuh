@@ -71,6 +71,8 @@ struct FusedParams {
     uint32_t tiles_per_bucket_log2;
     uint32_t gcap;           // ring entries per bucket (multiple of 4)
     uint32_t ring;           // genomes in flight
+    uint32_t fast_b;         // 1: bucket == one full 64 KiB tile, every destination 16-byte aligned (the lean B loop applies)
+    uint32_t nb_magic;       // ceil(2^32 / NB): item / NB == umulhi(item, nb_magic) for item < n_items
     uint64_t words;          // u64 words per filter
     uint32_t *sync;          // [0] next chunk, [1] next item
     uint32_t *done;          // [n_genomes]
@@ -349,6 +351,7 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
         uint32_t n_raw = 0;
 
 #define FU_B_WANT(it) (((P.genomes[(it) / NB].n_bases + FU_CHUNK_BASES - 1) / FU_CHUNK_BASES) * (FU_P_THREADS / 32))
+#define FU_B_WANT_G(g) (((P.genomes[(g)].n_bases + FU_CHUNK_BASES - 1) / FU_CHUNK_BASES) * (FU_P_THREADS / 32))
 #define FU_B_ISSUE_LOADS(it)                                                                       \
     {                                                                                              \
         const uint32_t gi_ = claim[5], b_ = (it) - gi_ * NB, slot_ = claim[6];                     \
@@ -363,6 +366,89 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
         const uint32_t v_ = (((x) >> P.tile_log2) == tf) ? (1u << ((x) & 31)) : 0u;                \
         asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(saddr + (((x) >> 3) & word_mask)), "r"(v_) : "memory"); \
     }
+
+        if (P.fast_b) {
+            // ---- lean loop for the common geometry (bucket == one full 64 KiB tile): 3 barriers per tile and as few
+            // instructions as possible -- next to hashing warps a B warp only issues once every ~30 cycles, so the
+            // length of its instruction stream IS its latency.
+            //   A  zero the tile                                   (tid 32 resolves the next claim meanwhile)   bar
+            //   B  OR the positions in, fence.proxy.async                                                       bar
+            //   C  tid 0: bulk store, then wait for its smem read-out;  all: prefetch the next item's positions bar
+            constexpr uint32_t TILE_VEC = FU_TILE_BYTES / 16;
+            const uint32_t word_mask = ((FU_TILE_BYTES * 8 - 1) >> 3) & ~3u;
+            uint32_t pend = 0;
+            if (tid == 32) {
+                const uint32_t it = atomicAdd(P.sync + 1, 1u);
+                pend = atomicAdd(P.sync + 1, 1u);
+                const uint32_t g = __umulhi(it, P.nb_magic);
+                if (it < n_items) fu_wait_ge(P.done + g, FU_B_WANT_G(g));
+                claim[4] = it;
+                claim[5] = g;
+            }
+            fu_bar(2, FU_B_THREADS);
+            uint32_t item = claim[4], gi = claim[5];
+#define FU_B_FAST_LOADS()                                                                              \
+    {                                                                                                  \
+        const uint32_t b_ = item - gi * NB;                                                            \
+        const uint4 *src_ = (const uint4 *)(P.gbuf + ((uint64_t)(gi % P.ring) * NB + b_) * P.gcap);    \
+        n_raw = __ldcg(P.gcnt + (uint64_t)gi * NB + b_);                                               \
+        _Pragma("unroll") for (int u = 0; u < FU_REG_QUADS; u++)                                       \
+            e[u] = __ldcg(src_ + min(u * FU_B_THREADS + tid, (P.gcap >> 2) - 1u));                     \
+    }
+#define FU_B_OR1(x) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(saddr + (((x) >> 3) & word_mask)), "r"(1u << ((x) & 31)) : "memory");
+            if (item < n_items) FU_B_FAST_LOADS()
+            while (item < n_items) {
+                uint32_t nxt = 0, nxt_gi = 0, nxt_done = 0;
+                if (tid == 32) {
+                    nxt = pend;
+                    pend = atomicAdd(P.sync + 1, 1u);
+                    nxt_gi = __umulhi(nxt, P.nb_magic);
+                    if (nxt < n_items) nxt_done = fu_ld_acquire(P.done + nxt_gi);
+                }
+                const uint32_t cur_gi = gi;
+                const uint32_t b = item - gi * NB;
+                uint64_t *dst = P.filters + P.genomes[gi].filter_word_off + (uint64_t)b * (FU_TILE_BYTES / 8);
+                // A
+                uint4 *tv = (uint4 *)tile;
+#pragma unroll
+                for (uint32_t i = 0; i < (TILE_VEC + FU_B_THREADS - 1) / FU_B_THREADS; i++)
+                    if (i * FU_B_THREADS + tid < TILE_VEC) tv[i * FU_B_THREADS + tid] = make_uint4(0, 0, 0, 0);
+                const uint32_t n = min(n_raw, P.gcap);
+                if (tid == 32) {
+                    if (nxt < n_items && nxt_done < FU_B_WANT_G(nxt_gi)) fu_wait_ge(P.done + nxt_gi, FU_B_WANT_G(nxt_gi));
+                    claim[4] = nxt;
+                    claim[5] = nxt_gi;
+                }
+                fu_bar(2, FU_B_THREADS);
+                // B
+#pragma unroll
+                for (int u = 0; u < FU_REG_QUADS; u++)
+                    if ((u * FU_B_THREADS + tid) * 4u < n) { FU_B_OR1(e[u].x) FU_B_OR1(e[u].y) FU_B_OR1(e[u].z) FU_B_OR1(e[u].w) }
+                if (n > FU_REG_ENTRIES * FU_B_THREADS) {  // oversized bucket (skewed input)
+                    const uint32_t *src = P.gbuf + ((uint64_t)(gi % P.ring) * NB + b) * P.gcap;
+                    for (uint32_t i = FU_REG_ENTRIES * FU_B_THREADS + tid; i < n; i += FU_B_THREADS) {
+                        const uint32_t p = __ldcg(src + i);
+                        FU_B_OR1(p)
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                fu_bar(2, FU_B_THREADS);
+                // C
+                item = claim[4];
+                gi = claim[5];
+                if (item < n_items) FU_B_FAST_LOADS()
+                if (tid == 0) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(saddr), "r"(FU_TILE_BYTES), "l"(evict_first) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                }
+                if (tid == 64) atomicAdd(P.consumed + cur_gi, 1u);
+                fu_bar(2, FU_B_THREADS);
+            }
+#undef FU_B_OR1
+#undef FU_B_FAST_LOADS
+            return;
+        }
 
         // Three lanes of different warps carry the long-latency control operations so that none of them
         // serialises behind another: tid 0 issues / drains the bulk stores, tid 32 claims items (two ahead, so
@@ -476,6 +562,7 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
         }
 #undef FU_B_OR
 #undef FU_B_ISSUE_LOADS
+#undef FU_B_WANT_G
 #undef FU_B_WANT
         if (store_pending && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }

@@ -917,6 +917,12 @@ static int build_fused(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *
     P.words = words;
     P.n_genomes = n_genomes;
     P.n_chunks_total = (uint32_t)fchunks;
+    P.nb_magic = (uint32_t)(((1ull << 32) + NB - 1) / NB);
+    // lean B loop: bucket == one full 64 KiB tile, every tile complete, every destination 16-byte aligned
+    P.fast_b = (shift == FU_TILE_LOG2) && (num_bits % (1ull << FU_TILE_LOG2) == 0) && ((((uintptr_t)d_filters) & 15) == 0);
+    for (const DevGenome &g : dg) P.fast_b = P.fast_b && ((g.filter_word_off & 1) == 0);
+    // exactness of item / NB by multiply-high: item * (magic * NB - 2^32) < 2^32
+    if (P.fast_b && (uint64_t)n_genomes * NB * ((uint64_t)P.nb_magic * NB - (1ull << 32)) >= (1ull << 32)) P.fast_b = 0;
 
     uint64_t max_kmers = 0;
     for (const DevGenome &g : dg) max_kmers = std::max<uint64_t>(max_kmers, g.n_bases >= k ? (uint64_t)g.n_bases - k + 1 : 0);
@@ -1572,7 +1578,7 @@ extern "C" int msbt_bf_popcount(msbt_ctx *ctx, const uint64_t *const *h_filters,
     if (rc) return rc;
     CU_TRY(ctx, cudaMemsetAsync(d_out, 0, (size_t)n * 8, stream));
     const uint64_t vec = std::max<uint64_t>(words >> 1, 1);
-    uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((vec + 255) / 256, std::max<uint64_t>(1, (uint64_t)ctx->num_sms * 8 / n)));
+    uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((vec + 255) / 256, std::max<uint64_t>(1, ((uint64_t)ctx->num_sms * 32 + n - 1) / n)));
     for (uint32_t off = 0; off < n; off += 65535) {
         uint32_t cnt = std::min<uint32_t>(65535, n - off);
         bf_popcount_kernel<<<dim3((unsigned)gx, cnt), 256, 0, stream>>>(d_f + off, words, (unsigned long long *)d_out + off);
