@@ -28,7 +28,7 @@
 #pragma once
 
 #ifndef MSBT_FU_P_THREADS
-#define MSBT_FU_P_THREADS 576
+#define MSBT_FU_P_THREADS 640
 #endif
 constexpr int FU_P_THREADS = MSBT_FU_P_THREADS;      // partition warps (role P)
 constexpr int FU_THREADS = 1024;
