@@ -940,7 +940,7 @@ static int build_fused(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *
         P.gcap = (uint32_t)cap;
     }
     const uint64_t slot_bytes = (uint64_t)NB * P.gcap * 4;
-    P.ring = (uint32_t)std::max<uint64_t>(2, std::min<uint64_t>(4, (72ull << 20) / std::max<uint64_t>(slot_bytes, 1)));
+    P.ring = (uint32_t)std::max<uint64_t>(2, std::min<uint64_t>(4, (100ull << 20) / std::max<uint64_t>(slot_bytes, 1)));
 
     // scratch: [genome table][sync 64 B][done][consumed][dirty][gcnt n_genomes x NB] | [gbuf ring x NB x gcap]
     const size_t t_b = align_up(sizeof(DevGenome) * n_genomes, 256);
@@ -1046,7 +1046,7 @@ static int build_phased(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t 
         P.gcap = (uint32_t)cap;
     }
     const uint64_t slot_bytes = (uint64_t)NB * P.gcap * 4;
-    P.ring = (uint32_t)std::max<uint64_t>(2, std::min<uint64_t>(4, (72ull << 20) / std::max<uint64_t>(slot_bytes, 1)));
+    P.ring = (uint32_t)std::max<uint64_t>(2, std::min<uint64_t>(4, (100ull << 20) / std::max<uint64_t>(slot_bytes, 1)));
 
     // scratch: [genome table][sync 256 B][done][consumed][dirty][gcnt n_genomes x NB] | [gbuf ring x NB x gcap]
     const size_t t_b = align_up(sizeof(DevGenome) * n_genomes, 256);
