@@ -98,10 +98,27 @@ class CudaBackend:
             # raw FASTA text goes host -> device once; parsing and 2-bit packing happen on the GPU (msbt_fasta_pack_device)
             batch = self.ctx.pack_fasta_device(read_files(fa), self.k)
             filt = self.ctx.build_filters(batch, self.k, self.num_bits, min_abund=min_abund)
-            for i, out in enumerate(out_paths[lo: lo + self.sketch_batch]):
-                row = filt[i].clone()
-                self._write(out, row)
-                self._put(out, row)
+            outs = out_paths[lo: lo + self.sketch_batch]
+            # device -> pinned host copies are queued back to back; the `.bf` files are written by a small thread pool
+            # while the next copies are in flight (file writes release the GIL)
+            from concurrent.futures import ThreadPoolExecutor
+            header = bffile.BloomHeader(kmer_size=self.k, num_bits=self.num_bits)
+            with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as pool:
+                pending = []
+                for i, out in enumerate(outs):
+                    row = filt[i].clone()
+                    host = torch.empty(self.words, dtype=torch.int64, pin_memory=True)
+                    host.copy_(row[: self.words], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record()
+
+                    def write(out=out, host=host, done=done):
+                        done.synchronize()
+                        bffile.write_bf(out, header, host.numpy().view(np.uint64))
+                    pending.append(pool.submit(write))
+                    self._put(out, row)
+                for job in pending:
+                    job.result()
 
     def sketch_resident(self, fasta_paths: Sequence[str], min_abund: int = 1) -> torch.Tensor:
         """Filters of the given FASTA files left on the device only (query side of `profile`)."""
