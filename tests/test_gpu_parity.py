@@ -346,3 +346,24 @@ def test_fasta_pack_device_feeds_k1(ctx, oracle):
     w = 1 << 14
     for i, t in enumerate(texts):
         assert np.array_equal(to_np(out[i, :w]), oracle.makebf(t, k, m)), i
+
+
+@pytest.mark.parametrize("num_bits", [1 << 32, (1 << 32) + 64])
+def test_makebf_maximum_filter_size(ctx, oracle, num_bits):
+    """The largest filter the u32-position kernels take (2^32 bits = 512 MiB, fused path with 4-tile buckets) and the first
+    size beyond it (falls back to the direct kernel with 64-bit positions): bit-exact, checked through the sparse set of
+    positions (the oracle's full 512 MiB filter would be compared word for word as well, but positions localise a failure)."""
+    from metasbt_b200 import ops
+    k = 31
+    fa = util.codes_to_fasta(util.synthetic_codes(31337, 200_000), "g", 80) + b">n\nACGTNNNNACGTACGTACGTACGTACGTACGTACGTACGTACGTA\n"
+    batch = ops.GenomeBatch([ops.pack_fasta(fa, k)], ctx.device)
+    out = ctx.build_filters(batch, k, num_bits)
+    torch.cuda.synchronize()
+    w = ops.filter_words(num_bits)
+    want = oracle.makebf(fa, k, num_bits)
+    got = out[0, :w].cpu().numpy().view(np.uint64)
+    nz_g, nz_w = np.flatnonzero(got), np.flatnonzero(want)
+    assert np.array_equal(nz_g, nz_w) and np.array_equal(got[nz_g], want[nz_w])
+    assert int(ctx.bf_popcount([out[0]], num_bits)[0]) == oracle.bf_popcount(want) > 199_000
+    del out
+    torch.cuda.empty_cache()
