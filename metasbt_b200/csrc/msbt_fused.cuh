@@ -236,17 +236,6 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
             }
             fu_bar(1, FU_P_THREADS);  // barrier B: the chunk is staged
             FU_T(tp2)
-            if (tid == 0) {
-                nxt = pend;
-                pend = atomicAdd(P.sync + 0, 1u);
-                nxt_gi = gi;  // claims are monotonic: scan forward from the current genome
-                if (nxt < P.n_chunks_total) {
-                    while (nxt_gi + 1 < P.n_genomes && P.genomes[nxt_gi + 1].fchunk_begin <= nxt) nxt_gi++;
-                    // relaxed is enough: P only WRITES the slot after seeing the count, and B bumped it after its reads
-                    if (nxt_gi >= P.ring) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(nxt_free) : "l"(P.consumed + (nxt_gi - P.ring)) : "memory");
-                    else nxt_free = NB;
-                }
-            }
             // Flush, warp by warp (each warp owns a contiguous range of staging rows, so no CTA barrier is needed):
             //  A  one lane per row: one ring reservation per (chunk, bucket), rounded up to whole quads; the result is
             //     packed back into the row's counter as (offset << 8) | n;
@@ -267,6 +256,18 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
                         const uint32_t b = rb + lane + 32 * j;
                         nn[j] = (b < r1) ? min(cnt[b], P.cap) : 0u;
                         oo[j] = nn[j] ? atomicAdd(gc + b, (nn[j] + 3u) & ~3u) : 0u;
+                    }
+                    if (rb == r0 && tid == 0) {
+                        // tid 0 resolves the next chunk's claim while the reservations are in flight
+                        nxt = pend;
+                        pend = atomicAdd(P.sync + 0, 1u);
+                        nxt_gi = gi;  // claims are monotonic: scan forward from the current genome
+                        if (nxt < P.n_chunks_total) {
+                            while (nxt_gi + 1 < P.n_genomes && P.genomes[nxt_gi + 1].fchunk_begin <= nxt) nxt_gi++;
+                            // relaxed is enough: P only WRITES the slot after seeing the count, and B bumped it after its reads
+                            if (nxt_gi >= P.ring) asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(nxt_free) : "l"(P.consumed + (nxt_gi - P.ring)) : "memory");
+                            else nxt_free = NB;
+                        }
                     }
 #pragma unroll
                     for (int j = 0; j < 4; j++) {

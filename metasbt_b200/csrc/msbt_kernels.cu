@@ -1303,6 +1303,10 @@ extern "C" int msbt_fasta_pack_device(msbt_ctx *ctx, const char *d_text, const u
     const uint8_t *text = (const uint8_t *)d_text;
     std::vector<unsigned long long> tot(2 * (size_t)n_files, 0), out(2 * (size_t)n_files, 0);
     uint32_t *d_bt = nullptr;
+    struct BtGuard {  // the run tables are freed on every exit path
+        uint32_t *&p;
+        ~BtGuard() { if (p) cudaFree(p); }
+    } bt_guard{d_bt};
     if (n_chunks) {
         fp_line_summary_kernel<<<n_chunks, FP_THREADS, 0, stream>>>(text, d_files, n_files, n_chunks, d_sum);
         LAUNCH_CHECK(ctx);
@@ -1331,9 +1335,7 @@ extern "C" int msbt_fasta_pack_device(msbt_ctx *ctx, const char *d_text, const u
                                                           min_run, (unsigned long long *)d_packed);
         LAUNCH_CHECK(ctx);
         CU_TRY(ctx, cudaMemcpyAsync(out.data(), d_out, sizeof(unsigned long long) * 2 * n_files, cudaMemcpyDeviceToHost, stream));
-        const cudaError_t e = cudaStreamSynchronize(stream);
-        cudaFree(d_bt);
-        if (e != cudaSuccess) return fail(ctx, MSBT_ECUDA, "fasta_pack_device: %s", cudaGetErrorString(e));
+        CU_TRY(ctx, cudaStreamSynchronize(stream));
     }
     for (uint32_t i = 0; i < n_files; i++) {
         h_descs[i].packed_word_off = files[i].packed_word_off;
