@@ -34,11 +34,14 @@ constexpr int FU_P_THREADS = MSBT_FU_P_THREADS;      // partition warps (role P)
 constexpr int FU_THREADS = 1024;
 constexpr int FU_B_THREADS = FU_THREADS - FU_P_THREADS;  // tile-build warps (role B)
 constexpr uint32_t FU_CHUNK_BASES = FU_P_THREADS * 32;  // k-mer starts per chunk
-constexpr uint32_t FU_MAX_BUCKETS = 2048;               // at 2^30 bits: bucket == one 64 KiB tile, B needs a single pass
-constexpr uint32_t FU_STAGE_WORDS = 16 * (FU_MAX_BUCKETS + 1);  // staging rows: (NB + 1) x cap
+#ifndef MSBT_FU_NB
+#define MSBT_FU_NB 2048
+#endif
+constexpr uint32_t FU_MAX_BUCKETS = MSBT_FU_NB;         // 2048: at 2^30 bits a bucket is one 64 KiB tile (single-pass build)
+constexpr uint32_t FU_STAGE_WORDS = (32768 / FU_MAX_BUCKETS) * (FU_MAX_BUCKETS + 1);  // staging rows: (NB + 1) x cap
 constexpr uint32_t FU_TILE_LOG2 = 19;                   // <= 2^19 bits = 64 KiB per tile
 constexpr uint32_t FU_TILE_BYTES = 1u << (FU_TILE_LOG2 - 3);
-constexpr int FU_REG_QUADS = (768 + FU_B_THREADS - 1) / FU_B_THREADS;  // 16-byte groups of bucket positions per B thread in registers
+constexpr int FU_REG_QUADS = (768 * (2048 / (int)FU_MAX_BUCKETS) + FU_B_THREADS - 1) / FU_B_THREADS;  // 16-byte groups of bucket positions per B thread in registers
 constexpr int FU_REG_ENTRIES = 4 * FU_REG_QUADS;
 // dynamic shared memory: [tile 64 KiB][cnt NB][stage][claims]
 constexpr size_t FU_SMEM_BYTES = FU_TILE_BYTES + FU_MAX_BUCKETS * 4 + (size_t)FU_STAGE_WORDS * 4 + 64;
@@ -398,6 +401,7 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
     }
 #define FU_B_OR1(x) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(saddr + (((x) >> 3) & word_mask)), "r"(1u << ((x) & 31)) : "memory");
             if (item < n_items) FU_B_FAST_LOADS()
+            const uint32_t tpb_log2 = P.tiles_per_bucket_log2, tpb = 1u << tpb_log2;
             while (item < n_items) {
                 uint32_t nxt = 0, nxt_gi = 0, nxt_done = 0;
                 if (tid == 32) {
@@ -408,44 +412,64 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
                 }
                 const uint32_t cur_gi = gi;
                 const uint32_t b = item - gi * NB;
-                uint64_t *dst = P.filters + P.genomes[gi].filter_word_off + (uint64_t)b * (FU_TILE_BYTES / 8);
-                // A
-                uint4 *tv = (uint4 *)tile;
+                uint64_t *dst = P.filters + P.genomes[gi].filter_word_off + ((uint64_t)b << tpb_log2) * (FU_TILE_BYTES / 8);
+                uint32_t n = 0;
+                for (uint32_t sub = 0; sub < tpb; sub++) {
+                    const bool last = sub + 1 == tpb;
+                    // A
+                    uint4 *tv = (uint4 *)tile;
 #pragma unroll
-                for (uint32_t i = 0; i < (TILE_VEC + FU_B_THREADS - 1) / FU_B_THREADS; i++)
-                    if (i * FU_B_THREADS + tid < TILE_VEC) tv[i * FU_B_THREADS + tid] = make_uint4(0, 0, 0, 0);
-                const uint32_t n = min(n_raw, P.gcap);
-                if (tid == 32) {
-                    if (nxt < n_items && nxt_done < FU_B_WANT_G(nxt_gi)) fu_wait_ge(P.done + nxt_gi, FU_B_WANT_G(nxt_gi));
-                    claim[4] = nxt;
-                    claim[5] = nxt_gi;
-                }
-                fu_bar(2, FU_B_THREADS);
-                // B
-#pragma unroll
-                for (int u = 0; u < FU_REG_QUADS; u++)
-                    if ((u * FU_B_THREADS + tid) * 4u < n) { FU_B_OR1(e[u].x) FU_B_OR1(e[u].y) FU_B_OR1(e[u].z) FU_B_OR1(e[u].w) }
-                if (n > FU_REG_ENTRIES * FU_B_THREADS) {  // oversized bucket (skewed input)
-                    const uint32_t *src = P.gbuf + ((uint64_t)(gi % P.ring) * NB + b) * P.gcap;
-                    for (uint32_t i = FU_REG_ENTRIES * FU_B_THREADS + tid; i < n; i += FU_B_THREADS) {
-                        const uint32_t p = __ldcg(src + i);
-                        FU_B_OR1(p)
+                    for (uint32_t i = 0; i < (TILE_VEC + FU_B_THREADS - 1) / FU_B_THREADS; i++)
+                        if (i * FU_B_THREADS + tid < TILE_VEC) tv[i * FU_B_THREADS + tid] = make_uint4(0, 0, 0, 0);
+                    if (sub == 0) n = min(n_raw, P.gcap);  // the prefetched loads land here
+                    if (sub == 0 && tid == 32) {
+                        if (nxt < n_items && nxt_done < FU_B_WANT_G(nxt_gi)) fu_wait_ge(P.done + nxt_gi, FU_B_WANT_G(nxt_gi));
+                        claim[4] = nxt;
+                        claim[5] = nxt_gi;
                     }
+                    fu_bar(2, FU_B_THREADS);
+                    // B
+                    if (tpb == 1) {
+#pragma unroll
+                        for (int u = 0; u < FU_REG_QUADS; u++)
+                            if ((u * FU_B_THREADS + tid) * 4u < n) { FU_B_OR1(e[u].x) FU_B_OR1(e[u].y) FU_B_OR1(e[u].z) FU_B_OR1(e[u].w) }
+                    } else {
+                        const uint32_t tf = (b << tpb_log2) + sub;  // a position of another tile ORs 0 into this one
+#define FU_B_OR2(x)                                                                                           \
+    {                                                                                                         \
+        const uint32_t v_ = (((x) >> FU_TILE_LOG2) == tf) ? (1u << ((x) & 31)) : 0u;                          \
+        asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(saddr + (((x) >> 3) & word_mask)), "r"(v_) : "memory"); \
+    }
+#pragma unroll
+                        for (int u = 0; u < FU_REG_QUADS; u++)
+                            if ((u * FU_B_THREADS + tid) * 4u < n) { FU_B_OR2(e[u].x) FU_B_OR2(e[u].y) FU_B_OR2(e[u].z) FU_B_OR2(e[u].w) }
+                    }
+                    if (n > FU_REG_ENTRIES * FU_B_THREADS) {  // oversized bucket (skewed input)
+                        const uint32_t *src = P.gbuf + ((uint64_t)(cur_gi % P.ring) * NB + b) * P.gcap;
+                        const uint32_t tf = (b << tpb_log2) + sub;
+                        for (uint32_t i = FU_REG_ENTRIES * FU_B_THREADS + tid; i < n; i += FU_B_THREADS) {
+                            const uint32_t p = __ldcg(src + i);
+                            if ((p >> FU_TILE_LOG2) == tf) FU_B_OR1(p)
+                        }
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    fu_bar(2, FU_B_THREADS);
+                    // C
+                    if (last) {
+                        item = claim[4];
+                        gi = claim[5];
+                        if (item < n_items) FU_B_FAST_LOADS()
+                    }
+                    if (tid == 0) {
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst + (uint64_t)sub * (FU_TILE_BYTES / 8)), "r"(saddr), "r"(FU_TILE_BYTES), "l"(evict_first) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    }
+                    if (last && tid == 64) atomicAdd(P.consumed + cur_gi, 1u);
+                    fu_bar(2, FU_B_THREADS);
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                fu_bar(2, FU_B_THREADS);
-                // C
-                item = claim[4];
-                gi = claim[5];
-                if (item < n_items) FU_B_FAST_LOADS()
-                if (tid == 0) {
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst), "r"(saddr), "r"(FU_TILE_BYTES), "l"(evict_first) : "memory");
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-                }
-                if (tid == 64) atomicAdd(P.consumed + cur_gi, 1u);
-                fu_bar(2, FU_B_THREADS);
             }
+#undef FU_B_OR2
 #undef FU_B_OR1
 #undef FU_B_FAST_LOADS
             return;

@@ -919,7 +919,7 @@ static int build_fused(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *
     P.n_chunks_total = (uint32_t)fchunks;
     P.nb_magic = (uint32_t)(((1ull << 32) + NB - 1) / NB);
     // lean B loop: bucket == one full 64 KiB tile, every tile complete, every destination 16-byte aligned
-    P.fast_b = (shift == FU_TILE_LOG2) && (num_bits % (1ull << FU_TILE_LOG2) == 0) && ((((uintptr_t)d_filters) & 15) == 0);
+    P.fast_b = (shift >= FU_TILE_LOG2) && (num_bits % (1ull << shift) == 0) && ((((uintptr_t)d_filters) & 15) == 0);  // whole buckets of full tiles
     for (const DevGenome &g : dg) P.fast_b = P.fast_b && ((g.filter_word_off & 1) == 0);
     // exactness of item / NB by multiply-high: item * (magic * NB - 2^32) < 2^32
     if (P.fast_b && (uint64_t)n_genomes * NB * ((uint64_t)P.nb_magic * NB - (1ull << 32)) >= (1ull << 32)) P.fast_b = 0;
