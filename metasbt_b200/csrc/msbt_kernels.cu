@@ -1978,14 +1978,26 @@ bitslice_kernel(const uint64_t *const *__restrict__ leaves, uint32_t n_leaves, u
     const uint32_t cols = min(32u, lw - lg0);                   // column words of this tile
     const uint64_t n_rowwords = (row_end - row_begin + 31) >> 5;
     const uint64_t first_word = row_begin >> 5;                 // row_begin is a multiple of 32
+    const bool vec_ok = (first_word & 3) == 0;                  // leaf pointers are 16-byte aligned (checked by the host)
     for (uint64_t wb = (uint64_t)blockIdx.x * BS_WORDS; wb < n_rowwords; wb += (uint64_t)gridDim.x * BS_WORDS) {
         __syncthreads();
-        // load: 8 lanes per leaf read its 8 consecutive words, 32 leaves per pass
-        for (uint32_t l = threadIdx.x >> 3; l < cols * 32; l += 32) {
-            const uint32_t leaf = leaf0 + l, ww = threadIdx.x & 7;
-            uint32_t v = 0;
-            if (leaf < n_leaves && wb + ww < n_rowwords) v = __ldg((const uint32_t *)leaves[leaf] + first_word + wb + ww);
-            in[l * BS_IN_STRIDE + ww] = v;
+        if (vec_ok && wb + BS_WORDS <= n_rowwords) {
+            // load: 2 lanes per leaf, one 16-byte load each (32 bytes = one sector per leaf), 128 leaves per pass
+            for (uint32_t l = threadIdx.x >> 1; l < cols * 32; l += 128) {
+                const uint32_t leaf = leaf0 + l, h = threadIdx.x & 1;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (leaf < n_leaves) v = ld_stream((const uint4 *)((const uint32_t *)leaves[leaf] + first_word + wb) + h);
+                uint32_t *d = in + l * BS_IN_STRIDE + 4 * h;
+                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            }
+        } else {
+            // general: 8 lanes per leaf read its 8 consecutive words, 32 leaves per pass
+            for (uint32_t l = threadIdx.x >> 3; l < cols * 32; l += 32) {
+                const uint32_t leaf = leaf0 + l, ww = threadIdx.x & 7;
+                uint32_t v = 0;
+                if (leaf < n_leaves && wb + ww < n_rowwords) v = __ldg((const uint32_t *)leaves[leaf] + first_word + wb + ww);
+                in[l * BS_IN_STRIDE + ww] = v;
+            }
         }
         __syncthreads();
         // transpose: warp ww handles row word ww of every leaf group
@@ -1995,10 +2007,19 @@ bitslice_kernel(const uint64_t *const *__restrict__ leaves, uint32_t n_leaves, u
         }
         __syncthreads();
         // store: full row segments
-        for (uint32_t idx = threadIdx.x; idx < BS_WORDS * 32 * cols; idx += 256) {
-            const uint32_t r = idx / cols, c = idx - r * cols;
-            const uint64_t row = wb * 32 + r;  // relative row
-            if (row_begin + row < row_end) sliced[row * lw + lg0 + c] = out[r * BS_OUT_STRIDE + c];
+        if (cols == 32) {
+#pragma unroll 4
+            for (uint32_t idx = threadIdx.x; idx < BS_WORDS * 32 * 32; idx += 256) {
+                const uint32_t r = idx >> 5, c = idx & 31;
+                const uint64_t row = wb * 32 + r;  // relative row
+                if (row_begin + row < row_end) sliced[row * lw + lg0 + c] = out[r * BS_OUT_STRIDE + c];
+            }
+        } else {
+            for (uint32_t idx = threadIdx.x; idx < BS_WORDS * 32 * cols; idx += 256) {
+                const uint32_t r = idx / cols, c = idx - r * cols;
+                const uint64_t row = wb * 32 + r;  // relative row
+                if (row_begin + row < row_end) sliced[row * lw + lg0 + c] = out[r * BS_OUT_STRIDE + c];
+            }
         }
     }
 }
