@@ -1,5 +1,5 @@
-"""`metasbt index | profile | sketch`: the three sub-commands of the reference CLI that reach the hot
-path (/root/reference/metasbt/metasbt.py: index :319-553, profile :1020-1143, sketch :1145-1244),
+"""`metasbt index | profile | sketch | update`: the sub-commands of the reference CLI that reach the hot
+path (/root/reference/metasbt/metasbt.py: index :319-553, profile :1020-1143, sketch :1145-1244, update :1730-1920),
 flag for flag and default for default, over the in-process GPU operators.
 
 What is deliberately different from the reference CLI:
@@ -22,7 +22,7 @@ from typing import List, Optional, Sequence
 
 from .core import Database, Entry, __version__
 
-COMMANDS = ("index", "profile", "sketch")
+COMMANDS = ("index", "profile", "sketch", "update")
 
 
 def _index_parser() -> argparse.ArgumentParser:
@@ -149,6 +149,46 @@ class MetaSBT(object):
             out.append(Database._profile(self.database, genome_filepath, sketch_filepath, args.uncertainty,
                                          args.pruning_threshold))
         return out
+
+
+    # ------------------------------------------------------------------ update (metasbt.py:1730-1920)
+    def update(self, argv: List[str]):
+        """Add new genomes (MAGs) to an existing database: profile them, assign the ones that fall inside a known species
+        (is_known), cluster the rest into new taxa (characterize), then re-index every touched cluster (update)."""
+        parser = _genomes_parser("update", argv, profile=True)
+        parser.description = "Update a MetaSBT database with new genomes."
+        for action in parser._actions:
+            if action.dest == "database":
+                action.required, action.default = True, None
+        parser.add_argument("--dereplicate", required=False, default=0.0, type=float, dest="dereplicate",
+                            help="Dereplicate genomes based of their ANI distance according the specified threshold.")
+        parser.add_argument("--completeness", type=float, required=False, default=0.0,
+                            help="Percentage threshold on genomes completeness.")
+        parser.add_argument("--contamination", type=float, required=False, default=100.0,
+                            help="Percentage threshold on genomes contamination.")
+        parser.add_argument("--pack", action="store_true", default=False, help="Pack the database into a compressed tarball.")
+        args = parser.parse_args(argv)
+        if args.completeness > 0.0 or args.contamination < 100.0:
+            raise NotImplementedError("quality control (checkm/checkv/busco) is outside the B200 hot path")
+        if args.dereplicate > 0.0:
+            raise NotImplementedError("--dereplicate is outside the B200 hot path in this version")
+        if args.pack:
+            raise NotImplementedError("--pack (tar + sha256sum) is outside the B200 hot path")
+        # the reference holds the paths in a set (metasbt.py:1845): sorted here, so runs are reproducible
+        genomes = sorted(set(self._open(args)))
+        # profiles (and sketches) first: is_known / add read the memoised tables (metasbt.py:1866)
+        self.profile(argv, parse_known_args=True)
+        species_assignments = self.database.is_known_many(genomes)
+        self.database.add_many([(genome, False, species_assignments[genome]) for genome in genomes])
+        characterized, unassigned = dict(), set()
+        try:
+            characterized, unassigned = self.database.characterize()
+        except Exception as exc:
+            # the reference swallows every exception here (metasbt.py:1904-1910); only "nothing to characterize" is expected
+            if "no unknown genomes" not in str(exc):
+                raise
+        self.database.update()
+        return species_assignments, characterized, unassigned
 
 
 def run(argv: Optional[Sequence[str]] = None) -> None:

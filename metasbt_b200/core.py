@@ -7,7 +7,8 @@ get_full_taxonomy, is_known, add_children} -- with the same signatures, exceptio
 and result files (`clusters.tsv`, `genomes.tsv`, `metadata.json`, `<name>.txt`,
 `tree/index.detbrief.sbt`, `tmp/profiles/<genome>.txt`) as /root/reference/metasbt/core.py.
 Out of scope and raising NotImplementedError: kitsune/ntcard estimation (pass --kmer-size and
---filter-size), flat=False trees (howdesbt cluster/build), qc/dereplicate/characterize/merge/remove.
+--filter-size), flat=False trees (howdesbt cluster/build), qc/dereplicate/merge/remove.
+The `update` consumers of the same kernels (is_known, characterize, _estimate_boundaries) are included.
 
 Differences that are deliberate (documented in DESIGN.md):
 * process fan-outs (mp.Pool over dist/_profile, core.py:4036, metasbt.py:1124) are batch calls;
@@ -280,13 +281,16 @@ class Database(object):
             filename = os.path.splitext(os.path.basename(filepath))[0]
             if filename in self.genomes or filename in seen:
                 raise Exception("A genome with the same name already exists in the database!")
-            if not taxonomy:
-                raise NotImplementedError("adding unassigned genomes (the `update` command) is outside the B200 hot path")
             seen.add(filename)
             prepared.append((filepath, filename, Entry(self, filename, filename, "genome", taxonomy=taxonomy, known=reference), taxonomy))
         Entry.sketch_many([p[2] for p in prepared], [p[0] for p in prepared])
 
         for filepath, filename, genome_obj, taxonomy in prepared:
+            if not taxonomy:
+                # a MAG with no species close enough (core.py:972-980): keep its profile for characterize()
+                genome_obj.profile = self.profile(filepath, genome_obj.sketch_filepath)
+                self._unknowns.append(genome_obj)
+                continue
             if not self._is_defined(taxonomy):
                 raise ValueError("The assigned taxonomy is malformed or not defined!")
             taxonomy = self._format_taxonomy(taxonomy)
@@ -540,7 +544,211 @@ class Database(object):
     def _unsupported(self, *a, **k):
         raise NotImplementedError("outside the B200 hot path (SURVEY.md 8: index / profile only)")
 
-    qc = dereplicate = characterize = is_known = merge = remove = cluster = _unsupported
+    qc = dereplicate = merge = remove = cluster = _unsupported
+
+    # ------------------------------------------------------------------ N2: the `update` consumers of K1/K3/K4
+    @staticmethod
+    def _is_known(instance: "Database", filepath: str) -> Tuple[str, Optional[str]]:
+        return (filepath, instance.is_known(filepath))
+
+    def _closest_centroid_check(self, genome_obj: "Entry", level: str) -> Optional[str]:
+        """Shared by is_known (core.py:782-841): best match of `level` in the genome's profile, distance to that species'
+        centroid (one K3 call), accepted iff within the species' boundary."""
+        matches = genome_obj.profile[level]
+        best = sorted(matches.keys(), key=lambda match: matches[match])[0]
+        if level == "genome":
+            best = "|".join(best.split("|")[:-1])  # drop the trailing t__<genome>
+        species_name = best.split("|")[-1]
+        species_id = self.clusters["species"][species_name].identifier
+        centroid = self.report[species_id]["centroid"]
+        centroid_sketch = os.path.join(self.root, "sketches", f"{centroid}.bf")
+        _, dists = self.dist(genome_obj.sketch_filepath, [centroid_sketch], self.metadata["kmer_size"], tmp=self.tmp, resume=False)
+        _, max_boundary = self._estimate_boundaries(self.report[species_id]["taxonomy"])
+        return best if dists[centroid_sketch] <= max_boundary else None
+
+    def is_known(self, filepath: str) -> Optional[str]:
+        """Can this MAG be assigned to a species of the database?  (core.py:729-843)
+        Returns the species-level taxonomy or None.  Run before add()."""
+        if not self._validate_metadata(self.metadata):
+            raise Exception("No database metadata found!")
+        if not self._is_supported(filepath):
+            raise ValueError("Input file format is not supported!")
+        filename = os.path.splitext(os.path.basename(filepath))[0]
+        if filename in self.genomes:
+            return self.genomes[filename].get_full_taxonomy()
+        if not self.report:
+            raise Exception("No database report defined!")
+        genome_obj = Entry(self, filename, filename, "genome", taxonomy=None, known=False)
+        genome_sketch_filepath = genome_obj.sketch(filepath)
+        genome_obj.profile = self.profile(filepath, genome_sketch_filepath)
+        # the species of the closest genome first, then the closest species (they can differ)
+        for level in ["genome", "species"]:
+            taxonomy = self._closest_centroid_check(genome_obj, level)
+            if taxonomy is not None:
+                return taxonomy
+        return None
+
+    def is_known_many(self, filepaths: Sequence[str]) -> Dict[str, Optional[str]]:
+        """The pool fan-out of metasbt.py:1878-1897 as one call: every missing sketch is built by ONE makebf batch,
+        then each genome is checked as is_known() does."""
+        todo = []
+        for filepath in filepaths:
+            if not self._is_supported(filepath):
+                raise ValueError("Input file format is not supported!")
+            filename = os.path.splitext(os.path.basename(filepath))[0]
+            if filename not in self.genomes:
+                todo.append((Entry(self, filename, filename, "genome", taxonomy=None, known=False), filepath))
+        if todo and self._validate_metadata(self.metadata):
+            Entry.sketch_many([t[0] for t in todo], [t[1] for t in todo])
+        return OrderedDict((filepath, self.is_known(filepath)) for filepath in filepaths)
+
+    def _estimate_boundaries(self, taxonomy: str) -> Tuple[float, float]:
+        """Boundaries of a (possibly not yet existing) cluster (core.py:1295-1386): species are fixed at 5 %; otherwise the
+        mean of the boundaries of the clusters of that level under the closest ancestor that has any.  As in the reference,
+        the shortcut through the report only fires for labels taxonomy_exists() accepts, i.e. never for a partial label
+        (core.py:348 wants seven levels), and a kingdom cannot be estimated."""
+        if not taxonomy:
+            raise ValueError("Taxonomy is not provided!")
+        names = taxonomy.split("|")
+        cluster_level = LEVELS[len(names) - 1]
+        if cluster_level == "species":
+            return (0.0, 0.05)
+        if self.taxonomy_exists(taxonomy):
+            cluster_id = self.clusters[cluster_level][names[-1]].identifier
+            min_ani, max_ani = self.report[cluster_id]["boundaries"]
+            if min_ani is not None and max_ani is not None:
+                return (min_ani, max_ani)
+        if cluster_level == "kingdom":
+            raise Exception(f"Unable to retrieve boundaries for {taxonomy}")
+        min_bounds: List[float] = list()
+        max_bounds: List[float] = list()
+        # ancestors from the direct parent up to the kingdom; stop at the first one with usable siblings
+        for depth in range(len(names) - 2, -1, -1):
+            parent_level, parent_name = LEVELS[depth], names[depth]
+            if parent_name in self.clusters[parent_level]:
+                for child in self.clusters[parent_level][parent_name].get_children(up_to=cluster_level):
+                    child_obj = self.clusters[cluster_level][child]
+                    if child_obj.identifier in self.report:
+                        min_ani, max_ani = self.report[child_obj.identifier]["boundaries"]
+                        if min_ani is not None and max_ani is not None:
+                            min_bounds.append(min_ani)
+                            max_bounds.append(max_ani)
+            if min_bounds or max_bounds:
+                break
+        if not min_bounds and not max_bounds:
+            raise Exception(f"Unable to retrieve boundaries for {taxonomy}")
+        return (round(statistics.mean(min_bounds), 5), round(statistics.mean(max_bounds), 5))
+
+    def characterize(self) -> Tuple[Dict[str, Set[str]], Set[str]]:
+        """Cluster the unassigned genomes together and define new clusters (core.py:982-1283).
+
+        The all-pairs ANI distances come from ONE K3 all-pairs call (the reference runs a pool of `dist` jobs); the
+        dendrogram is scipy's average linkage (the reference calls fastcluster.linkage(method="average"), which
+        implements the same algorithm).  One reference behaviour is kept on purpose, so that assignments are identical:
+        the dendrogram cut always follows the flat cluster of the FIRST unknown genome -- the reference indexes the
+        fcluster result with the inner loop's variable, which is always 0 (core.py:1107 shadows :1080, used at :1131).
+        """
+        if not self._validate_metadata(self.metadata):
+            raise Exception("No database metadata found!")
+        if not self._unknowns:
+            raise Exception("There are no unknown genomes to be characterized!")
+        import scipy.cluster.hierarchy as hier
+
+        sketches = [genome.sketch_filepath for genome in self._unknowns]
+        names_of = [os.path.splitext(os.path.basename(path))[0] for path in sketches]
+        dendro = None
+        if len(sketches) > 1:
+            print(f"Computing pair-wise distances between {len(sketches)} uncharacterized genomes")
+            inter = self.backend.dist_all_pairs(sketches)
+            k = self.metadata["kmer_size"]
+            condensed = list()
+            for i in range(len(sketches)):
+                for j in range(i + 1, len(sketches)):
+                    union = int(inter[i][i]) + int(inter[j][j]) - int(inter[i][j])
+                    condensed.append(ani_distance(int(inter[i][j]), union, k))
+            dendro = hier.linkage(condensed, method="average")
+
+        def cut(height: float):
+            return hier.fcluster(dendro, height, criterion="distance") if dendro is not None else [1]
+
+        assignments: Dict[str, str] = dict()
+        unassigned: Set[str] = set()
+        processed: Set[str] = set()
+        print(f"Clustering {len(sketches)} genomes. This may take a while..")
+        # genus up to kingdom (the species level was tried by is_known/add)
+        for level in reversed(LEVELS[:-1]):
+            if len(processed) == len(self._unknowns):
+                break
+            print(f"Clustering at the {level} level")
+            for genome_obj in self._unknowns:
+                if genome_obj.sketch_filepath not in processed:
+                    matches = genome_obj.profile[level]
+                    closest_taxonomy = sorted(matches.keys(), key=lambda match: matches[match])[0]
+                    closest_id = self.clusters[level][closest_taxonomy.split("|")[-1]].identifier
+                    centroid_sketch = self.genomes[self.report[closest_id]["centroid"]].sketch_filepath
+                    _, dists = self.dist(genome_obj.sketch_filepath, [centroid_sketch], self.metadata["kmer_size"],
+                                         tmp=self.tmp, resume=False)
+                    try:
+                        _, max_boundary = self._estimate_boundaries(self.report[closest_id]["taxonomy"])
+                    except Exception:
+                        max_boundary = None  # outside the kingdom boundaries: stays unassigned
+                    if max_boundary is not None and dists[centroid_sketch] <= max_boundary:
+                        clusters = cut(max_boundary)
+                        cluster_id = clusters[0]  # sic: see the docstring
+                        for sketch_filepath, sketch_name, assigned in zip(sketches, names_of, clusters):
+                            if assigned == cluster_id and sketch_filepath not in processed:
+                                assignments[sketch_name] = closest_taxonomy
+                                processed.add(sketch_filepath)
+                                print(f"\t[{len(processed)}/{len(self._unknowns)}] {level}={closest_taxonomy}\t{sketch_name}")
+                if level == "kingdom" and genome_obj.sketch_filepath not in processed:
+                    unassigned.add(genome_obj.name)
+        print(f"{len(unassigned)} genomes have not been characterized")
+
+        characterized: Dict[str, Set[str]] = dict()
+        partially: "OrderedDict[str, Set[str]]" = OrderedDict()
+        partial_genomes: Set[str] = set()
+        for sketch_name, taxonomy in assignments.items():
+            if taxonomy.count("|") + 1 == len(LEVELS):
+                characterized.setdefault(taxonomy, set()).add(sketch_name)
+            else:
+                partially.setdefault(taxonomy, set()).add(sketch_name)
+                partial_genomes.add(sketch_name)
+        print(f"{len(partial_genomes)} genomes have been partially characterized")
+        if partially:
+            print("Processing partially characterized genomes. This will create new clusters..")
+
+        done = 0
+        new_clusters = False
+        # top-down: every pass extends each partial label by one level with brand-new MSBT clusters, cutting the
+        # dendrogram at the boundary estimated for a sibling-less cluster of that level
+        while len(partially) > 0:
+            for taxonomy in list(partially.keys()):
+                print(f"Expanding {taxonomy}")
+                next_prefix = LEVELS[taxonomy.count("|") + 1][0]
+                _, max_boundary = self._estimate_boundaries(f"{taxonomy}|{next_prefix}__tmp")
+                clusters = cut(max_boundary)
+                clusters_map: Dict[int, int] = dict()
+                for sketch_filepath, sketch_name, assigned in zip(sketches, names_of, clusters):
+                    if sketch_name in partially[taxonomy]:
+                        if assigned not in clusters_map:
+                            self.metadata["clusters_count"] += 1
+                            clusters_map[assigned] = self.metadata["clusters_count"]
+                            new_clusters = True
+                        assigned_taxonomy = f"{taxonomy}|{next_prefix}__MSBT{clusters_map[assigned]}"
+                        if self._is_defined(assigned_taxonomy):
+                            characterized.setdefault(assigned_taxonomy, set()).add(sketch_name)
+                            # the sketch path stands in for the genome path: the sketch exists, so add() reuses it
+                            self.add(sketch_filepath, reference=False, taxonomy=assigned_taxonomy)
+                            done += 1
+                            print(f"\t[{done}/{len(partial_genomes)}] species={assigned_taxonomy}\t{sketch_name}")
+                        else:
+                            partially.setdefault(assigned_taxonomy, set()).add(sketch_name)
+                del partially[taxonomy]
+
+        self._unknowns = list()
+        if new_clusters:
+            self._dump_metadata()
+        return characterized, unassigned
 
 
 class Entry(object):

@@ -7,7 +7,7 @@ import os
 from typing import Any, Dict
 
 from metasbt_b200 import bffile, cli
-from tests import dataset
+from tests import dataset, dataset_update
 
 
 def _rel(text: str, root: str) -> str:
@@ -24,6 +24,23 @@ def run_config1(workdir: str, backend=None) -> Dict[str, Any]:
                        backend=backend)
     assert app.database is not None and len(prof.result) == 6
     return snapshot(workdir)
+
+
+def run_update(workdir: str, backend=None) -> Dict[str, Any]:
+    """`metasbt index` on the related-taxa data set, then `metasbt update` with its six MAGs."""
+    refs_tsv, mags_txt, _ = dataset_update.write(os.path.join(workdir, "inputs"))
+    cli.MetaSBT(["index", "--workdir", workdir, "--database", "db", "--references", refs_tsv,
+                 "--kmer-size", str(dataset_update.K), "--filter-size", str(dataset_update.FILTER_BITS),
+                 "--min-kmer-occurrences", str(dataset_update.MIN_OCC), "--nproc", "1"], backend=backend)
+    app = cli.MetaSBT(["update", "--workdir", workdir, "--database", "db", "--genomes", mags_txt, "--nproc", "1"],
+                      backend=backend)
+    species_assignments, characterized, unassigned = app.result
+    snap = snapshot(workdir)
+    snap["update"] = {
+        "species_assignments": {os.path.basename(k): v for k, v in species_assignments.items()},
+        "characterized": {k: sorted(v) for k, v in characterized.items()},
+        "unassigned": sorted(unassigned)}
+    return json.loads(json.dumps(snap, sort_keys=True))
 
 
 def snapshot(workdir: str) -> Dict[str, Any]:
