@@ -713,6 +713,149 @@ kmer_count2_emit_kernel(const unsigned long long *__restrict__ tab, uint64_t n_s
     }
 }
 
+// ---- exact multiplicity, prefiltered form (k <= 31, any min_abund >= 2).  On assemblies almost every k-mer occurs
+// once, so an exact counter for all of them (one 64-bit CAS each, above) is wasted work.  Instead:
+//   1 mark    every k-mer sets one bit of a one-hash bit table (32 bits per base: ~2 % already-set hits); a k-mer that
+//             finds its bit set MAY be a repeat and goes to the candidate list.  Every k-mer that occurs >= 2 times is a
+//             candidate (its second occurrence finds the bit its first one set); false positives are k-mers of count 1;
+//   2 prepare size the exact table from the number of candidates (device side, no host round trip) and zero it;
+//   3 insert  candidates -> keys of the exact table (deduplicated by CAS);
+//   4 count   every k-mer looks itself up (a read of a table that is small and cache resident) and, if present, adds 1;
+//   5 emit    keys with count >= min_abund set their filter bit.
+struct PreState {
+    uint32_t n_cand;     // candidates appended by the mark pass
+    uint32_t slot_mask;  // exact table size - 1 (prepare)
+};
+constexpr unsigned long long PRE_OCC = 1ull << 63;  // k <= 31: keys < 2^62, so an occupied slot is never 0
+constexpr uint32_t PRE_BLOCK_LIST = 1024;           // candidates a block gathers in shared memory before one global reservation
+
+__device__ __forceinline__ void pre_mark(uint64_t key, uint32_t *__restrict__ bits, uint64_t bit_mask, uint64_t *s_list,
+                                         uint32_t *s_n, uint64_t *__restrict__ cand, PreState *st) {
+    const uint64_t h = msbt_fmix64(key ^ 0xD6E8FEB86659FD93ULL) & bit_mask;
+    const uint32_t m = 1u << (h & 31);
+    if (atomicOr(bits + (h >> 5), m) & m) {
+        const uint32_t i = atomicAdd(s_n, 1u);
+        if (i < PRE_BLOCK_LIST) s_list[i] = key;
+        else cand[atomicAdd(&st->n_cand, 1u)] = key;  // a very repetitive stretch: straight to the global list
+    }
+}
+
+#define MSBT_PRE_MARK_STEP(J)                                                        \
+    {                                                                                \
+        uint64_t lo_, hi_;                                                           \
+        kb.template get<J>(lo_, hi_);                                                \
+        if ((vg >> J) & 1u) pre_mark(lo_, bits, bit_mask, s_list, &s_n, cand, st);   \
+    }
+
+__global__ void __launch_bounds__(TILE_THREADS, 4)
+kmer_pre_mark_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ run_ends, DevGenome g, uint32_t k,
+                     uint32_t *__restrict__ bits, uint64_t bit_mask, uint64_t *__restrict__ cand, PreState *st) {
+    __shared__ uint64_t s_list[PRE_BLOCK_LIST];
+    __shared__ uint32_t s_n, s_base;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+    const uint32_t n_words = (g.n_bases + 31) / 32;
+    for (uint32_t w = blockIdx.x * TILE_THREADS + threadIdx.x; w < n_words; w += gridDim.x * TILE_THREADS) {
+        const uint32_t vm = valid_mask(run_ends + g.run_off, g.n_runs, w * 32, k);
+        if (vm == 0) continue;
+        KmerBlock<1> kb;
+        kb.init(packed + g.packed_word_off + w, k);
+#pragma unroll 1
+        for (uint32_t grp = 0; grp < 4; grp++) {
+            const uint32_t vg = (vm >> (8 * grp)) & 0xFFu;
+            MSBT_PRE_MARK_STEP(0) MSBT_PRE_MARK_STEP(1) MSBT_PRE_MARK_STEP(2) MSBT_PRE_MARK_STEP(3)
+            MSBT_PRE_MARK_STEP(4) MSBT_PRE_MARK_STEP(5) MSBT_PRE_MARK_STEP(6) MSBT_PRE_MARK_STEP(7)
+            kb.advance8();
+        }
+    }
+    __syncthreads();
+    const uint32_t n = min(s_n, PRE_BLOCK_LIST);
+    if (threadIdx.x == 0 && n) s_base = atomicAdd(&st->n_cand, n);
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += TILE_THREADS) cand[s_base + i] = s_list[i];
+}
+
+__device__ __forceinline__ uint32_t pre_slots(uint32_t n_cand, uint32_t max_slots) {
+    uint32_t slots = 1024;
+    while (slots < 2u * n_cand && slots < max_slots) slots <<= 1;
+    return slots;
+}
+
+__global__ void __launch_bounds__(256)
+kmer_pre_prepare_kernel(PreState *st, unsigned long long *__restrict__ tab, uint32_t *__restrict__ cnt, uint32_t max_slots) {
+    const uint32_t slots = pre_slots(st->n_cand, max_slots);
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += gridDim.x * blockDim.x) {
+        tab[s] = 0ull;
+        cnt[s] = 0u;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) st->slot_mask = slots - 1;  // read by the next kernels only
+}
+
+__global__ void __launch_bounds__(256)
+kmer_pre_insert_kernel(const PreState *st, const uint64_t *__restrict__ cand, unsigned long long *__restrict__ tab) {
+    const uint32_t n = st->n_cand, mask = st->slot_mask;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long want = cand[i] | PRE_OCC;
+        uint32_t slot = (uint32_t)ht_slot(cand[i], mask);
+        while (true) {
+            const unsigned long long old = atomicCAS(tab + slot, 0ull, want);
+            if (old == 0ull || old == want) break;
+            slot = (slot + 1) & mask;
+        }
+    }
+}
+
+#define MSBT_PRE_COUNT_STEP(J)                                                       \
+    {                                                                                \
+        uint64_t lo_, hi_;                                                           \
+        kb.template get<J>(lo_, hi_);                                                \
+        if ((vg >> J) & 1u) {                                                        \
+            const unsigned long long want_ = lo_ | PRE_OCC;                          \
+            uint32_t slot_ = (uint32_t)ht_slot(lo_, mask);                           \
+            while (true) {                                                           \
+                const unsigned long long v_ = __ldg(tab + slot_);                    \
+                if (v_ == 0ull) break;                                               \
+                if (v_ == want_) { atomicAdd(cnt + slot_, 1u); break; }              \
+                slot_ = (slot_ + 1) & mask;                                          \
+            }                                                                        \
+        }                                                                            \
+    }
+
+__global__ void __launch_bounds__(TILE_THREADS, 4)
+kmer_pre_count_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ run_ends, DevGenome g, uint32_t k,
+                      const PreState *st, const unsigned long long *__restrict__ tab, uint32_t *__restrict__ cnt) {
+    if (st->n_cand == 0) return;  // no k-mer can occur twice
+    const uint32_t mask = st->slot_mask;
+    const uint32_t n_words = (g.n_bases + 31) / 32;
+    for (uint32_t w = blockIdx.x * TILE_THREADS + threadIdx.x; w < n_words; w += gridDim.x * TILE_THREADS) {
+        const uint32_t vm = valid_mask(run_ends + g.run_off, g.n_runs, w * 32, k);
+        if (vm == 0) continue;
+        KmerBlock<1> kb;
+        kb.init(packed + g.packed_word_off + w, k);
+#pragma unroll 1
+        for (uint32_t grp = 0; grp < 4; grp++) {
+            const uint32_t vg = (vm >> (8 * grp)) & 0xFFu;
+            MSBT_PRE_COUNT_STEP(0) MSBT_PRE_COUNT_STEP(1) MSBT_PRE_COUNT_STEP(2) MSBT_PRE_COUNT_STEP(3)
+            MSBT_PRE_COUNT_STEP(4) MSBT_PRE_COUNT_STEP(5) MSBT_PRE_COUNT_STEP(6) MSBT_PRE_COUNT_STEP(7)
+            kb.advance8();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256)
+kmer_pre_emit_kernel(const PreState *st, const unsigned long long *__restrict__ tab, const uint32_t *__restrict__ cnt,
+                     uint32_t min_abund, KmerSpec spec, uint32_t *__restrict__ out) {
+    if (st->n_cand == 0) return;
+    const uint32_t slots = st->slot_mask + 1;
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += gridDim.x * blockDim.x) {
+        const unsigned long long v = tab[s];
+        if (v != 0ull && cnt[s] >= min_abund) {
+            const uint64_t pos = msbt_position(msbt_kmer_hash(v & ~PRE_OCC, 0, spec.k, spec.pos.seed), spec.pos);
+            if (pos < spec.pos.num_bits) atomicOr(out + (pos >> 5), 1u << (pos & 31));
+        }
+    }
+}
+
 static uint32_t ceil_log2_u64(uint64_t x) {
     uint32_t l = 0;
     while ((1ull << l) < x && l < 63) l++;
@@ -1189,6 +1332,48 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
         }
     }
 
+    if (min_abund >= 2 && k <= 31 && max_bases < (1ull << 30) && !getenv("MSBT_MIN_TABLE")) {
+        // prefiltered exact counting (see kmer_pre_mark_kernel); MSBT_MIN_TABLE=1 selects the plain count tables below
+        uint64_t bit_count = 1ull << 16;
+        while (bit_count < 32 * max_bases && bit_count < (1ull << 33)) bit_count <<= 1;
+        uint64_t max_slots = 1024;
+        while (max_slots < 2 * max_bases) max_slots <<= 1;
+        const size_t st_off = 0, bits_off = 256;
+        const size_t cand_off = align_up(bits_off + bit_count / 8, 256);
+        const size_t tab_off = align_up(cand_off + max_bases * 8, 256);
+        const size_t cnt_off = align_up(tab_off + max_slots * 8, 256);
+        int rc = ensure_scratch(ctx, cnt_off + max_slots * 4);
+        if (rc) return rc;
+        char *S = (char *)ctx->d_scratch;
+        PreState *st = (PreState *)(S + st_off);
+        uint32_t *bits = (uint32_t *)(S + bits_off);
+        uint64_t *cand = (uint64_t *)(S + cand_off);
+        unsigned long long *tab = (unsigned long long *)(S + tab_off);
+        uint32_t *cnt = (uint32_t *)(S + cnt_off);
+        for (uint32_t i = 0; i < n_genomes; i++) {
+            if (dg[i].n_bases < k) continue;
+            uint64_t gbits = 1ull << 16;
+            while (gbits < 32ull * dg[i].n_bases && gbits < bit_count) gbits <<= 1;
+            uint64_t gslots = 1024;
+            while (gslots < 2ull * dg[i].n_bases) gslots <<= 1;
+            CU_TRY(ctx, cudaMemsetAsync(S, 0, bits_off + gbits / 8, stream));  // state + bit table
+            const uint32_t n_words = (dg[i].n_bases + 31) / 32;
+            const int grid = (int)std::min<uint64_t>((n_words + TILE_THREADS - 1) / TILE_THREADS, (uint64_t)ctx->num_sms * 8);
+            const int grid2 = ctx->num_sms * 8;
+            kmer_pre_mark_kernel<<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, dg[i], k, bits, gbits - 1, cand, st);
+            LAUNCH_CHECK(ctx);
+            kmer_pre_prepare_kernel<<<grid2, 256, 0, stream>>>(st, tab, cnt, (uint32_t)gslots);
+            LAUNCH_CHECK(ctx);
+            kmer_pre_insert_kernel<<<grid2, 256, 0, stream>>>(st, cand, tab);
+            LAUNCH_CHECK(ctx);
+            kmer_pre_count_kernel<<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, dg[i], k, st, tab, cnt);
+            LAUNCH_CHECK(ctx);
+            kmer_pre_emit_kernel<<<grid2, 256, 0, stream>>>(st, tab, cnt, min_abund, spec,
+                                                            (uint32_t *)(d_filters + dg[i].filter_word_off));
+            LAUNCH_CHECK(ctx);
+        }
+        return MSBT_OK;
+    }
     if (min_abund >= 2 && min_abund <= 3 && k <= 31) {
         // compact table: 8 bytes per slot, load factor <= 2/3
         uint64_t max_slots = 1024;

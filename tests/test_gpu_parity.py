@@ -68,8 +68,19 @@ def test_makebf_skewed_inputs_overflow_path(ctx, oracle, variant):
         assert np.array_equal(g, oracle.makebf(f, k, num_bits, rolling=True))
 
 
-@pytest.mark.parametrize("k,min_abund", [(5, 2), (9, 2), (9, 3), (21, 2), (31, 2), (31, 3), (31, 4), (32, 2), (32, 3)])
-def test_makebf_min_abundance(ctx, oracle, k, min_abund):
+@pytest.fixture(params=["prefiltered", "tables"])
+def min_path(request, monkeypatch):
+    """min_abund >= 2 has two implementations: candidates prefiltered by a bit table (default for k <= 31) and plain count
+    tables (k = 32, and everything when MSBT_MIN_TABLE is set)."""
+    if request.param == "tables":
+        monkeypatch.setenv("MSBT_MIN_TABLE", "1")
+    else:
+        monkeypatch.delenv("MSBT_MIN_TABLE", raising=False)
+    return request.param
+
+
+@pytest.mark.parametrize("k,min_abund", [(5, 2), (9, 2), (9, 3), (21, 2), (31, 2), (31, 3), (31, 4), (31, 7), (32, 2), (32, 3)])
+def test_makebf_min_abundance(ctx, oracle, k, min_abund, min_path):
     rng = random.Random(k * 7 + min_abund)
     base = util.messy_fasta(rng, 2, 3000, "ACGT")
     fastas = [base + base[: len(base) // 2] + util.messy_fasta(rng, 2, 2000, "ACGTN"), b">r\n" + b"ACGT" * 200 + b"\n", b""]
@@ -284,7 +295,7 @@ def test_full_size_genomes_bit_exact_and_properties(ctx, oracle, variant):
 
 
 @pytest.mark.parametrize("min_abund", [2, 3])
-def test_makebf_min_abundance_large_genome(ctx, oracle, min_abund):
+def test_makebf_min_abundance_large_genome(ctx, oracle, min_abund, min_path):
     """MetaSBT's CLI default (--min-kmer-occurrences 2) on a 1.2 Mbp genome with repeated segments, a low-complexity
     stretch and an N run: exact canonical multiplicity (forward and reverse-complement copies count together)."""
     from metasbt_b200 import ops
@@ -297,6 +308,20 @@ def test_makebf_min_abundance_large_genome(ctx, oracle, min_abund):
     want = oracle.makebf(fa, k, m, min_abund)
     assert np.array_equal(got[0], want)
     assert oracle.bf_popcount(want) > 20_000 and oracle.bf_popcount(got[1]) == 0
+
+
+def test_makebf_min_abundance_all_repeats(ctx, oracle, min_path):
+    """A genome that is one 40 kbp segment repeated six times (plus its reverse complement): nearly every k-mer is a
+    candidate, so the per-block candidate lists overflow and the exact table is as large as it gets."""
+    k, m = 31, 1 << 22
+    seg = util.synthetic_codes(91, 40_000)
+    codes = np.concatenate([seg] * 6 + [(3 - seg)[::-1]] + [util.synthetic_codes(92, 10_000)])
+    fa = util.codes_to_fasta(codes, "rep6", 80)
+    for min_abund in (2, 7, 8):
+        _, got = build(ctx, [fa], k, m, min_abund=min_abund)
+        want = oracle.makebf(fa, k, m, min_abund)
+        assert np.array_equal(got[0], want)
+    assert oracle.bf_popcount(oracle.makebf(fa, k, m, 7)) > 30_000 and oracle.bf_popcount(want) == 0
 
 
 def _ingest_cases():
