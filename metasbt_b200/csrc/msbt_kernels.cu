@@ -1306,12 +1306,15 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
         if (rc <= 0) return rc;
         if (tiles) return fail(ctx, MSBT_EINVAL, "variant 4: geometry not applicable to this batch");
     }
-    if (fused_ok && (variant == 3 || (variant == 0 && num_bits >= (1ull << 26)))) {
+    // auto: the fused kernel from 2^25 bits up (34 us/genome at 5 Mbp for every size up to 2^28), the direct kernel below
+    // (a filter of <= 2 MiB is L2 resident: 26-29 us/genome).  The tiled variant is never chosen automatically: with few
+    // tiles it has no parallelism left (3.5 ms/genome at 2^22 bits).  tools/bench_small_filters.py
+    if (fused_ok && (variant == 3 || (variant == 0 && num_bits >= (1ull << 25)))) {
         const int rc = build_fused(ctx, d_packed, d_run_ends, dg, tiles, spec, words, d_filters, stream);
         if (rc <= 0) return rc;
         if (variant == 3 && tiles) return fail(ctx, MSBT_EINVAL, "variant 3: geometry not applicable to this batch");
     }
-    const bool tiled = tiled_ok && (variant == 2 || (variant == 0 && num_bits >= (1ull << TB_TILE_LOG2)));
+    const bool tiled = tiled_ok && variant == 2;
     if (tiled) {
         const int rc = build_tiled(ctx, d_packed, d_run_ends, dg, tiles, spec, words, d_filters, stream);
         if (rc <= 0) return rc;
