@@ -26,7 +26,7 @@ SYMBOLS = [
     "msbt_abi_version", "msbt_ctx_create", "msbt_ctx_destroy", "msbt_last_error", "msbt_sync",
     "msbt_launch_count", "msbt_fasta_pack", "msbt_fasta_pack_device", "msbt_kmer_bloom_build", "msbt_bf_or_reduce",
     "msbt_bf_popcount", "msbt_bf_and_popcount_1vN", "msbt_bf_and_popcount_allpairs",
-    "msbt_bf_extract_positions", "msbt_bf_extract_positions_batch", "msbt_query_batch", "msbt_bitslice_build", "msbt_query_batch_sliced",
+    "msbt_bf_extract_positions", "msbt_bf_extract_positions_batch", "msbt_query_batch", "msbt_bitslice_build", "msbt_query_batch_sliced", "msbt_sliced_row_words",
 ]
 
 MSBT_OK, MSBT_EINVAL, MSBT_ENOMEM, MSBT_ENOSPC, MSBT_ECUDA = 0, -22, -12, -28, -5
@@ -112,6 +112,8 @@ def lib() -> ctypes.CDLL:
     L.msbt_bitslice_build.restype = i32
     L.msbt_query_batch_sliced.argtypes = [vp, vp, u32, u64, u64, vp, P(u64), u32, vp, vp]
     L.msbt_query_batch_sliced.restype = i32
+    L.msbt_sliced_row_words.argtypes = [u32]
+    L.msbt_sliced_row_words.restype = u32
     _LIB = L
     return L
 

@@ -2156,7 +2156,7 @@ __device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
 
 __global__ void __launch_bounds__(256)
 bitslice_kernel(const uint64_t *const *__restrict__ leaves, uint32_t n_leaves, uint64_t row_begin, uint64_t row_end,
-                uint32_t lw, uint32_t *__restrict__ sliced) {
+                uint32_t lw, uint32_t ls, uint32_t *__restrict__ sliced) {
     extern __shared__ uint32_t bs_smem[];
     uint32_t *in = bs_smem;                                     // [BS_LEAVES][BS_IN_STRIDE]
     uint32_t *out = bs_smem + BS_LEAVES * BS_IN_STRIDE;         // [BS_WORDS * 32][BS_OUT_STRIDE]
@@ -2200,13 +2200,13 @@ bitslice_kernel(const uint64_t *const *__restrict__ leaves, uint32_t n_leaves, u
             for (uint32_t idx = threadIdx.x; idx < BS_WORDS * 32 * 32; idx += 256) {
                 const uint32_t r = idx >> 5, c = idx & 31;
                 const uint64_t row = wb * 32 + r;  // relative row
-                if (row_begin + row < row_end) sliced[row * lw + lg0 + c] = out[r * BS_OUT_STRIDE + c];
+                if (row_begin + row < row_end) sliced[row * ls + lg0 + c] = out[r * BS_OUT_STRIDE + c];
             }
         } else {
             for (uint32_t idx = threadIdx.x; idx < BS_WORDS * 32 * cols; idx += 256) {
                 const uint32_t r = idx / cols, c = idx - r * cols;
                 const uint64_t row = wb * 32 + r;  // relative row
-                if (row_begin + row < row_end) sliced[row * lw + lg0 + c] = out[r * BS_OUT_STRIDE + c];
+                if (row_begin + row < row_end) sliced[row * ls + lg0 + c] = out[r * BS_OUT_STRIDE + c];
             }
         }
     }
@@ -2230,16 +2230,38 @@ __device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uin
     carry = c_;
 }
 
+// W = u32 words per lane and load (1, 2 or 4): a warp reads 128 * W contiguous bytes of a row per position, and a CTA
+// covers 1024 * W leaves.  Wider loads mean fewer, longer DRAM bursts per row (rows are 32-byte aligned: the stride is
+// a multiple of 8 words) at the price of W times the counter registers.
+template <int W>
+struct QsVec;
+template <>
+struct QsVec<1> {
+    uint32_t v[1];
+    __device__ __forceinline__ void load(const uint32_t *p) { v[0] = __ldg(p); }
+};
+template <>
+struct QsVec<2> {
+    uint32_t v[2];
+    __device__ __forceinline__ void load(const uint32_t *p) { const uint2 t = __ldg((const uint2 *)p); v[0] = t.x; v[1] = t.y; }
+};
+template <>
+struct QsVec<4> {
+    uint32_t v[4];
+    __device__ __forceinline__ void load(const uint32_t *p) { const uint4 t = __ldg((const uint4 *)p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+};
+
+template <int W>
 __global__ void __launch_bounds__(QS_WARPS * 32)
-query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint32_t lw, uint64_t row_begin, uint64_t row_end,
+query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint32_t lw, uint32_t ls, uint64_t row_begin, uint64_t row_end,
                     const uint32_t *__restrict__ positions, const unsigned long long *__restrict__ q_off,
                     uint32_t *__restrict__ hits) {
-    __shared__ uint32_t sm_hits[1024];
+    __shared__ uint32_t sm_hits[1024 * W];
     __shared__ unsigned long long sm_range[2];
     const uint32_t q = blockIdx.z;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t col = blockIdx.y * 32 + lane;
-    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) sm_hits[i] = 0;
+    const uint32_t col = (blockIdx.y * 32 + lane) * W;  // first column word of this lane (ls is a multiple of 8: whole vectors)
+    for (uint32_t i = threadIdx.x; i < 1024 * W; i += blockDim.x) sm_hits[i] = 0;
     if (threadIdx.x == 0) {
         // positions are ascending: the ones inside [row_begin, row_end) form one contiguous range
         const unsigned long long b = q_off[q], e = q_off[q + 1];
@@ -2255,11 +2277,13 @@ query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint
     const unsigned long long sub_b = rb + ((unsigned long long)blockIdx.x * QS_WARPS + warp) * QS_SUB;
     if (sub_b < re) {
         const unsigned long long sub_e = min(sub_b + (unsigned long long)QS_SUB, re);
-        const uint32_t *__restrict__ colp = sliced + (col < lw ? col : 0);
-        const bool live = col < lw;
-        uint32_t P[12];
+        const bool live = col < lw;  // padding words (lw .. ls) may be read by a live vector; their leaves are dropped below
+        const uint32_t *__restrict__ colp = sliced + (live ? col : 0);
+        uint32_t P[W][12];
 #pragma unroll
-        for (int i = 0; i < 12; i++) P[i] = 0;
+        for (int w = 0; w < W; w++)
+#pragma unroll
+            for (int i = 0; i < 12; i++) P[w][i] = 0;
         for (unsigned long long base = sub_b; base < sub_e; base += 28) {
             // 28 positions per round: one coalesced load of positions, then 4 groups of 7 independent row reads
             const unsigned long long idx = base + lane;
@@ -2267,42 +2291,56 @@ query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint
             // (issuing all 28 row reads before the first use was measured: 76 registers, lower occupancy, 1.5x slower)
 #pragma unroll
             for (int g7 = 0; g7 < 4; g7++) {
-                uint32_t x[7];
+                QsVec<W> x[7];
 #pragma unroll
                 for (int j = 0; j < 7; j++) {
                     const uint32_t p = __shfl_sync(0xffffffffu, mypos, g7 * 7 + j);
-                    x[j] = (p != 0xFFFFFFFFu && live) ? __ldg(colp + ((uint64_t)p - row_begin) * lw) : 0u;
-                }
-                uint32_t sa, ca, sb, cb, ones, cc, twos, fours;
-                full_add(x[0], x[1], x[2], sa, ca);
-                full_add(x[3], x[4], x[5], sb, cb);
-                full_add(sa, sb, x[6], ones, cc);
-                full_add(ca, cb, cc, twos, fours);
-                uint32_t k;
-                k = P[0] & ones; P[0] ^= ones;
-                full_add(P[1], twos, k, P[1], k);
-                full_add(P[2], fours, k, P[2], k);
+                    if (p != 0xFFFFFFFFu && live) x[j].load(colp + ((uint64_t)p - row_begin) * ls);
+                    else {
 #pragma unroll
-                for (int i = 3; i < 12; i++) { const uint32_t t = P[i] & k; P[i] ^= k; k = t; }
+                        for (int w = 0; w < W; w++) x[j].v[w] = 0u;
+                    }
+                }
+#pragma unroll
+                for (int w = 0; w < W; w++) {
+                    uint32_t sa, ca, sb, cb, ones, cc, twos, fours;
+                    full_add(x[0].v[w], x[1].v[w], x[2].v[w], sa, ca);
+                    full_add(x[3].v[w], x[4].v[w], x[5].v[w], sb, cb);
+                    full_add(sa, sb, x[6].v[w], ones, cc);
+                    full_add(ca, cb, cc, twos, fours);
+                    uint32_t k;
+                    k = P[w][0] & ones; P[w][0] ^= ones;
+                    full_add(P[w][1], twos, k, P[w][1], k);
+                    full_add(P[w][2], fours, k, P[w][2], k);
+#pragma unroll
+                    for (int i = 3; i < 12; i++) { const uint32_t t = P[w][i] & k; P[w][i] ^= k; k = t; }
+                }
             }
         }
         if (live) {
-#pragma unroll 4
-            for (int l = 0; l < 32; l++) {
-                uint32_t c = 0;
 #pragma unroll
-                for (int i = 0; i < 12; i++) c |= ((P[i] >> l) & 1u) << i;
-                if (c) atomicAdd(sm_hits + lane * 32 + l, c);
+            for (int w = 0; w < W; w++) {
+#pragma unroll 4
+                for (int l = 0; l < 32; l++) {
+                    uint32_t c = 0;
+#pragma unroll
+                    for (int i = 0; i < 12; i++) c |= ((P[w][i] >> l) & 1u) << i;
+                    if (c) atomicAdd(sm_hits + (lane * W + w) * 32 + l, c);
+                }
             }
         }
     }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < 1024; i += blockDim.x) {
-        const uint32_t leaf = blockIdx.y * 1024 + i;
+    for (uint32_t i = threadIdx.x; i < 1024 * W; i += blockDim.x) {
+        const uint32_t leaf = blockIdx.y * 1024 * W + i;
         const uint32_t c = sm_hits[i];
         if (c && leaf < n_leaves) atomicAdd(hits + (uint64_t)q * n_leaves + leaf, c);
     }
 }
+
+// Row stride of the bit-sliced matrix: ceil(n_leaves / 32) words rounded up to 8 words, so that every row starts on a
+// 32-byte sector boundary (10,000 leaves: 313 -> 320 words; an unaligned 128-byte row segment costs five sectors, not four).
+extern "C" uint32_t msbt_sliced_row_words(uint32_t n_leaves) { return (((n_leaves + 31) / 32) + 7u) & ~7u; }
 
 extern "C" int msbt_bitslice_build(msbt_ctx *ctx, const uint64_t *const *h_leaves, uint32_t n_leaves,
                                    uint64_t row_begin, uint64_t row_end, uint32_t *d_sliced, void *stream_) {
@@ -2324,7 +2362,8 @@ extern "C" int msbt_bitslice_build(msbt_ctx *ctx, const uint64_t *const *h_leave
     const uint32_t gy = (lw + 31) / 32;
     const uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((n_rowwords + BS_WORDS - 1) / BS_WORDS,
                                                                   std::max<uint64_t>(1, (uint64_t)ctx->num_sms * 12 / gy)));
-    bitslice_kernel<<<dim3((unsigned)gx, gy), 256, BS_SMEM_BYTES, stream>>>(d_l, n_leaves, row_begin, row_end, lw, d_sliced);
+    bitslice_kernel<<<dim3((unsigned)gx, gy), 256, BS_SMEM_BYTES, stream>>>(d_l, n_leaves, row_begin, row_end, lw,
+                                                                             msbt_sliced_row_words(n_leaves), d_sliced);
     LAUNCH_CHECK(ctx);
     return MSBT_OK;
 }
@@ -2357,10 +2396,19 @@ extern "C" int msbt_query_batch_sliced(msbt_ctx *ctx, const uint32_t *d_sliced, 
     // hits accumulate with atomics: clear first (partial results of other bit ranges are summed by the caller)
     CU_TRY(ctx, cudaMemsetAsync(d_hits, 0, (size_t)n_queries * n_leaves * 4, stream));
     const uint64_t per_cta = (uint64_t)QS_WARPS * QS_SUB;
-    const uint32_t gx = (uint32_t)((max_pos + per_cta - 1) / per_cta), gy = (lw + 31) / 32;
+    const uint32_t gx = (uint32_t)((max_pos + per_cta - 1) / per_cta);
+    const uint32_t ls = msbt_sliced_row_words(n_leaves);
+    // words per lane: 8-byte loads (256 contiguous bytes of a row per warp) once a row has at least 64 words; 16-byte loads
+    // need 134 registers and lose to the occupancy drop (tools/bench_query.py, 10,000 leaves: W = 1 / 2 / 4 ->
+    // 48 % / 66 % / 40 % of the HBM peak)
+    int W = ls >= 64 ? 2 : 1;
+    if (const char *e = getenv("MSBT_QS_W")) { const int w = atoi(e); if (w == 1 || w == 2 || w == 4) W = w; }  // tuning aid
+    const uint32_t gy = (ls + 32 * W - 1) / (32 * W);
     if (gy > 65535) return fail(ctx, MSBT_EINVAL, "query_batch_sliced: too many leaves");
-    query_sliced_kernel<<<dim3(gx, gy, n_queries), QS_WARPS * 32, 0, stream>>>(d_sliced, n_leaves, lw, row_begin, row_end,
-                                                                                 d_positions, d_off, d_hits);
+    const dim3 grid(gx, gy, n_queries);
+    if (W == 4) query_sliced_kernel<4><<<grid, QS_WARPS * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_off, d_hits);
+    else if (W == 2) query_sliced_kernel<2><<<grid, QS_WARPS * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_off, d_hits);
+    else query_sliced_kernel<1><<<grid, QS_WARPS * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_off, d_hits);
     LAUNCH_CHECK(ctx);
     return MSBT_OK;
 }

@@ -351,9 +351,13 @@ class Context:
         self._check(rc, "msbt_query_batch")
         return hits
 
+    def sliced_row_words(self, n_leaves: int) -> int:
+        """u32 words per row of the bit-sliced matrix for `n_leaves` leaves (ceil(L/32) rounded up to 8 words)."""
+        return int(self._L.msbt_sliced_row_words(n_leaves))
+
     def bitslice(self, leaves: Sequence[torch.Tensor], row_begin: int, row_end: int) -> torch.Tensor:
-        """Bit-sliced leaf matrix for rows [row_begin, row_end): int32[rows, ceil(L/32)]."""
-        lw = (len(leaves) + 31) // 32
+        """Bit-sliced leaf matrix for rows [row_begin, row_end): int32[rows, sliced_row_words(L)] (rows padded to 32 bytes)."""
+        lw = self.sliced_row_words(len(leaves))
         out = torch.empty((max(row_end - row_begin, 0), lw), dtype=torch.int32, device=self.device)
         rc = self._L.msbt_bitslice_build(self._h, _ptr_array(leaves), len(leaves), row_begin, row_end, out.data_ptr(), self._stream())
         self._check(rc, "msbt_bitslice_build")

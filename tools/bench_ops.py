@@ -153,7 +153,7 @@ def run(ctx, n_leaves=1024, filter_bits=1 << 28, n_mags=64, genome_bp=5_000_000,
     # the queries are the real MAG positions above, so the gather pattern and the traffic are the real ones.
     try:
         L4, shard_rows = 10_000, m // 8
-        lw4 = (L4 + 31) // 32
+        lw4 = ctx.sliced_row_words(L4)
         big = torch.empty((shard_rows, lw4), dtype=torch.int32, device=dev)
         step = 1 << 20
         gen = torch.Generator(device=dev)

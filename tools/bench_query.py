@@ -56,7 +56,7 @@ def main():
     ctx = ops.Context(local)
     k, m, L = 31, a.filter_bits, a.leaves
     row_begin, row_end = shard.bit_ranges(m, world)[rank]
-    lw = (L + 31) // 32
+    lw = ctx.sliced_row_words(L)  # row stride: ceil(L/32) rounded up to 8 words
 
     # ---- setup (untimed): leaves in groups, only this rank's rows of the sliced matrix are kept
     sliced = torch.empty((row_end - row_begin, lw), dtype=torch.int32, device=dev)
