@@ -317,13 +317,15 @@ class Context:
         n = min(int(count.item()), cap)
         return pos[:n]
 
-    def extract_positions_batch(self, filters: Sequence[torch.Tensor], num_bits: int, cap: Optional[int] = None) -> List[torch.Tensor]:
-        """Ascending set-bit positions of every filter of a batch (three launches for the whole batch).
+    def extract_positions_packed(self, filters: Sequence[torch.Tensor], num_bits: int, cap: Optional[int] = None
+                                 ) -> Tuple[torch.Tensor, List[int]]:
+        """Ascending set-bit positions of every filter of a batch, back to back in ONE int32 tensor (uint32 bit
+        patterns), plus the n + 1 host offsets that delimit them (three launches for the whole batch).
         `cap`: upper bound on the total count (e.g. the summed k-mer counts); None sizes the buffer with one
-        extra counting pass.  Returns one int32 view (uint32 bit patterns) per filter."""
+        extra counting pass."""
         n = len(filters)
         if n == 0:
-            return []
+            return torch.zeros(1, dtype=torch.int32, device=self.device), [0]
         words = filter_words(num_bits)
         ptrs = _ptr_array(filters)
         offs = torch.empty(n + 1, dtype=torch.int64, device=self.device)
@@ -334,8 +336,14 @@ class Context:
         pos = torch.empty(max(cap, 1), dtype=torch.int32, device=self.device)
         rc = self._L.msbt_bf_extract_positions_batch(self._h, ptrs, n, words, pos.data_ptr(), cap, offs.data_ptr(), self._stream())
         self._check(rc, "msbt_bf_extract_positions_batch")
-        h = offs.cpu().tolist()
-        return [pos[min(h[i], cap): min(h[i + 1], cap)] for i in range(n)]
+        return pos, [min(int(x), cap) for x in offs.cpu().tolist()]
+
+    def extract_positions_batch(self, filters: Sequence[torch.Tensor], num_bits: int, cap: Optional[int] = None) -> List[torch.Tensor]:
+        """The same as one int32 view per filter."""
+        if len(filters) == 0:
+            return []
+        pos, h = self.extract_positions_packed(filters, num_bits, cap)
+        return [pos[h[i]: h[i + 1]] for i in range(len(filters))]
 
     def query_batch(self, leaves: Sequence[torch.Tensor], positions: Sequence[torch.Tensor]) -> torch.Tensor:
         """hits[q][l] = number of query q's positions set in leaf l (row-major probe) -> int32[q, l]."""
@@ -366,14 +374,20 @@ class Context:
     def query_batch_sliced(self, sliced: torch.Tensor, n_leaves: int, row_begin: int, row_end: int,
                            positions: Sequence[torch.Tensor]) -> torch.Tensor:
         """Partial hits of the positions that fall into rows [row_begin, row_end) -> int32[q, l]."""
-        nq = len(positions)
-        hits = torch.zeros((nq, n_leaves), dtype=torch.int32, device=self.device)
-        if nq == 0 or n_leaves == 0:
+        offs = [0]
+        for p in positions:
+            offs.append(offs[-1] + p.numel())
+        allpos = torch.cat([p.reshape(-1) for p in positions]) if offs[-1] else torch.zeros(1, dtype=torch.int32, device=self.device)
+        return self.query_sliced_packed(sliced, n_leaves, row_begin, row_end, allpos, offs)
+
+    def query_sliced_packed(self, sliced: torch.Tensor, n_leaves: int, row_begin: int, row_end: int,
+                            allpos: torch.Tensor, offsets: Sequence[int]) -> torch.Tensor:
+        """query_batch_sliced on positions that already sit back to back in one tensor (extract_positions_packed)."""
+        nq = len(offsets) - 1
+        hits = torch.zeros((max(nq, 0), n_leaves), dtype=torch.int32, device=self.device)
+        if nq <= 0 or n_leaves == 0:
             return hits
-        offs = (ctypes.c_uint64 * (nq + 1))()
-        for i, p in enumerate(positions):
-            offs[i + 1] = offs[i] + p.numel()
-        allpos = torch.cat([p.reshape(-1) for p in positions]) if offs[nq] else torch.zeros(1, dtype=torch.int32, device=self.device)
+        offs = (ctypes.c_uint64 * (nq + 1))(*[int(x) for x in offsets])
         rc = self._L.msbt_query_batch_sliced(self._h, sliced.data_ptr(), n_leaves, row_begin, row_end, allpos.data_ptr(),
                                              offs, nq, hits.data_ptr(), self._stream())
         self._check(rc, "msbt_query_batch_sliced")

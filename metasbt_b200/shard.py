@@ -4,9 +4,9 @@ gloo in the CPU tests), so the partition / merge arithmetic is testable without 
 
 * K1 construction  : genomes are independent -> contiguous blocks balanced by k-mer count, NO collective.
 * K3 / K3' counts  : filters sharded by bit range -> partial counts -> all_reduce(SUM) of u64 counters.
-* K4 query         : bit-sliced leaf matrix sharded by contiguous row (bit) range; every rank probes the
-                     positions that fall into its rows -> partial hits[B][L] -> all_reduce(SUM) (or
-                     reduce_scatter over MAG rows when each rank only needs its own MAGs).
+* K4 query         : bit-sliced leaf matrix sharded by contiguous row (bit) range; every rank extracts and probes
+                     the positions that fall into its rows -> partial hits[B][L] -> all_reduce(SUM)
+                     (query_sharded).
 * K2 union         : OR is not an NCCL reduction op.  Partials are merged by bit range: all_to_all of
                      range r of every partial to rank r, local OR, all_gather of the merged ranges.
 """
@@ -55,6 +55,24 @@ def all_reduce_counts(partial: torch.Tensor, group=None) -> torch.Tensor:
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
     return partial
+
+
+def query_sharded(ctx, sliced: torch.Tensor, n_leaves: int, num_bits: int, query_filters: Sequence[torch.Tensor],
+                  cap: int | None = None, group=None, rank: int | None = None, world: int | None = None) -> torch.Tensor:
+    """K4 across ranks.  `sliced` holds this rank's rows of the bit-sliced leaf matrix (ops.Context.bitslice on
+    bit_ranges(num_bits, world)[rank]); `query_filters` are the queries' own min=1 filters (whole, on every rank).
+    Each rank extracts only the positions of ITS bit range (word sub-views of the query filters: the ranges are 128-bit
+    aligned), probes its shard with them and the partial hit matrices are summed -> int32[q, l] on every rank.
+    With explicit `rank` / `world` the partial matrix of that shard is returned and no collective runs (tests)."""
+    partial_only = rank is not None and world is not None
+    if not partial_only:
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(group) if world > 1 else 0
+    rb, re_ = bit_ranges(num_bits, world)[rank]
+    w0, w1 = rb // 64, (re_ + 63) // 64
+    pos, offs = ctx.extract_positions_packed([f[w0:w1] for f in query_filters], (w1 - w0) * 64, cap)
+    hits = ctx.query_sliced_packed(sliced, n_leaves, 0, re_ - rb, pos, offs)  # positions are relative to rb
+    return hits if partial_only else all_reduce_counts(hits, group)
 
 
 def or_merge(partial: torch.Tensor, num_bits: int, group=None) -> torch.Tensor:

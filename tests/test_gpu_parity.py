@@ -324,6 +324,28 @@ def test_makebf_min_abundance_all_repeats(ctx, oracle, min_path):
     assert oracle.bf_popcount(oracle.makebf(fa, k, m, 7)) > 30_000 and oracle.bf_popcount(want) == 0
 
 
+def test_query_sharded_partials_add_up(ctx, oracle):
+    """shard.query_sharded: every bit-range shard extracts only its own positions from the query filters and probes its own
+    rows; the partial hit matrices of 1, 2, 3 and 5 shards add up to the oracle's hits (odd world sizes: uneven ranges)."""
+    from metasbt_b200 import shard
+    rng = random.Random(99)
+    k, num_bits, n_leaves = 15, (1 << 14) + 192, 70
+    leaf_fa = [util.messy_fasta(rng, 2, 1500, "ACGT") for _ in range(n_leaves)]
+    leaves_dev, leaf_bits = build(ctx, leaf_fa, k, num_bits)
+    queries = [leaf_fa[3] + util.messy_fasta(rng, 1, 800, "ACGT"), leaf_fa[40][: len(leaf_fa[40]) // 2], b">e\nACG\n"]
+    qf, _ = build(ctx, queries, k, num_bits)
+    want = np.stack([oracle.query_hits(oracle.positions_distinct(q, k, num_bits), leaf_bits) for q in queries])
+    leaves = [leaves_dev[i] for i in range(n_leaves)]
+    for world in (1, 2, 3, 5):
+        total = None
+        for rank in range(world):
+            rb, re_ = shard.bit_ranges(num_bits, world)[rank]
+            part = shard.query_sharded(ctx, ctx.bitslice(leaves, rb, re_), n_leaves, num_bits, [qf[i] for i in range(len(queries))],
+                                       rank=rank, world=world)
+            total = part if total is None else total + part
+        assert np.array_equal(total.cpu().numpy().astype(np.uint64), want), world
+
+
 def _ingest_cases():
     rng = random.Random(42)
     big_line = b">one_line\n" + util.codes_to_fasta(util.synthetic_codes(5, 20000), "x", 0).split(b"\n", 1)[1]

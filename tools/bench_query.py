@@ -6,9 +6,9 @@ leaf matrix is sharded by contiguous bit range over the GPUs of one box (SURVEY.
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29513 tools/bench_query.py ...
 
 Every rank: builds all leaves (K1; related genomes, 10 per species), keeps only ITS rows of the bit-sliced matrix
-(msbt_bitslice_build on [row_begin, row_end)), hashes all MAGs of the batch (K1 + ordered extraction: redundant across
-ranks, as SURVEY 8e proposes) and probes its shard (msbt_query_batch_sliced); the partial hit matrices are summed with one
-NCCL all_reduce.  A step = one batch of MAGs through hash -> extract -> probe -> all_reduce; time = CUDA events on the
+(msbt_bitslice_build on [row_begin, row_end)), hashes all MAGs of the batch (K1, redundant across ranks as SURVEY 8e
+proposes), extracts the positions of its own bit range and probes its shard (shard.query_sharded); the partial hit
+matrices are summed with one NCCL all_reduce.  A step = one batch of MAGs through hash -> extract -> probe -> all_reduce; time = CUDA events on the
 launching stream between barriers, max over ranks.  Strong scaling: the total problem is fixed, the shard shrinks with N.
 The default filter size (2^25 bits) is chosen so that the whole 10,000-leaf matrix (42 GB) also fits ONE GPU; at 2^28 bits
 it needs the 8 GPUs the config names.  Prints one JSON line on rank 0."""
@@ -90,13 +90,11 @@ def main():
     qf = ctx.alloc_filters(a.mags, m)
     launches0 = None
 
+    qrows = [qf[i] for i in range(a.mags)]
+
     def step():
-        ctx.build_filters(qbatch, k, m, out=qf)
-        positions = ctx.extract_positions_batch([qf[i] for i in range(a.mags)], m, cap=a.mags * a.mag_bp)
-        hits = ctx.query_batch_sliced(sliced, L, row_begin, row_end, positions)
-        if world > 1:
-            dist.all_reduce(hits, op=dist.ReduceOp.SUM)
-        return hits, positions
+        ctx.build_filters(qbatch, k, m, out=qf)  # every rank hashes the whole batch (K1)
+        return shard.query_sharded(ctx, sliced, L, m, qrows, cap=a.mags * a.mag_bp)  # extract own range, probe, all_reduce
 
     for _ in range(a.warmup):
         step()
@@ -106,7 +104,7 @@ def main():
     launches0 = ctx.launch_count
     e0.record()
     for _ in range(a.steps):
-        hits, positions = step()
+        hits = step()
     e1.record()
     torch.cuda.synchronize()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -116,13 +114,15 @@ def main():
     launches = ctx.launch_count - launches0
 
     # probe-only time of this rank's shard (the dominant kernel) for the roofline
+    w0, w1 = row_begin // 64, (row_end + 63) // 64
+    pos, offs = ctx.extract_positions_packed([f[w0:w1] for f in qrows], (w1 - w0) * 64, cap=a.mags * a.mag_bp)
     e0.record()
-    ctx.query_batch_sliced(sliced, L, row_begin, row_end, positions)
+    ctx.query_sliced_packed(sliced, L, 0, row_end - row_begin, pos, offs)
     e1.record()
     torch.cuda.synchronize()
     t_probe = e0.elapsed_time(e1) / 1e3
-    n_pos = sum(int(p.numel()) for p in positions)
-    in_range = sum(int(((p >= row_begin) & (p < row_end)).sum()) for p in positions)
+    in_range = int(offs[-1])
+    n_pos = int(sum(int(c) for c in ctx.bf_popcount(qrows, m).tolist()))
     best = hits.argmax(dim=1).cpu().tolist()
     same_species = sum(1 for q, g in enumerate(src) if best[q] // 10 == g // 10)
     checksum = int((hits.to(torch.int64) * (torch.arange(L, device=dev, dtype=torch.int64) % 1009 + 1)).sum().item())
@@ -139,7 +139,7 @@ def main():
             "ms_per_step": sec * 1e3 / a.steps, "higher_is_better": True, "scaling": "strong", "dtype": "u32", "data": "synthetic",
             "config": {"workload": "configs[3]: %d MAGs x %.1f Mbp per step against %d leaves (5 Mbp genomes, 10 per species), k=31, 2^%d-bit filters"
                                    % (a.mags, a.mag_bp / 1e6, L, m.bit_length() - 1),
-                       "sharding": "rows [r*m/N, (r+1)*m/N) of the bit-sliced matrix per rank; hashing replicated; hits all_reduce(SUM)",
+                       "sharding": "rows [r*m/N, (r+1)*m/N) of the bit-sliced matrix per rank; hashing replicated, extraction and probe per bit range; hits all_reduce(SUM)",
                        "l2": "the shard (%.1f GB) is far larger than L2" % (sliced.numel() * 4 / 1e9)},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": "query_sliced_kernel (rank 0's shard)", "achieved": algo / t_probe / 1e9, "peak": peak,

@@ -74,6 +74,9 @@ def main():
     shard.all_reduce_counts(hits)
     ref = np.stack([O.query_hits(O.positions_distinct(q, k, m), want) for q in queries])
     assert np.array_equal(hits.cpu().numpy().astype(np.uint64), ref), "K4 rank %d" % rank
+    # the same through shard.query_sharded (each rank extracts only the positions of its own bit range)
+    hits2 = shard.query_sharded(ctx, sliced, n, m, [qf[i] for i in range(len(queries))])
+    assert np.array_equal(hits2.cpu().numpy().astype(np.uint64), ref), "K4 query_sharded rank %d" % rank
     dist.barrier()
     if rank == 0:
         print("multi-GPU parity ok: world=%d, K1 blocks %s, K2 OR-merge, K3 and K4 bit-range shards all match the oracle" % (world, counts))
