@@ -52,12 +52,20 @@ class CudaBackend:
         self.sketch_batch = max(1, sketch_batch_bytes // (self.stride * 8))
         self._cache: "OrderedDict[str, torch.Tensor]" = OrderedDict()
         self._bytes = 0
+        # bit-sliced leaf matrices of flat trees that are queried repeatedly (see query_hits)
+        self.sliced_min_leaves = 256
+        self.sliced_cache_bytes = 48 << 30
+        self._sliced: "OrderedDict[Tuple[str, ...], torch.Tensor]" = OrderedDict()
+        self._sliced_bytes = 0
+        self._tree_queries: Dict[Tuple[str, ...], int] = dict()
+        self.sliced_probes = 0  # queries served by the bit-sliced probe (observability / tests)
 
     # ------------------------------------------------------------------ device filter cache
     def _put(self, path: str, t: torch.Tensor) -> None:
         path = os.path.abspath(path)
         if path in self._cache:
             self._bytes -= self._cache.pop(path).numel() * 8
+            self._drop_sliced(path)
         self._cache[path] = t
         self._bytes += t.numel() * 8
         while self._bytes > self.cache_bytes and len(self._cache) > 1:
@@ -65,9 +73,16 @@ class CudaBackend:
             self._bytes -= old.numel() * 8
 
     def forget(self, path: str) -> None:
-        t = self._cache.pop(os.path.abspath(path), None)
+        path = os.path.abspath(path)
+        t = self._cache.pop(path, None)
         if t is not None:
             self._bytes -= t.numel() * 8
+        self._drop_sliced(path)
+
+    def _drop_sliced(self, path: str) -> None:
+        """A filter was rewritten: every cached bit-sliced matrix that contains it is stale."""
+        for key in [k for k in self._sliced if path in k]:
+            self._sliced_bytes -= self._sliced.pop(key).numel() * 4
 
     def filter(self, path: str) -> torch.Tensor:
         """Device tensor (int64[stride]) of the filter stored at `path` (cached)."""
@@ -172,9 +187,40 @@ class CudaBackend:
         total = int(positions.numel())
         if not leaf_paths:
             return [], total
-        leaves = [self.filter(p) for p in leaf_paths]
-        hits = self.ctx.query_batch(leaves, [positions])
+        sliced = self._sliced_tree(leaf_paths)
+        if sliced is not None:
+            self.sliced_probes += 1
+            hits = self.ctx.query_batch_sliced(sliced, len(leaf_paths), 0, self.num_bits, [positions])
+        else:
+            hits = self.ctx.query_batch([self.filter(p) for p in leaf_paths], [positions])
         return [int(x) for x in hits[0].cpu()], total
+
+    def _sliced_tree(self, leaf_paths: Sequence[str]) -> Optional[torch.Tensor]:
+        """Bit-sliced matrix of a flat tree's leaves, or None when the row-major probe should serve the query.
+        The row-major probe reads one 32-byte sector per (position, leaf); the bit-sliced one reads 1/8 byte per
+        (position, leaf) but needs the leaves transposed first (one pass over all of them).  A tree with many leaves
+        that is queried again -- `profile` walks the same trees for every input genome -- gets transposed on its second
+        query and the matrix is kept (LRU, bounded in bytes; dropped when one of its filters is rewritten)."""
+        n = len(leaf_paths)
+        if n < self.sliced_min_leaves:
+            return None
+        key = tuple(os.path.abspath(p) for p in leaf_paths)
+        t = self._sliced.get(key)
+        if t is not None:
+            self._sliced.move_to_end(key)
+            return t
+        seen = self._tree_queries.get(key, 0) + 1
+        self._tree_queries[key] = seen
+        nbytes = self.num_bits * self.ctx.sliced_row_words(n) * 4
+        if seen < 2 or nbytes > self.sliced_cache_bytes:
+            return None
+        t = self.ctx.bitslice([self.filter(p) for p in key], 0, self.num_bits)
+        self._sliced[key] = t
+        self._sliced_bytes += nbytes
+        while self._sliced_bytes > self.sliced_cache_bytes and len(self._sliced) > 1:
+            _, old = self._sliced.popitem(last=False)
+            self._sliced_bytes -= old.numel() * 4
+        return t
 
     def query_many(self, query_filters: Sequence[torch.Tensor], leaf_paths: Sequence[str]):
         """hits[q][l] and totals[q] for device-resident query filters against the given leaves."""

@@ -414,3 +414,43 @@ def test_makebf_maximum_filter_size(ctx, oracle, num_bits):
     assert int(ctx.bf_popcount([out[0]], num_bits)[0]) == oracle.bf_popcount(want) > 199_000
     del out
     torch.cuda.empty_cache()
+
+
+def test_backend_sliced_tree_cache(ctx, oracle, tmp_path):
+    """CudaBackend.query_hits: a flat tree with many leaves is transposed on its second query and probed bit-sliced from
+    then on; the hits equal the oracle's every time, and rewriting one leaf invalidates the cached matrix."""
+    from metasbt_b200 import backend as B, bffile
+    rng = random.Random(4242)
+    k, num_bits, n_leaves = 21, 1 << 16, 300
+    be = B.CudaBackend(k, num_bits)
+    fas, bfs = [], []
+    for i in range(n_leaves):
+        fa = tmp_path / ("leaf%03d.fa" % i)
+        fa.write_bytes(util.messy_fasta(rng, 1, 900, "ACGT"))
+        fas.append(str(fa))
+        bfs.append(str(tmp_path / ("leaf%03d.bf" % i)))
+    be.sketch_many(fas, bfs, 1)
+    qfa = tmp_path / "query.fa"
+    qfa.write_bytes(open(fas[7], "rb").read() + open(fas[123], "rb").read() + util.messy_fasta(rng, 1, 500, "ACGTN"))
+    positions = be.query_positions(str(qfa))
+    qpos = oracle.positions_distinct(qfa.read_bytes(), k, num_bits)
+
+    def want():
+        return [int(x) for x in oracle.query_hits(qpos, [bffile.read_bf(p)[1] for p in bfs])]
+
+    for expected_sliced in (0, 1, 2):
+        hits, total = be.query_hits(positions, bfs)
+        assert total == len(qpos) and hits == want()
+        assert be.sliced_probes == expected_sliced
+    for i in (7, 123):  # the query contains these leaves whole
+        assert hits[i] == oracle.bf_popcount(bffile.read_bf(bfs[i])[1])
+    # rewrite leaf 5 with the content of leaf 7: the cached matrix must go, the next answer must see the new leaf
+    be.sketch_many([fas[7]], [bfs[5]], 1)
+    hits, _ = be.query_hits(positions, bfs)
+    assert hits == want() and hits[5] == hits[7]
+    # small trees stay on the row-major probe
+    before = be.sliced_probes
+    for _ in range(3):
+        h, _ = be.query_hits(positions, bfs[:40])
+        assert h == want()[:40]
+    assert be.sliced_probes == before
