@@ -2131,83 +2131,149 @@ extern "C" int msbt_query_batch(msbt_ctx *ctx, const uint64_t *const *h_leaves, 
     return MSBT_OK;
 }
 
-// Bit-slice transpose.  sliced[(p - row_begin) * lw + (l >> 5)] bit (l & 31) = bit p of leaf l.
-// CTA tile = up to 1024 leaves x 256 rows: every leaf contributes one 32-byte run (sector-efficient reads), the
-// 32 x 32 bit blocks are transposed in registers with a 5-stage shuffle butterfly, and the tile leaves as full
-// 128-byte row segments (coalesced writes) -- read every leaf once, write the sliced matrix once.
-constexpr int BS_WORDS = 8;                       // u32 words (= 256 rows) of every leaf per CTA
-constexpr int BS_LEAVES = 1024;                   // leaves per CTA (32 column words)
+// Bit-slice transpose.  sliced[(p - row_begin) * ls + (l >> 5)] bit (l & 31) = bit p of leaf l.
+// CTA tile = up to 512 leaves x 1024 rows: every leaf contributes one full 128-byte line per iteration (with one 32-byte
+// sector per leaf the memory system fetched 3.2 x the leaf bytes from DRAM: profiles/r01_ncu_k4_summary.txt), the
+// 32 x 32 bit blocks are transposed in registers with a 5-stage shuffle butterfly, and every warp streams its 32 rows
+// out as 64-byte row segments through a private staging buffer -- read every leaf once, write the sliced matrix once.
+// 100 KiB of shared memory per CTA: two CTAs per SM, one loading while the other one transposes.
+constexpr int BS_WORDS = 32;                      // u32 words (= 1024 rows, 128 bytes) of every leaf per CTA iteration
+constexpr int BS_COLS = 16;                       // column words (= 512 leaves) per CTA
+constexpr int BS_LEAVES = BS_COLS * 32;
+constexpr int BS_THREADS = 512;
+constexpr int BS_WARPS = BS_THREADS / 32;
 constexpr int BS_IN_STRIDE = BS_WORDS + 1;        // smem padding: conflict-free column reads
-constexpr int BS_OUT_STRIDE = 33;
-constexpr size_t BS_SMEM_BYTES = ((size_t)BS_LEAVES * BS_IN_STRIDE + (size_t)BS_WORDS * 32 * BS_OUT_STRIDE) * 4;
+constexpr int BS_OUT_STRIDE = BS_COLS + 1;
+constexpr size_t BS_SMEM_BYTES = ((size_t)BS_LEAVES * BS_IN_STRIDE + (size_t)BS_WARPS * 32 * BS_OUT_STRIDE) * 4;
 
-__device__ __forceinline__ uint32_t transpose32(uint32_t x, uint32_t lane) {
-    // lane r holds row r of a 32 x 32 bit matrix; returns column r (bit c = old row c, bit r)
-#define MSBT_T32_STAGE(J, M)                                                                   \
-    {                                                                                          \
-        const uint32_t t = __shfl_xor_sync(0xffffffffu, x, J);                                 \
-        x = (lane & J) ? ((x & ~M) | ((t & ~M) >> J)) : ((x & M) | ((t & M) << J));            \
+// 32 x 32 bit transpose across a warp: lane r holds row r; returns column r (bit c = old row c, bit r).
+// Stage J (mask M = the low J bits of every 2J-bit group): a lane of the lower half keeps (x & M) and takes
+// (t & M) << J from its partner, a lane of the upper half keeps (x & ~M) and takes (t & ~M) >> J.  Both are
+// (x & K) | (rot(t) & ~K) with a per-lane keep mask K and a per-lane rotation (left by J or by 32 - J; the bits a
+// rotation wraps around fall outside ~K), so a stage is SHFL + SHF + LOP3 with no predication.
+struct T32Lane {
+    uint32_t keep[5], rot[5];
+    __device__ __forceinline__ explicit T32Lane(uint32_t lane) {
+        const uint32_t m[5] = {0x0000FFFFu, 0x00FF00FFu, 0x0F0F0F0Fu, 0x33333333u, 0x55555555u};
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+            const uint32_t j = 16u >> s;
+            const bool up = (lane & j) != 0;
+            keep[s] = up ? ~m[s] : m[s];
+            rot[s] = up ? 32u - j : j;
+        }
     }
-    MSBT_T32_STAGE(16, 0x0000FFFFu) MSBT_T32_STAGE(8, 0x00FF00FFu) MSBT_T32_STAGE(4, 0x0F0F0F0Fu)
-    MSBT_T32_STAGE(2, 0x33333333u) MSBT_T32_STAGE(1, 0x55555555u)
-#undef MSBT_T32_STAGE
+};
+
+__device__ __forceinline__ uint32_t transpose32(uint32_t x, const T32Lane &tl) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const uint32_t t = __shfl_xor_sync(0xffffffffu, x, 16 >> s);
+        const uint32_t r = __funnelshift_l(t, t, tl.rot[s]);
+        asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(x) : "r"(tl.keep[s]), "r"(x), "r"(r));  // keep ? x : r
+    }
     return x;
 }
 
-__global__ void __launch_bounds__(256)
+// two independent transposes interleaved (the five stages of one are a dependent chain of shuffles)
+__device__ __forceinline__ void transpose32x2(uint32_t &x, uint32_t &y, const T32Lane &tl) {
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const uint32_t tx = __shfl_xor_sync(0xffffffffu, x, 16 >> s), ty = __shfl_xor_sync(0xffffffffu, y, 16 >> s);
+        const uint32_t rx = __funnelshift_l(tx, tx, tl.rot[s]), ry = __funnelshift_l(ty, ty, tl.rot[s]);
+        asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(x) : "r"(tl.keep[s]), "r"(x), "r"(rx));
+        asm("lop3.b32 %0, %1, %2, %3, 0xCA;" : "=r"(y) : "r"(tl.keep[s]), "r"(y), "r"(ry));
+    }
+}
+
+// One warp: transpose row word ww of the `cols` leaf groups held in `in`, stage the 32 rows x cols words in the warp's
+// `out` buffer and write them as row segments (two rows per store instruction when cols == BS_COLS).
+template <bool FULL>
+__device__ __forceinline__ void bitslice_warp(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t ww, uint32_t cols,
+                                              uint32_t lane, const T32Lane &tl, uint32_t *__restrict__ dst_row0, uint32_t ls,
+                                              uint32_t rows_valid) {
+    const uint32_t *src = in + lane * BS_IN_STRIDE + ww;
+    if (FULL) {
+#pragma unroll
+        for (int lg = 0; lg < BS_COLS; lg += 2) {
+            uint32_t x = src[lg * 32 * BS_IN_STRIDE], y = src[(lg + 1) * 32 * BS_IN_STRIDE];
+            transpose32x2(x, y, tl);
+            out[lane * BS_OUT_STRIDE + lg] = x;
+            out[lane * BS_OUT_STRIDE + lg + 1] = y;
+        }
+        __syncwarp();
+        // a store instruction writes rows i and i + 16 (16 * BS_OUT_STRIDE = 16 mod 32: the two half-warps read
+        // disjoint banks of the staging buffer)
+        constexpr int RPI = 32 / BS_COLS, RGAP = 32 / RPI;  // rows per instruction, distance between them
+        const uint32_t c = lane % BS_COLS, r0 = (lane / BS_COLS) * RGAP;
+        uint32_t *d = dst_row0 + (size_t)r0 * ls + c;
+        const uint32_t *o = out + r0 * BS_OUT_STRIDE + c;
+#pragma unroll
+        for (int i = 0; i < RGAP; i++) {
+            if (r0 + i < rows_valid) d[(size_t)i * ls] = o[i * BS_OUT_STRIDE];
+        }
+    } else {
+        for (uint32_t lg = 0; lg < cols; lg++) out[lane * BS_OUT_STRIDE + lg] = transpose32(src[lg * 32 * BS_IN_STRIDE], tl);
+        __syncwarp();
+        for (uint32_t idx = lane; idx < 32 * cols; idx += 32) {
+            const uint32_t r = idx / cols, c = idx - r * cols;
+            if (r < rows_valid) dst_row0[(size_t)r * ls + c] = out[r * BS_OUT_STRIDE + c];
+        }
+    }
+    __syncwarp();
+}
+
+__global__ void __launch_bounds__(BS_THREADS, 2)
 bitslice_kernel(const uint64_t *const *__restrict__ leaves, uint32_t n_leaves, uint64_t row_begin, uint64_t row_end,
                 uint32_t lw, uint32_t ls, uint32_t *__restrict__ sliced) {
     extern __shared__ uint32_t bs_smem[];
     uint32_t *in = bs_smem;                                     // [BS_LEAVES][BS_IN_STRIDE]
-    uint32_t *out = bs_smem + BS_LEAVES * BS_IN_STRIDE;         // [BS_WORDS * 32][BS_OUT_STRIDE]
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t *out = bs_smem + BS_LEAVES * BS_IN_STRIDE + warp * 32 * BS_OUT_STRIDE;  // per warp: [32][BS_OUT_STRIDE]
     const uint32_t leaf0 = blockIdx.y * BS_LEAVES;
     const uint32_t lg0 = leaf0 >> 5;
-    const uint32_t cols = min(32u, lw - lg0);                   // column words of this tile
+    const uint32_t cols = min((uint32_t)BS_COLS, lw - lg0);     // column words of this tile
     const uint64_t n_rowwords = (row_end - row_begin + 31) >> 5;
     const uint64_t first_word = row_begin >> 5;                 // row_begin is a multiple of 32
     const bool vec_ok = (first_word & 3) == 0;                  // leaf pointers are 16-byte aligned (checked by the host)
+    const T32Lane tl(lane);
     for (uint64_t wb = (uint64_t)blockIdx.x * BS_WORDS; wb < n_rowwords; wb += (uint64_t)gridDim.x * BS_WORDS) {
         __syncthreads();
         if (vec_ok && wb + BS_WORDS <= n_rowwords) {
-            // load: 2 lanes per leaf, one 16-byte load each (32 bytes = one sector per leaf), 128 leaves per pass
-            for (uint32_t l = threadIdx.x >> 1; l < cols * 32; l += 128) {
-                const uint32_t leaf = leaf0 + l, h = threadIdx.x & 1;
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (leaf < n_leaves) v = ld_stream((const uint4 *)((const uint32_t *)leaves[leaf] + first_word + wb) + h);
-                uint32_t *d = in + l * BS_IN_STRIDE + 4 * h;
-                d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+            // load: 8 lanes per leaf, one 16-byte load each (a full 128-byte line per leaf), 64 leaves per pass;
+            // all loads of a thread are issued before the first one is used
+            constexpr int PASSES = BS_LEAVES / (BS_THREADS / 8);
+            const uint32_t q = threadIdx.x & 7;
+            uint4 v[PASSES];
+#pragma unroll
+            for (int p = 0; p < PASSES; p++) {
+                const uint32_t l = (threadIdx.x >> 3) + p * (BS_THREADS / 8), leaf = leaf0 + l;
+                v[p] = make_uint4(0, 0, 0, 0);
+                if (l < cols * 32 && leaf < n_leaves) v[p] = ld_stream((const uint4 *)((const uint32_t *)leaves[leaf] + first_word + wb) + q);
+            }
+#pragma unroll
+            for (int p = 0; p < PASSES; p++) {
+                const uint32_t l = (threadIdx.x >> 3) + p * (BS_THREADS / 8);
+                uint32_t *d = in + l * BS_IN_STRIDE + 4 * q;
+                d[0] = v[p].x; d[1] = v[p].y; d[2] = v[p].z; d[3] = v[p].w;
             }
         } else {
-            // general: 8 lanes per leaf read its 8 consecutive words, 32 leaves per pass
-            for (uint32_t l = threadIdx.x >> 3; l < cols * 32; l += 32) {
-                const uint32_t leaf = leaf0 + l, ww = threadIdx.x & 7;
-                uint32_t v = 0;
-                if (leaf < n_leaves && wb + ww < n_rowwords) v = __ldg((const uint32_t *)leaves[leaf] + first_word + wb + ww);
-                in[l * BS_IN_STRIDE + ww] = v;
+            // general (unaligned first word or the last, partial tile): a warp reads the 32 words of one leaf
+            for (uint32_t l = warp; l < cols * 32; l += BS_WARPS) {
+                const uint32_t leaf = leaf0 + l;
+                uint32_t x = 0;
+                if (leaf < n_leaves && wb + lane < n_rowwords) x = __ldg((const uint32_t *)leaves[leaf] + first_word + wb + lane);
+                in[l * BS_IN_STRIDE + lane] = x;
             }
         }
         __syncthreads();
-        // transpose: warp ww handles row word ww of every leaf group
-        for (uint32_t lg = 0; lg < cols; lg++) {
-            const uint32_t x = transpose32(in[(lg * 32 + lane) * BS_IN_STRIDE + warp], lane);
-            out[(warp * 32 + lane) * BS_OUT_STRIDE + lg] = x;  // row (wb + warp) * 32 + lane, column word lg0 + lg
-        }
-        __syncthreads();
-        // store: full row segments
-        if (cols == 32) {
-#pragma unroll 4
-            for (uint32_t idx = threadIdx.x; idx < BS_WORDS * 32 * 32; idx += 256) {
-                const uint32_t r = idx >> 5, c = idx & 31;
-                const uint64_t row = wb * 32 + r;  // relative row
-                if (row_begin + row < row_end) sliced[row * ls + lg0 + c] = out[r * BS_OUT_STRIDE + c];
-            }
-        } else {
-            for (uint32_t idx = threadIdx.x; idx < BS_WORDS * 32 * cols; idx += 256) {
-                const uint32_t r = idx / cols, c = idx - r * cols;
-                const uint64_t row = wb * 32 + r;  // relative row
-                if (row_begin + row < row_end) sliced[row * ls + lg0 + c] = out[r * BS_OUT_STRIDE + c];
-            }
+        // transpose + store: warp w handles row words w, w + BS_WARPS of every leaf group
+        for (uint32_t ww = warp; ww < BS_WORDS && wb + ww < n_rowwords; ww += BS_WARPS) {
+            const uint64_t row0 = (wb + ww) * 32;  // relative row of the warp's first row
+            const uint32_t rows_valid = (uint32_t)min((uint64_t)32, row_end - row_begin - row0);
+            uint32_t *dst = sliced + row0 * ls + lg0;
+            if (cols == BS_COLS) bitslice_warp<true>(in, out, ww, cols, lane, tl, dst, ls, rows_valid);
+            else bitslice_warp<false>(in, out, ww, cols, lane, tl, dst, ls, rows_valid);
         }
     }
 }
@@ -2251,7 +2317,7 @@ struct QsVec<4> {
     __device__ __forceinline__ void load(const uint32_t *p) { const uint4 t = __ldg((const uint4 *)p); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
 };
 
-template <int W>
+template <int W, int G>
 __global__ void __launch_bounds__(QS_WARPS * 32)
 query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint32_t lw, uint32_t ls, uint64_t row_begin, uint64_t row_end,
                     const uint32_t *__restrict__ positions, const unsigned long long *__restrict__ q_off,
@@ -2284,37 +2350,44 @@ query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint
         for (int w = 0; w < W; w++)
 #pragma unroll
             for (int i = 0; i < 12; i++) P[w][i] = 0;
+        uint32_t nextpos = (lane < 28 && sub_b + lane < sub_e) ? positions[sub_b + lane] : 0xFFFFFFFFu;
         for (unsigned long long base = sub_b; base < sub_e; base += 28) {
-            // 28 positions per round: one coalesced load of positions, then 4 groups of 7 independent row reads
-            const unsigned long long idx = base + lane;
-            const uint32_t mypos = (lane < 28 && idx < sub_e) ? positions[idx] : 0xFFFFFFFFu;
+            // 28 positions per round: one coalesced load of positions (issued one round ahead, so that its latency is not
+            // in front of every round's row reads), then 4 groups of 7 independent row reads
+            const uint32_t mypos = nextpos;
+            const unsigned long long idx = base + 28 + lane;
+            nextpos = (lane < 28 && idx < sub_e) ? positions[idx] : 0xFFFFFFFFu;
             // (issuing all 28 row reads before the first use was measured: 76 registers, lower occupancy, 1.5x slower)
 #pragma unroll
-            for (int g7 = 0; g7 < 4; g7++) {
-                QsVec<W> x[7];
+            for (int g7 = 0; g7 < 4; g7 += G) {
+                QsVec<W> x[G][7];  // G groups of 7 rows in flight per lane
 #pragma unroll
-                for (int j = 0; j < 7; j++) {
-                    const uint32_t p = __shfl_sync(0xffffffffu, mypos, g7 * 7 + j);
-                    if (p != 0xFFFFFFFFu && live) x[j].load(colp + ((uint64_t)p - row_begin) * ls);
-                    else {
+                for (int g = 0; g < G; g++)
 #pragma unroll
-                        for (int w = 0; w < W; w++) x[j].v[w] = 0u;
+                    for (int j = 0; j < 7; j++) {
+                        const uint32_t p = __shfl_sync(0xffffffffu, mypos, (g7 + g) * 7 + j);
+                        if (p != 0xFFFFFFFFu && live) x[g][j].load(colp + ((uint64_t)p - row_begin) * ls);
+                        else {
+#pragma unroll
+                            for (int w = 0; w < W; w++) x[g][j].v[w] = 0u;
+                        }
                     }
-                }
 #pragma unroll
-                for (int w = 0; w < W; w++) {
-                    uint32_t sa, ca, sb, cb, ones, cc, twos, fours;
-                    full_add(x[0].v[w], x[1].v[w], x[2].v[w], sa, ca);
-                    full_add(x[3].v[w], x[4].v[w], x[5].v[w], sb, cb);
-                    full_add(sa, sb, x[6].v[w], ones, cc);
-                    full_add(ca, cb, cc, twos, fours);
-                    uint32_t k;
-                    k = P[w][0] & ones; P[w][0] ^= ones;
-                    full_add(P[w][1], twos, k, P[w][1], k);
-                    full_add(P[w][2], fours, k, P[w][2], k);
+                for (int g = 0; g < G; g++)
 #pragma unroll
-                    for (int i = 3; i < 12; i++) { const uint32_t t = P[w][i] & k; P[w][i] ^= k; k = t; }
-                }
+                    for (int w = 0; w < W; w++) {
+                        uint32_t sa, ca, sb, cb, ones, cc, twos, fours;
+                        full_add(x[g][0].v[w], x[g][1].v[w], x[g][2].v[w], sa, ca);
+                        full_add(x[g][3].v[w], x[g][4].v[w], x[g][5].v[w], sb, cb);
+                        full_add(sa, sb, x[g][6].v[w], ones, cc);
+                        full_add(ca, cb, cc, twos, fours);
+                        uint32_t k;
+                        k = P[w][0] & ones; P[w][0] ^= ones;
+                        full_add(P[w][1], twos, k, P[w][1], k);
+                        full_add(P[w][2], fours, k, P[w][2], k);
+#pragma unroll
+                        for (int i = 3; i < 12; i++) { const uint32_t t = P[w][i] & k; P[w][i] ^= k; k = t; }
+                    }
             }
         }
         if (live) {
@@ -2356,13 +2429,13 @@ extern "C" int msbt_bitslice_build(msbt_ctx *ctx, const uint64_t *const *h_leave
     rc = upload_ptrs(ctx, h_leaves, n_leaves, stream, &d_l);
     if (rc) return rc;
     const uint32_t lw = (n_leaves + 31) / 32;
-    if (lw > 65535) return fail(ctx, MSBT_EINVAL, "bitslice_build: too many leaves");
+    if ((lw + BS_COLS - 1) / BS_COLS > 65535) return fail(ctx, MSBT_EINVAL, "bitslice_build: too many leaves");
     const uint64_t n_rowwords = (row_end - row_begin + 31) >> 5;
     CU_TRY(ctx, cudaFuncSetAttribute(bitslice_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BS_SMEM_BYTES));
-    const uint32_t gy = (lw + 31) / 32;
+    const uint32_t gy = (lw + BS_COLS - 1) / BS_COLS;
     const uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((n_rowwords + BS_WORDS - 1) / BS_WORDS,
-                                                                  std::max<uint64_t>(1, (uint64_t)ctx->num_sms * 12 / gy)));
-    bitslice_kernel<<<dim3((unsigned)gx, gy), 256, BS_SMEM_BYTES, stream>>>(d_l, n_leaves, row_begin, row_end, lw,
+                                                                  std::max<uint64_t>(1, (uint64_t)ctx->num_sms * 8 / gy)));
+    bitslice_kernel<<<dim3((unsigned)gx, gy), BS_THREADS, BS_SMEM_BYTES, stream>>>(d_l, n_leaves, row_begin, row_end, lw,
                                                                              msbt_sliced_row_words(n_leaves), d_sliced);
     LAUNCH_CHECK(ctx);
     return MSBT_OK;
@@ -2406,9 +2479,14 @@ extern "C" int msbt_query_batch_sliced(msbt_ctx *ctx, const uint32_t *d_sliced, 
     const uint32_t gy = (ls + 32 * W - 1) / (32 * W);
     if (gy > 65535) return fail(ctx, MSBT_EINVAL, "query_batch_sliced: too many leaves");
     const dim3 grid(gx, gy, n_queries);
-    if (W == 4) query_sliced_kernel<4><<<grid, QS_WARPS * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_off, d_hits);
-    else if (W == 2) query_sliced_kernel<2><<<grid, QS_WARPS * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_off, d_hits);
-    else query_sliced_kernel<1><<<grid, QS_WARPS * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_off, d_hits);
+    int G = 2;  // groups of 7 row reads in flight per lane (W = 1 only; 1,024 leaves: 46.5 % -> 47.6 % of the HBM peak)
+    if (const char *e = getenv("MSBT_QS_G")) { const int g = atoi(e); if (g == 1 || g == 2) G = g; }  // tuning aid
+#define MSBT_QS_LAUNCH(WW, GG) query_sliced_kernel<WW, GG><<<grid, QS_WARPS * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_off, d_hits)
+    if (W == 4) MSBT_QS_LAUNCH(4, 1);
+    else if (W == 2) MSBT_QS_LAUNCH(2, 1);
+    else if (G == 2) MSBT_QS_LAUNCH(1, 2);
+    else MSBT_QS_LAUNCH(1, 1);
+#undef MSBT_QS_LAUNCH
     LAUNCH_CHECK(ctx);
     return MSBT_OK;
 }

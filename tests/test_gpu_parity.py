@@ -234,6 +234,30 @@ def test_committed_known_answers(ctx, variant):
         assert [int(x) for x in pos.cpu().numpy().view(np.uint32)] == kat["query_positions"], kat["name"]
 
 
+@pytest.mark.parametrize("n_leaves,num_bits,row_begin,row_end", [
+    (45, 1 << 16, 0, 1 << 16),                 # one partial column group, whole 1,024-row tiles
+    (600, 70000, 0, 70000),                    # two column groups (512 + 88 leaves), ragged last tile and last row word
+    (1100, 1 << 17, 32 * 5, 32 * 5 + 40001),   # first word not 16-byte aligned: the general load path
+    (513, 1 << 17, 4096, 4096 + 3000),         # aligned sub-range, 1 leaf in the last column group
+    (33, 4000, 128, 3999),                     # smaller than one tile
+])
+def test_bitslice_is_the_transpose(ctx, n_leaves, num_bits, row_begin, row_end):
+    """msbt_bitslice_build against a numpy transposition of the same leaves (row p, bit l = bit p of leaf l)."""
+    from metasbt_b200 import ops
+    rng = np.random.default_rng(n_leaves)
+    w = ops.filter_stride_words(num_bits)   # rows 16-byte aligned, as the C-ABI demands
+    host = rng.integers(-(1 << 63), (1 << 63) - 1, size=(n_leaves, w), dtype=np.int64)
+    dev = torch.from_numpy(host).to(ctx.device)
+    got = ctx.bitslice([dev[i] for i in range(n_leaves)], row_begin, row_end).cpu().numpy().view(np.uint32)
+    lw = (n_leaves + 31) // 32
+    assert got.shape == (row_end - row_begin, ctx.sliced_row_words(n_leaves))
+    bits = np.unpackbits(host.view(np.uint8), axis=1, bitorder="little")[:, row_begin:row_end]   # [leaf, row]
+    cols = np.zeros((row_end - row_begin, lw * 32), dtype=np.uint8)
+    cols[:, :n_leaves] = bits.T
+    want = np.packbits(cols, axis=1, bitorder="little").view(np.uint32)
+    assert np.array_equal(got[:, :lw], want)
+
+
 def test_query_sliced_many_leaves_and_chunks(ctx, oracle):
     """Bit-sliced probe with > 1024 leaves (several column groups), queries long enough for several warp sub-chunks
     and CTAs, an empty query, and a split into three bit-range shards that must add up."""
