@@ -1700,6 +1700,195 @@ bf_allpairs_kernel(const uint64_t *const *__restrict__ filters, uint32_t n, uint
         }
 }
 
+// All pairs, carry-save version (the default).  POPC runs at 16 lanes/clk/SM, and the kernel above spends one POPC per
+// 32 pair-bits.  Here a CTA stages one 1 KiB run of up to 2 x 16 filters in shared memory (every filter of the two
+// blocks is read once per block pair) and a LANE owns a 2 x 2 BLOCK OF PAIRS (filters 2di, 2di+1 against 2dj, 2dj+1):
+// per 4 words it reads four 16-byte operands from shared memory, ANDs them and feeds four carry-save accumulators
+// (see apc_step for the depth of the tree).  The 2 x 2
+// blocking halves the shared-memory bytes per pair-word (a warp-wide 16-byte load takes four data cycles whatever it
+// broadcasts), which is what bounds a one-pair-per-lane version (measured: 4.9 ms for 64 filters of 2^28 bits against
+// 5.3 ms for the POPC kernel).  When a block pair has fewer than 32 lane blocks (a 10-genome species has 15), the spare
+// lanes take other word ranges of the tile, so the warp stays full.
+constexpr int APC_B = 16;                    // filters per block (8 duos)
+constexpr int APC_TW = 256;                  // u32 words of every filter per tile (1 KiB)
+constexpr int APC_THREADS = 256;
+constexpr int APC_WARPS = APC_THREADS / 32;
+constexpr size_t APC_SMEM_BYTES = (size_t)2 * 2 * APC_B * (APC_TW + 4) * 4;  // two tile buffers; rows are 16-byte aligned and 4 banks apart
+
+__device__ __forceinline__ void csa32(uint32_t &hi, uint32_t &lo, uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t s_, c_;  // the outputs may alias the inputs
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s_) : "r"(a), "r"(b), "r"(c));  // a ^ b ^ c
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(c_) : "r"(a), "r"(b), "r"(c));  // majority
+    lo = s_;
+    hi = c_;
+}
+
+struct ApcPair {
+    uint32_t ones, twos_count;
+};
+
+// 4 words of one pair.  The tree is deliberately only one level deep: LOP3/AND issue at 64 lanes/clk/SM (the ALU pipe)
+// and POPC at 16, so a word costs max(0.5 * ALU ops, 2 * POPCs) cycles per warp -- 2.0 with a POPC per word, 1.44 with
+// a full 16-word Harley-Seal tree (2.9 ALU ops per word; measured: ALU pipe 86 % busy, 4.6 ms for 64 filters of 2^28
+// bits), and 1.0 on BOTH pipes with one carry-save step per two words (2 ALU ops and half a POPC per word).
+__device__ __forceinline__ void apc_step(ApcPair &s, const uint4 &a, const uint4 &b) {
+    uint32_t t;
+    csa32(t, s.ones, s.ones, a.x & b.x, a.y & b.y);
+    s.twos_count += __popc(t);
+    csa32(t, s.ones, s.ones, a.z & b.z, a.w & b.w);
+    s.twos_count += __popc(t);
+}
+
+// Row of filter f of a block of nf filters inside the tile: first members of the duos in rows 0 .., second members
+// behind them.  Rows are 4 banks apart, so the eight lanes of a quarter warp, which read the same member of eight
+// different duos, hit 8 x 4 distinct banks.
+__device__ __forceinline__ uint32_t apc_row(uint32_t f, uint32_t nf) { return (f & 1) * ((nf + 1) / 2) + (f >> 1); }
+
+__device__ __forceinline__ void apc_step4(ApcPair (&st)[4], const uint32_t *a0, const uint32_t *a1, const uint32_t *b0, const uint32_t *b1) {
+    const uint4 va0 = *(const uint4 *)a0, va1 = *(const uint4 *)a1, vb0 = *(const uint4 *)b0, vb1 = *(const uint4 *)b1;
+    apc_step(st[0], va0, vb0);
+    apc_step(st[1], va0, vb1);
+    apc_step(st[2], va1, vb0);
+    apc_step(st[3], va1, vb1);
+}
+
+__global__ void __launch_bounds__(APC_THREADS, 3)
+bf_allpairs_csa_kernel(const uint64_t *const *__restrict__ filters, uint32_t n, uint64_t words,
+                       unsigned long long *__restrict__ out) {
+    extern __shared__ __align__(16) uint32_t apc_tile[];            // rows of tw + 4 words: I block, then J block
+    __shared__ const uint64_t *sm_ptr[2 * APC_B];
+    __shared__ uint8_t sm_lb[64];                                   // lane block -> (di << 4) | dj
+    __shared__ unsigned long long sm_cnt[64 * 4];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // block pair (I <= J) from the linear index
+    const uint32_t nb = (n + APC_B - 1) / APC_B;
+    uint32_t I = 0, t = blockIdx.y;
+    while (t >= nb - I) { t -= nb - I; I++; }
+    const uint32_t J = I + t;
+    const bool diag = I == J;
+    const uint32_t ni = min((uint32_t)APC_B, n - I * APC_B), nj = min((uint32_t)APC_B, n - J * APC_B);
+    const uint32_t di_n = (ni + 1) / 2, dj_n = (nj + 1) / 2;
+    const uint32_t LB = diag ? di_n * (di_n + 1) / 2 : di_n * dj_n;  // lane blocks: 1 .. 64
+    // words of every filter per tile: the tile buffer holds 32 rows of 1 KiB; with fewer filters the rows get longer
+    // (10 filters: 2 KiB each), so that a CTA keeps the same number of bytes in flight per load phase
+    const uint32_t nslices = diag ? ni : ni + nj;
+    const uint32_t tw = nslices <= 8 ? 4 * APC_TW : nslices <= 16 ? 2 * APC_TW : APC_TW, stride = tw + 4, tv = tw / 4;
+    const uint32_t tsh = 31 - __clz(tv);  // tv is a power of two
+    // lanes: LB >= 32 -> R rounds of 32 lane blocks; LB < 32 -> one round, `sub` word ranges side by side in a warp
+    const uint32_t R = (LB + 31) / 32;
+    uint32_t sub = 1;
+    while (2 * sub * LB <= 32 && 2 * sub * 16 <= tw) sub <<= 1;
+    // work items (one per warp): R rounds x S spans of the tile; a lane's word range = span / sub words, >= 16
+    uint32_t S = 1;
+    while (R * S * 2 <= APC_WARPS && S * sub * 2 * 16 <= tw) S <<= 1;
+    const uint32_t lane_words = tw / (S * sub);
+    if (threadIdx.x < 2 * APC_B) {
+        const uint32_t sl = threadIdx.x;
+        const uint64_t *p = nullptr;
+        if (sl < ni) p = filters[I * APC_B + sl];
+        else if (!diag && sl < ni + nj) p = filters[J * APC_B + sl - ni];
+        sm_ptr[sl] = p;
+    }
+    if (threadIdx.x < 64) {
+        uint32_t code = 0;
+        const uint32_t p = threadIdx.x;
+        if (p < LB) {
+            if (diag) {  // row-major upper triangle of duos, with the diagonal
+                uint32_t i = 0, r = p;
+                while (r >= di_n - i) { r -= di_n - i; i++; }
+                code = (i << 4) | (i + r);
+            } else code = ((p / dj_n) << 4) | (p % dj_n);
+        }
+        sm_lb[p] = (uint8_t)code;
+    }
+    sm_cnt[threadIdx.x] = 0;  // 256 threads, 256 counters
+    __syncthreads();
+    // this lane's 2 x 2 block and word range
+    const bool warp_act = warp < R * S;
+    const uint32_t r = warp_act ? warp % R : 0, sp = warp_act ? warp / R : 0;
+    const uint32_t lb = sub > 1 ? lane % LB : r * 32 + lane, g = sub > 1 ? lane / LB : 0;
+    const bool lane_act = warp_act && lb < LB && g < sub;
+    const uint32_t code = lane_act ? sm_lb[lb] : 0;
+    const uint32_t di = code >> 4, dj = code & 15;
+    const uint32_t woff = lane_act ? (sp * sub + g) * lane_words : 0;
+    // rows: the I block's filters first (duo members interleaved by apc_row), then the J block's
+    const uint32_t jbase = diag ? 0 : ni;
+    const uint32_t *a0 = apc_tile + apc_row(min(2 * di, ni - 1), ni) * stride + woff;
+    const uint32_t *a1 = apc_tile + apc_row(min(2 * di + 1, ni - 1), ni) * stride + woff;
+    const uint32_t *b0 = apc_tile + (jbase + apc_row(min(2 * dj, nj - 1), nj)) * stride + woff;
+    const uint32_t *b1 = apc_tile + (jbase + apc_row(min(2 * dj + 1, nj - 1), nj)) * stride + woff;
+    ApcPair st[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) st[k].ones = st[k].twos_count = 0;
+    const uint64_t vec_full = words >> 1;                           // whole uint4 of every filter
+    const uint64_t n_vec = (words + 1) >> 1;
+    const uint64_t n_tiles = (n_vec + tv - 1) / tv;
+    constexpr int LD_PASSES = 2 * APC_B * (APC_TW / 4) / APC_THREADS;  // 8
+    constexpr uint32_t BUF_WORDS = 2 * APC_B * (APC_TW + 4);
+    // two tile buffers: the 16-byte cp.async copies of the next tile are in flight while this one is consumed
+    auto issue_tile = [&](uint64_t tile, uint32_t buf) {
+        uint32_t *base = apc_tile + buf * BUF_WORDS;
+#pragma unroll
+        for (int k = 0; k < LD_PASSES; k++) {
+            const uint32_t idx = threadIdx.x + k * APC_THREADS, sl = idx >> tsh;
+            if (sl < nslices) {
+                const uint64_t gv = tile * tv + (idx & (tv - 1));
+                const uint64_t *fp = sm_ptr[sl];
+                const uint32_t row = sl < ni ? apc_row(sl, ni) : ni + apc_row(sl - ni, nj);
+                uint32_t *dst = base + row * stride + 4 * (idx & (tv - 1));
+                if (gv < vec_full) {
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+                                 "l"((const uint4 *)fp + gv) : "memory");
+                } else {  // past the last whole vector: the odd last word, or zeros
+                    uint4 z = make_uint4(0, 0, 0, 0);
+                    if (gv < n_vec) { const uint64_t w = fp[words - 1]; z.x = (uint32_t)w; z.y = (uint32_t)(w >> 32); }
+                    *(uint4 *)dst = z;
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t buf = 0;
+    if (blockIdx.x < n_tiles) issue_tile(blockIdx.x, 0);
+    for (uint64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t next = tile + gridDim.x;
+        if (next < n_tiles) {
+            issue_tile(next, buf ^ 1);
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+        } else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();  // this tile has landed for every thread
+        if (warp_act) {
+            const uint32_t bo = buf * BUF_WORDS;
+#pragma unroll 4
+            for (uint32_t w = 0; w < lane_words; w += 4) apc_step4(st, a0 + bo + w, a1 + bo + w, b0 + bo + w, b1 + bo + w);
+        }
+        __syncthreads();  // consumed: the next iteration refills this buffer
+        buf ^= 1;
+    }
+    // fold the carry-save planes; the word ranges of a pair meet in shared memory; one global atomic per pair and CTA
+    if (lane_act) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const unsigned long long c = 2ull * st[k].twos_count + __popc(st[k].ones);
+            if (c) atomicAdd(&sm_cnt[lb * 4 + k], c);
+        }
+    }
+    __syncthreads();
+    {
+        const uint32_t p = threadIdx.x >> 2, k = threadIdx.x & 3;   // 64 lane blocks x 4 pairs = 256 threads
+        const unsigned long long c = sm_cnt[threadIdx.x];
+        if (p < LB && c) {
+            const uint32_t cd = sm_lb[p];
+            const uint32_t li = 2 * (cd >> 4) + (k >> 1), lj = 2 * (cd & 15) + (k & 1);
+            const uint32_t fi = I * APC_B + li, fj = J * APC_B + lj;
+            if (li < ni && lj < nj && fi <= fj) {
+                atomicAdd(out + (uint64_t)fi * n + fj, c);
+                if (fi != fj) atomicAdd(out + (uint64_t)fj * n + fi, c);
+            }
+        }
+    }
+}
+
 // Upload a host array of n device pointers into scratch; returns the device copy.
 static int upload_ptrs(msbt_ctx *ctx, const uint64_t *const *h_ptrs, uint32_t n, cudaStream_t stream,
                        const uint64_t *const **d_out) {
@@ -1815,17 +2004,33 @@ extern "C" int msbt_bf_and_popcount_allpairs(msbt_ctx *ctx, const uint64_t *cons
     if (words == 0 || !d_intersect) return fail(ctx, MSBT_EINVAL, "bf_and_popcount_allpairs: null/empty input");
     int rc = check_ptrs(ctx, h_filters, n);
     if (rc) return rc;
-    const uint32_t tiles = (n + AP_T - 1) / AP_T;
-    if (tiles > 65535) return fail(ctx, MSBT_EINVAL, "allpairs: n=%u too large for one call", n);
     CU_TRY(ctx, cudaSetDevice(ctx->device));
+    int variant = 0;  // 0 = carry-save kernel (default), 1 = the plain POPC kernel (kept as the cross-check)
+    if (const char *e = getenv("MSBT_ALLPAIRS")) variant = atoi(e);
     const uint64_t *const *d_f;
+    if (variant == 1) {
+        const uint32_t tiles = (n + AP_T - 1) / AP_T;
+        if (tiles > 65535) return fail(ctx, MSBT_EINVAL, "allpairs: n=%u too large for one call", n);
+        rc = upload_ptrs(ctx, h_filters, n, stream, &d_f);
+        if (rc) return rc;
+        CU_TRY(ctx, cudaMemsetAsync(d_intersect, 0, (size_t)n * n * 8, stream));
+        const uint64_t vec = std::max<uint64_t>(words >> 1, 1);
+        const uint64_t pair_tiles = (uint64_t)tiles * (tiles + 1) / 2;
+        uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((vec + 255) / 256, std::max<uint64_t>(1, (uint64_t)ctx->num_sms * 8 / pair_tiles)));
+        bf_allpairs_kernel<<<dim3((unsigned)gx, tiles, tiles), 256, 0, stream>>>(d_f, n, words, (unsigned long long *)d_intersect);
+        LAUNCH_CHECK(ctx);
+        return MSBT_OK;
+    }
+    const uint64_t nb = (n + APC_B - 1) / APC_B, block_pairs = nb * (nb + 1) / 2;
+    if (block_pairs > 65535) return fail(ctx, MSBT_EINVAL, "allpairs: n=%u too large for one call", n);
     rc = upload_ptrs(ctx, h_filters, n, stream, &d_f);
     if (rc) return rc;
     CU_TRY(ctx, cudaMemsetAsync(d_intersect, 0, (size_t)n * n * 8, stream));
-    const uint64_t vec = std::max<uint64_t>(words >> 1, 1);
-    const uint64_t pair_tiles = (uint64_t)tiles * (tiles + 1) / 2;
-    uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((vec + 255) / 256, std::max<uint64_t>(1, (uint64_t)ctx->num_sms * 8 / pair_tiles)));
-    bf_allpairs_kernel<<<dim3((unsigned)gx, tiles, tiles), 256, 0, stream>>>(d_f, n, words, (unsigned long long *)d_intersect);
+    const uint64_t n_tiles = (((words + 1) >> 1) + APC_TW / 4 - 1) / (APC_TW / 4);  // upper bound (small n: longer tiles)
+    const uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, std::max<uint64_t>(1, (uint64_t)ctx->num_sms * 6 / block_pairs)));
+    CU_TRY(ctx, cudaFuncSetAttribute(bf_allpairs_csa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)APC_SMEM_BYTES));
+    bf_allpairs_csa_kernel<<<dim3((unsigned)gx, (unsigned)block_pairs), APC_THREADS, APC_SMEM_BYTES, stream>>>(
+        d_f, n, words, (unsigned long long *)d_intersect);
     LAUNCH_CHECK(ctx);
     return MSBT_OK;
 }

@@ -158,6 +158,31 @@ def test_filter_algebra(ctx, oracle, num_bits):
             assert int(ap[i, j]) == oracle.bf_and_popcount(hrows[i], hrows[j])
 
 
+@pytest.mark.parametrize("n,num_bits", [(1, 4096), (2, 64), (3, 100000), (10, (1 << 19) + 64), (16, 50000), (17, 8192 * 3 + 64),
+                                        (33, 1 << 16), (50, 12345)])
+def test_allpairs_block_shapes(ctx, oracle, n, num_bits, monkeypatch):
+    """K3 all pairs, carry-save kernel: one block, a full block, blocks with ragged ends, several tile pairs; odd word
+    counts; dense random bits (every carry-save plane in use).  Checked against the oracle's AND-popcount and against the
+    plain POPC kernel (MSBT_ALLPAIRS=1)."""
+    from metasbt_b200 import ops
+    rng = np.random.default_rng(n * 1000 + num_bits % 997)
+    w, stride = ops.filter_words(num_bits), ops.filter_stride_words(num_bits)
+    host = rng.integers(-(1 << 63), (1 << 63) - 1, size=(n, stride), dtype=np.int64)
+    host[:, w:] = 0
+    if n > 2:
+        host[2] = -1   # all ones: popcount = 64 * words, the largest count a pair can reach
+        host[2, w:] = 0
+    dev = torch.from_numpy(host).to(ctx.device)
+    rows = [dev[i] for i in range(n)]
+    bits = np.unpackbits(host[:, :w].copy().view(np.uint8), axis=1).astype(np.int64)
+    want = bits @ bits.T
+    got = ctx.bf_allpairs(rows, num_bits).cpu().numpy()
+    assert np.array_equal(got, want)
+    assert int(got[0, n - 1]) == oracle.bf_and_popcount(host[0, :w].view(np.uint64), host[n - 1, :w].view(np.uint64))
+    monkeypatch.setenv("MSBT_ALLPAIRS", "1")
+    assert np.array_equal(ctx.bf_allpairs(rows, num_bits).cpu().numpy(), want)
+
+
 def test_query_paths_agree_with_oracle(ctx, oracle):
     from metasbt_b200 import ops
     rng = random.Random(11)

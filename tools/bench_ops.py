@@ -110,6 +110,10 @@ def run(ctx, n_leaves=1024, filter_bits=1 << 28, n_mags=64, genome_bp=5_000_000,
     out["K3_allpairs_%d" % A] = entry(t, A * fbytes, pairs_per_s=A * (A - 1) / 2 / t,
                                       note="bytes = each filter read once (lower bound); the kernel re-reads tiles")
 
+    # ... and inside a 10-genome species (the shape Entry.get_boundaries sees most often)
+    t = _time(lambda: ctx.bf_allpairs(rows[:10], m))
+    out["K3_allpairs_10"] = entry(t, 10 * fbytes, pairs_per_s=45 / t, note="bytes = each filter read once")
+
     # K4: MAGs = 5 % mutated prefixes of leaves
     mw = []
     for q in range(n_mags):
