@@ -1,6 +1,7 @@
-"""CPU: pin the oracle (a) against MurmurHash3's published vectors, (b) C against its
+"""CPU: pin the oracle (a) against MurmurHash3's published vectors and Appleby's reference source, (b) C against its
 pure-Python twin, (c) against hand-derived k-mer facts.  PARITY UNPINNED beyond that: the
 reference holds no golden vector for this path."""
+import os
 import random
 
 import numpy as np
@@ -30,6 +31,50 @@ def test_murmur3_c_vs_python_all_lengths(oracle):
         data = bytes(rng.randrange(256) for _ in range(n))
         for seed in (0, 1, 0xDEADBEEF):
             assert oracle.murmur3_x64_128(data, seed) == oracle.py_murmur3_x64_128(data, seed)
+
+
+def _appleby_reference(tmp_path):
+    """Austin Appleby's public-domain MurmurHash3.cpp -- the smhasher file HowDeSBT itself vendors -- as shipped in the
+    source tree of scikit-learn in this image (third-party code, not part of /root/reference, compiled where it lies)."""
+    import ctypes
+    import shutil
+    import subprocess
+    try:
+        import sklearn
+    except Exception:
+        pytest.skip("scikit-learn is not installed")
+    src = os.path.join(os.path.dirname(sklearn.__file__), "utils", "src", "MurmurHash3.cpp")
+    if not os.path.exists(src) or shutil.which("g++") is None:
+        pytest.skip("MurmurHash3.cpp or g++ not available")
+    so = str(tmp_path / "libappleby_murmur3.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-I", os.path.dirname(src), "-o", so, src])
+    lib = ctypes.CDLL(so)
+    fn = getattr(lib, "_Z19MurmurHash3_x64_128PKvijPv", None) or lib.MurmurHash3_x64_128
+    fn.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_uint32, ctypes.c_void_p]
+    fn.restype = None
+    return fn
+
+
+def test_murmur3_against_appleby_reference_source(oracle, tmp_path):
+    """The oracle's MurmurHash3_x64_128 (and through it msbt_spec.h's device copy, which the GPU parity tests tie to the
+    oracle) against the original reference implementation, on every key length the k-mer path can produce (k = 1..64 ->
+    1..16 bytes) and beyond, with several seeds; plus the exact byte strings the k-mer hash feeds it."""
+    import ctypes
+    import random
+    ref = _appleby_reference(tmp_path)
+    rng = random.Random(2024)
+    out = (ctypes.c_uint64 * 2)()
+    for n in list(range(0, 50)) + [63, 64, 65, 255]:
+        for seed in (0, 1, 0x9747B28C, 0xFFFFFFFF):
+            data = bytes(rng.getrandbits(8) for _ in range(n))
+            ref(data, n, seed, ctypes.addressof(out))
+            assert oracle.murmur3_x64_128(data, seed) == (int(out[0]), int(out[1])), (n, seed)
+    for k in (1, 4, 5, 21, 31, 32, 33, 51, 64):
+        kmer = "".join(rng.choice("ACGT") for _ in range(k))
+        canon = oracle.py_canonical(kmer)
+        data = canon.to_bytes(16, "little")[:(k + 3) // 4]
+        ref(data, len(data), 0, ctypes.addressof(out))
+        assert oracle.kmer_hash(kmer, 0) == int(out[0]), (k, kmer)
 
 
 def test_canonical_rule(oracle):
