@@ -2523,7 +2523,7 @@ struct QsVec<4> {
 };
 
 template <int W, int G, bool QFAST>
-__global__ void __launch_bounds__(QS_WARPS * 32)
+__global__ void __launch_bounds__(QS_WARPS * 32, (W == 2 && G == 2 ? 3 : 0))
 query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint32_t lw, uint32_t ls, uint64_t row_begin, uint64_t row_end,
                     const uint32_t *__restrict__ positions, const unsigned long long *__restrict__ q_off,
                     uint32_t *__restrict__ hits) {
@@ -2691,11 +2691,12 @@ extern "C" int msbt_query_batch_sliced(msbt_ctx *ctx, const uint32_t *d_sliced, 
     bool qfast = n_queries > 1 && gx <= 65535;
     if (const char *e = getenv("MSBT_QS_ORDER")) qfast = qfast && atoi(e) != 0;
     const dim3 grid = qfast ? dim3(n_queries, gy, gx) : dim3(gx, gy, n_queries);
-    int G = 2;  // groups of 7 row reads in flight per lane (W = 1 only; 1,024 leaves: 46.5 % -> 47.6 % of the HBM peak)
+    int G = W == 1 ? 2 : 1;  // groups of 7 row reads in flight per lane (W = 1, 1,024 leaves: 46.5 % -> 47.6 % of the HBM peak)
     if (const char *e = getenv("MSBT_QS_G")) { const int g = atoi(e); if (g == 1 || g == 2) G = g; }  // tuning aid
 #define MSBT_QS_LAUNCH2(WW, GG, QF) query_sliced_kernel<WW, GG, QF><<<grid, QS_WARPS * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_off, d_hits)
 #define MSBT_QS_LAUNCH(WW, GG) do { if (qfast) MSBT_QS_LAUNCH2(WW, GG, true); else MSBT_QS_LAUNCH2(WW, GG, false); } while (0)
     if (W == 4) MSBT_QS_LAUNCH(4, 1);
+    else if (W == 2 && G == 2) MSBT_QS_LAUNCH(2, 2);
     else if (W == 2) MSBT_QS_LAUNCH(2, 1);
     else if (G == 2) MSBT_QS_LAUNCH(1, 2);
     else MSBT_QS_LAUNCH(1, 1);
