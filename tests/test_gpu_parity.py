@@ -159,7 +159,7 @@ def test_filter_algebra(ctx, oracle, num_bits):
 
 
 @pytest.mark.parametrize("n,num_bits", [(1, 4096), (2, 64), (3, 100000), (10, (1 << 19) + 64), (16, 50000), (17, 8192 * 3 + 64),
-                                        (33, 1 << 16), (50, 12345)])
+                                        (33, 1 << 16), (50, 12345), (130, 5000)])
 def test_allpairs_block_shapes(ctx, oracle, n, num_bits, monkeypatch):
     """K3 all pairs, carry-save kernel: one block, a full block, blocks with ragged ends, several tile pairs; odd word
     counts; dense random bits (every carry-save plane in use).  Checked against the oracle's AND-popcount and against the
