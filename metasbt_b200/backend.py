@@ -140,6 +140,29 @@ class CudaBackend:
         batch = self.ctx.pack_fasta_device(read_files(fasta_paths), self.k)
         return self.ctx.build_filters(batch, self.k, self.num_bits, min_abund=min_abund)
 
+    def count_union_bits(self, fasta_paths: Sequence[str], kmer_size: int, num_bits: int, modulus: int) -> int:
+        """Popcount of ONE filter of `num_bits` bits that receives every k-mer of every file whose hash, taken modulo
+        `modulus`, is below `num_bits` (estimate.py: distinct k-mer counting for the filter size)."""
+        acc = None
+        groups, size = [[]], 0
+        for path in fasta_paths:  # about 1 GiB of FASTA text per pass
+            if groups[-1] and size + os.path.getsize(path) > (1 << 30):
+                groups.append([])
+                size = 0
+            groups[-1].append(path)
+            size += os.path.getsize(path)
+        for group in groups:
+            if not group:
+                continue
+            batch = self.ctx.pack_fasta_device(read_files(group), kmer_size)
+            for i in range(batch.n):
+                batch.descs[i].filter_index = 0  # all genomes of the batch into one shared filter
+            part = self.ctx.build_filters(batch, kmer_size, num_bits, min_abund=1, modulus=modulus)
+            acc = part[0] if acc is None else self.ctx.bf_or([acc, part[0]], num_bits)
+        if acc is None:
+            return 0
+        return int(self.ctx.bf_popcount([acc], num_bits)[0])
+
     # ------------------------------------------------------------------ bfoperate --or
     def union(self, src_paths: Sequence[str], out_path: str) -> None:
         rows = [self.filter(p) for p in src_paths]

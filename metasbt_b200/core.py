@@ -256,7 +256,11 @@ class Database(object):
             raise NotImplementedError("k-mer size estimation (kitsune) is outside the B200 hot path: pass kmer_size")
         self.metadata["kmer_size"] = kmer_size
         if not filter_size:
-            raise NotImplementedError("filter size estimation (ntcard) is outside the B200 hot path: pass filter_size")
+            # core.py:470-529 runs ntCard here; the distinct k-mer count comes from K1 + K3' instead (estimate.py)
+            from . import estimate
+            counter = self._backend if self._backend is not None else get_backend(kmer_size, estimate.EST_BITS)
+            f0, _ = estimate.estimate_distinct_kmers(sorted(filepaths), kmer_size, counter.count_union_bits)
+            filter_size = estimate.filter_size_from_f0(f0, filter_expand_by)
         self.metadata["filter_size"] = filter_size
         self._dump_metadata()
 

@@ -32,6 +32,13 @@ class OracleBackend:
         for fa, out in zip(fasta_paths, out_paths):
             self._store(out, O.makebf(open(fa, "rb").read(), self.k, self.num_bits, min_abund))
 
+    def count_union_bits(self, fasta_paths: Sequence[str], kmer_size: int, num_bits: int, modulus: int) -> int:
+        acc = None
+        for fa in fasta_paths:
+            w = O.makebf(open(fa, "rb").read(), kmer_size, num_bits, 1, modulus=modulus, rolling=kmer_size <= 32)
+            acc = w if acc is None else O.bf_or([acc, w])
+        return 0 if acc is None else O.bf_popcount(acc)
+
     def union(self, src_paths: Sequence[str], out_path: str) -> None:
         self._store(out_path, O.bf_or([self._load(p) for p in src_paths]))
 

@@ -113,8 +113,8 @@ def test_cli_rejects_what_is_out_of_scope(tmp_path):
     with pytest.raises(NotImplementedError):
         cli.MetaSBT(base + ["--dereplicate", "0.01"], backend=object())
     with pytest.raises(NotImplementedError):
-        cli.MetaSBT(["index", "--workdir", str(tmp_path / "w2"), "--database", "db", "--references", refs, "--kmer-size", "31"],
-                    backend=object())  # filter size estimation = ntcard
+        cli.MetaSBT(["index", "--workdir", str(tmp_path / "w2"), "--database", "db", "--references", refs,
+                     "--filter-size", "4096"], backend=object())  # k-mer size estimation = kitsune
     with pytest.raises(FileNotFoundError):
         cli.MetaSBT(["profile", "--workdir", str(tmp_path / "nope"), "--database", "db", "--genome", refs])
 
