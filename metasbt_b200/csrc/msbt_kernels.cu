@@ -1757,6 +1757,7 @@ bf_allpairs_csa_kernel(const uint64_t *const *__restrict__ filters, uint32_t n, 
                        unsigned long long *__restrict__ out) {
     extern __shared__ __align__(16) uint32_t apc_tile[];            // rows of tw + 4 words: I block, then J block
     __shared__ const uint64_t *sm_ptr[2 * APC_B];
+    __shared__ uint32_t sm_dst[2 * APC_B];
     __shared__ uint8_t sm_lb[64];                                   // lane block -> (di << 4) | dj
     __shared__ unsigned long long sm_cnt[64 * 4];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1788,6 +1789,8 @@ bf_allpairs_csa_kernel(const uint64_t *const *__restrict__ filters, uint32_t n, 
         if (sl < ni) p = filters[I * APC_B + sl];
         else if (!diag && sl < ni + nj) p = filters[J * APC_B + sl - ni];
         sm_ptr[sl] = p;
+        // byte offset of the slice's row: the I block's filters first (duo members interleaved by apc_row), then the J block's
+        sm_dst[sl] = (sl < ni ? apc_row(sl, ni) : ni + apc_row(min(sl - ni, nj - 1), nj)) * stride * 4;
     }
     if (threadIdx.x < 64) {
         uint32_t code = 0;
@@ -1826,24 +1829,29 @@ bf_allpairs_csa_kernel(const uint64_t *const *__restrict__ filters, uint32_t n, 
     constexpr int LD_PASSES = 2 * APC_B * (APC_TW / 4) / APC_THREADS;  // 8
     constexpr uint32_t BUF_WORDS = 2 * APC_B * (APC_TW + 4);
     // two tile buffers: the 16-byte cp.async copies of the next tile are in flight while this one is consumed
+    // Thread t copies 16-byte chunk c = t mod tv of slices s0, s0 + ds, ... (tv divides the CTA size, so c is the same
+    // in every pass): per pass one pointer and one row offset come from shared memory, and the end-of-filter test
+    // is one test per tile.
+    const uint32_t c = threadIdx.x & (tv - 1), s0 = threadIdx.x >> tsh, ds = APC_THREADS >> tsh;
+    const uint32_t tile_sa = (uint32_t)__cvta_generic_to_shared(apc_tile) + 16 * c;
     auto issue_tile = [&](uint64_t tile, uint32_t buf) {
-        uint32_t *base = apc_tile + buf * BUF_WORDS;
+        const uint64_t gv = tile * tv + c;
+        if (gv < vec_full) {
+            const uint32_t sa = tile_sa + buf * (BUF_WORDS * 4);
 #pragma unroll
-        for (int k = 0; k < LD_PASSES; k++) {
-            const uint32_t idx = threadIdx.x + k * APC_THREADS, sl = idx >> tsh;
-            if (sl < nslices) {
-                const uint64_t gv = tile * tv + (idx & (tv - 1));
-                const uint64_t *fp = sm_ptr[sl];
-                const uint32_t row = sl < ni ? apc_row(sl, ni) : ni + apc_row(sl - ni, nj);
-                uint32_t *dst = base + row * stride + 4 * (idx & (tv - 1));
-                if (gv < vec_full) {
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
-                                 "l"((const uint4 *)fp + gv) : "memory");
-                } else {  // past the last whole vector: the odd last word, or zeros
-                    uint4 z = make_uint4(0, 0, 0, 0);
-                    if (gv < n_vec) { const uint64_t w = fp[words - 1]; z.x = (uint32_t)w; z.y = (uint32_t)(w >> 32); }
-                    *(uint4 *)dst = z;
-                }
+            for (int k = 0; k < LD_PASSES; k++) {
+                const uint32_t sl = s0 + k * ds;
+                if (sl < nslices)
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa + sm_dst[sl]), "l"((const uint4 *)sm_ptr[sl] + gv) : "memory");
+            }
+        } else {  // past the last whole vector: the odd last word, or zeros
+#pragma unroll 1
+            for (int k = 0; k < LD_PASSES; k++) {
+                const uint32_t sl = s0 + k * ds;
+                if (sl >= nslices) break;
+                uint4 z = make_uint4(0, 0, 0, 0);
+                if (gv < n_vec) { const uint64_t w = sm_ptr[sl][words - 1]; z.x = (uint32_t)w; z.y = (uint32_t)(w >> 32); }
+                *(uint4 *)((char *)apc_tile + buf * (BUF_WORDS * 4) + sm_dst[sl] + 16 * c) = z;
             }
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
