@@ -183,6 +183,28 @@ def test_allpairs_block_shapes(ctx, oracle, n, num_bits, monkeypatch):
     assert np.array_equal(ctx.bf_allpairs(rows, num_bits).cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("n", [10, 20])
+def test_allpairs_many_tiles_per_cta(ctx, oracle, n, monkeypatch):
+    """Filters long enough (2^25 bits) that every CTA of the carry-save kernel walks several tiles, i.e. the double-buffered
+    cp.async pipeline reaches its steady state (n = 10: one block pair, 2 KiB runs; n = 20: three block pairs, 1 KiB
+    runs, 13 tiles per CTA).  Checked against the plain POPC kernel, the popcount kernel (diagonal) and the oracle."""
+    from metasbt_b200 import ops
+    num_bits = (1 << 25) + 192   # not a multiple of the tile length
+    w = ops.filter_words(num_bits)
+    g = torch.Generator(device=ctx.device).manual_seed(n)
+    dev = torch.randint(-(1 << 62), 1 << 62, (n, ops.filter_stride_words(num_bits)), dtype=torch.int64, device=ctx.device, generator=g)
+    dev &= torch.randint(-(1 << 62), 1 << 62, dev.shape, dtype=torch.int64, device=ctx.device, generator=g)
+    dev[:, w:] = 0
+    rows = [dev[i] for i in range(n)]
+    got = ctx.bf_allpairs(rows, num_bits).cpu().numpy()
+    monkeypatch.setenv("MSBT_ALLPAIRS", "1")
+    assert np.array_equal(ctx.bf_allpairs(rows, num_bits).cpu().numpy(), got)
+    assert np.array_equal(np.diag(got), ctx.bf_popcount(rows, num_bits).cpu().numpy())
+    h0, h1, hl = (dev[i, :w].cpu().numpy().view(np.uint64) for i in (0, 1, n - 1))
+    assert int(got[0, 1]) == oracle.bf_and_popcount(h0, h1) and int(got[1, n - 1]) == oracle.bf_and_popcount(h1, hl)
+    assert np.array_equal(got, got.T)
+
+
 def test_query_paths_agree_with_oracle(ctx, oracle):
     from metasbt_b200 import ops
     rng = random.Random(11)
