@@ -144,7 +144,7 @@ int msbt_query_batch(msbt_ctx *ctx, const uint64_t *const *h_leaves, uint32_t n_
 
 /* Bit-sliced leaf matrix for large leaf counts: row p holds bit p of every
  * leaf, msbt_sliced_row_words(n_leaves) u32 words per row (ceil(n_leaves/32) rounded up to a
- * multiple of 8 words, so that rows start on 32-byte sectors; the padding words are never read).
+ * multiple of 8 words, so that rows start on 32-byte sectors; the content of the padding words is ignored).
  * Rows [row_begin, row_end) only, so that a rank that owns a bit range builds and probes just
  * its shard: d_sliced holds (row_end - row_begin) * msbt_sliced_row_words(n_leaves) words. */
 uint32_t msbt_sliced_row_words(uint32_t n_leaves);
