@@ -3,7 +3,7 @@
 PARITY UNPINNED: the reference holds no golden vector for this path and `howdesbt` is not
 available, so these fixtures pin OUR oracle (itself pinned to MurmurHash3's published
 vectors and cross-checked C vs pure Python), not a real howdesbt run.  If `howdesbt` is ever on PATH,
-tools/pin_against_howdesbt.py re-checks them against the real binary.
+tests/pin_against_howdesbt.py re-checks them against the real binary.
 
     python tests/golden/make_golden.py
 """

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Multi-GPU parity check over NCCL, run under torchrun on N GPUs of one box:
 
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29512 tools/multi_gpu_check.py
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29512 tests/multi_gpu_check.py
 
 * K1: genomes sharded in contiguous blocks, no collective; every rank's filters equal the oracle's.
 * K2: per-rank partial unions merged by bit range (all_to_all + local OR + all_gather) == OR of everything.

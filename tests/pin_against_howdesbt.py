@@ -4,7 +4,7 @@ committed known-answer inputs and compare with the CPU oracle -- the moment this
 If it fails, the first differing item says which line of csrc/msbt_spec.h + oracle/msbt_oracle.c to re-pin
 (hash input bytes, length, digest half, canonical rule, .bf header fields).  Without the binary it reports that and exits 0.
 
-    python tools/pin_against_howdesbt.py [--keep DIR]
+    python tests/pin_against_howdesbt.py [--keep DIR]
 """
 import argparse
 import json
