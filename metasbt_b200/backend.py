@@ -198,6 +198,20 @@ class CudaBackend:
         rows = [self.filter(p) for p in paths]
         return self.ctx.bf_allpairs(rows, self.num_bits).cpu().numpy()
 
+    def dist_all_pairs_many(self, groups: Sequence[Sequence[str]]) -> List[np.ndarray]:
+        """dist_all_pairs for many clusters: every all-pairs launch is queued first, the matrices come back in ONE
+        device->host copy (one synchronisation for the whole batch instead of one per cluster)."""
+        mats = [self.ctx.bf_allpairs([self.filter(p) for p in g], self.num_bits) for g in groups]
+        if not mats:
+            return []
+        flat = torch.cat([m.reshape(-1) for m in mats]).cpu().numpy()
+        out, off = [], 0
+        for g in groups:
+            n = len(g)
+            out.append(flat[off: off + n * n].reshape(n, n))
+            off += n * n
+        return out
+
     # ------------------------------------------------------------------ query --distinctkmers
     def query_positions(self, fasta_path: str) -> torch.Tensor:
         """Distinct hash positions of ALL k-mers of the file (no min filter), ascending, on the device.

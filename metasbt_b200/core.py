@@ -374,6 +374,20 @@ class Database(object):
         # K3': one batched popcount for every cluster representative
         all_clusters = [self.clusters[level][name] for level in reversed(LEVELS) for name in self.clusters[level]]
         densities = Entry.get_density_many(all_clusters)
+        # K3: the all-pairs matrices of every species whose boundaries will be recomputed, in one batch (the reference
+        # runs a pool of `dist` jobs per cluster, core.py:4036-4081); get_boundaries picks them up by their path tuple
+        todo = []
+        for cluster_obj in all_clusters:
+            if cluster_obj.level != "species":
+                continue
+            children = sorted(cluster_obj.get_children())
+            refs = set(g for g in cluster_obj.children if self.genomes[g].is_known())
+            previous = self.report.get(cluster_obj.identifier)
+            unchanged = (previous is not None and not previous["references"].difference(refs)
+                         and not previous["mags"].difference(cluster_obj.children.difference(refs)))
+            if len(children) >= 3 and not unchanged:
+                todo.append(tuple(self.genomes[c].sketch_filepath for c in children))
+        self._allpairs_prefetch = dict(zip(todo, self.backend.dist_all_pairs_many(todo))) if todo else dict()
         header = ["cluster_id", "level", "density", "references_count", "mags_count", "references_list", "mags_list",
                   "centroid", "known", "taxonomy", "internal", "min_ani", "max_ani"]
         with open(path, "w+") as handle:
@@ -409,6 +423,7 @@ class Database(object):
                        ",".join(references), ",".join(mags), centroid, known, taxonomy, internal,
                        "" if min_ani is None else str(min_ani), "" if max_ani is None else str(max_ani)]
                 handle.write("{}\n".format("\t".join(row)))
+        self._allpairs_prefetch = dict()
 
     # ------------------------------------------------------------------ dist (core.py:1664-1833)
     @staticmethod
@@ -965,7 +980,9 @@ class Entry(object):
 
         # all pairs in ONE call: I[i][j] = popc(A_i & A_j), diagonal = popcounts, U = I_ii + I_jj - I_ij
         paths = [db.genomes[c].sketch_filepath for c in children]
-        inter = db.backend.dist_all_pairs(paths)
+        inter = getattr(db, "_allpairs_prefetch", {}).pop(tuple(paths), None)
+        if inter is None:
+            inter = db.backend.dist_all_pairs(paths)
         k = db.metadata["kmer_size"]
         pairwise: Dict[str, List[float]] = {c: [] for c in children}
         for i, source in enumerate(children):

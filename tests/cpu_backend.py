@@ -56,6 +56,9 @@ class OracleBackend:
         f = [self._load(p) for p in paths]
         return np.array([[O.bf_and_popcount(a, b) for b in f] for a in f], dtype=np.int64)
 
+    def dist_all_pairs_many(self, groups: Sequence[Sequence[str]]) -> List[np.ndarray]:
+        return [self.dist_all_pairs(g) for g in groups]
+
     def query_positions(self, fasta_path: str) -> np.ndarray:
         return O.positions_distinct(open(fasta_path, "rb").read(), self.k, self.num_bits)
 
