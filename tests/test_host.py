@@ -46,6 +46,17 @@ def test_library_exports_every_declared_symbol(built):
     assert built.lib().msbt_abi_version() == 1
 
 
+def test_header_is_plain_c():
+    """include/msbt.h is the boundary a cgo / JNI / ctypes binding reads: it must compile as C99 on its own."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["gcc", "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Wextra", "-Werror",
+                           os.path.join(root, "include", "msbt.h")])
+
+
 def test_no_torch_types_in_abi():
     header = open(os.path.join(ROOT, "include", "msbt.h")).read()
     assert "torch" not in header.lower().replace("no torch", "") and "at::" not in header and "std::" not in header
