@@ -49,7 +49,16 @@ def parse_args():
     ap.add_argument("--filter-bits", type=int, default=FILTER_BITS)
     ap.add_argument("--kmer", type=int, default=K)
     ap.add_argument("--variant", type=int, default=0, help="K1 kernel variant (0 auto, 1 direct, 2 tiled, 3 fused, 4 phased)")
-    ap.add_argument("--e2e-genomes", type=int, default=32, help="genomes per end-to-end step (host buffers)")
+    ap.add_argument("--e2e-genomes", type=int, default=0, help="genomes per end-to-end step (0 = the whole workload)")
+    ap.add_argument("--e2e-steps", type=int, default=2, help="timed end-to-end passes per transport")
+    ap.add_argument("--e2e-chunk", type=int, default=16, help="genomes per pipeline chunk (pinned slot = chunk x filter bytes)")
+    ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
+    ap.add_argument("--no-check", action="store_true", help="skip the oracle check of the first filter")
+    ap.add_argument("--no-query", action="store_true", help="skip the MAG queries/s section (configs[3])")
+    ap.add_argument("--query-leaves", type=int, default=10000)
+    ap.add_argument("--query-bits", type=int, default=1 << 25, help="filter size of the query section at every N (fits one GPU)")
+    ap.add_argument("--query-bits-full", type=int, default=1 << 28, help="configs[3]'s own filter size, run in addition at N >= 8")
+    ap.add_argument("--query-mags", type=int, default=256)
     ap.add_argument("--cpu-genomes", type=int, default=0, help="genomes in the CPU-baseline sample (0 = 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -234,10 +243,100 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def host_fasta(args, rank, N, G, device):
+    """FASTA text of this rank's N genomes in ONE pinned host buffer (what N FASTA files would hold), generated on the
+    device and copied out -- input preparation, not timed.  -> (pinned uint8 tensor, offsets)"""
+    import torch
+    from metasbt_b200 import synth
+    first = synth.fasta_text_device(synth.genome_codes(0x5EED0000 + rank * N, G, device), "g%x" % (0x5EED0000 + rank * N))
+    per = first.numel() + 8
+    text = torch.empty(per * N, dtype=torch.uint8, pin_memory=True)
+    offsets, cur = [0], 0
+    for g in range(N):
+        seed = 0x5EED0000 + rank * N + g
+        t = first if g == 0 else synth.fasta_text_device(synth.genome_codes(seed, G, device), "g%x" % seed)
+        text[cur: cur + t.numel()].copy_(t)
+        cur += t.numel()
+        offsets.append(cur)
+    torch.cuda.synchronize()
+    return text, offsets
+
+
+def run_e2e(args, ctx, rank, world, device, barrier, dist, check_filter0):
+    """The same metric end to end through the public API (pipeline.SketchPipeline, what `metasbt index` drives):
+    FASTA bytes in pinned host memory -> H2D -> device ingest -> K1 -> filters back in pinned host memory, EVERY genome of
+    the workload, every step.  Both output transports are measured (dense filters over PCIe; sparse position lists over
+    PCIe + host-side rebuild of the dense words); the faster one is `e2e`, the other `e2e_alt`."""
+    import numpy as np
+    import torch
+    from metasbt_b200 import pipeline
+    k, m, G, N = args.kmer, args.filter_bits, args.genome_bp, args.genomes
+    ne = min(args.e2e_genomes or N, N)
+    text, offsets = host_fasta(args, rank, ne, G, device)
+    steps = max(1, min(args.steps, args.e2e_steps))
+    out = {}
+    first_words = {}
+    for mode in ("dense", "sparse"):
+        pipe = pipeline.SketchPipeline(ctx, k, m, min_abund=1, chunk_genomes=args.e2e_chunk, slots=2, mode=mode, variant=args.variant)
+
+        def sink(first, words, mode=mode):
+            if first == 0 and mode not in first_words:
+                first_words[mode] = np.array(words[0], copy=True)
+        warm = min(ne, 2 * args.e2e_chunk)
+        pipe.run(text, offsets[: warm + 1], sink=sink)   # warm-up: allocates the pinned slots, first-touches them
+        pipe.h2d_bytes = pipe.d2h_bytes = 0
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            pipe.run(text, offsets, sink=sink)
+        barrier()
+        dt = time.perf_counter() - t0
+        te = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dt = float(te.item())
+        out[mode] = {"value": ne * G * world * steps / dt / 1e6, "unit": UNIT,
+                     "h2d_bytes_per_step": int(pipe.h2d_bytes // steps), "d2h_bytes_per_step": int(pipe.d2h_bytes // steps),
+                     "genomes_per_step": ne, "steps": steps, "s_per_step": dt / steps, "transport": mode,
+                     "pcie_gbs_per_gpu": (pipe.h2d_bytes + pipe.d2h_bytes) / dt / 1e9,
+                     "host_filter_bytes_per_step": int(ne * (m // 8))}
+        pipe.close()
+        del pipe
+        torch.cuda.empty_cache()
+    # both transports must deliver the very filter the device-resident run built (and the oracle's, checked by the caller)
+    for mode, w in first_words.items():
+        if not check_filter0(w):
+            raise SystemExit("bench.py: e2e (%s) delivered a filter that differs from the device-resident build" % mode)
+    # the ceiling this leg runs under: all ranks copying device -> pinned host at once, nothing else going on
+    buf_d = torch.empty(1 << 30, dtype=torch.uint8, device=device)
+    buf_h = torch.empty(1 << 30, dtype=torch.uint8, pin_memory=True)
+    buf_h.copy_(buf_d)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        buf_h.copy_(buf_d, non_blocking=True)
+    barrier()
+    dt = time.perf_counter() - t0
+    tc = torch.tensor([dt], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    d2h_gbs = 4 * (1 << 30) / float(tc.item()) / 1e9
+    best = max(out, key=lambda md: out[md]["value"])
+    e2e = out[best]
+    e2e["note"] = ("FASTA bytes pinned-host->device + device ingest + K1 + every filter back in pinned host memory each step; "
+                   "%s transport" % best)
+    e2e["d2h_ceiling_gbs_per_gpu_all_ranks_copying"] = d2h_gbs
+    e2e["dense_ceiling_mbp_s"] = d2h_gbs * 1e9 / (m // 8) * G * world / 1e6
+    alt = out["sparse" if best == "dense" else "dense"]
+    return e2e, alt
+
+
 def run_ours(args):
+    import contextlib
+    import numpy as np
     import torch
     import torch.distributed as dist
-    from metasbt_b200 import _lib, ops, synth
+    from metasbt_b200 import _lib, numa, ops, synth
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -246,6 +345,9 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # host threads and pinned buffers on the NUMA node of this rank's GPU (restored before the CPU-baseline leg)
+    affinity0 = os.sched_getaffinity(0)
+    numa_info = numa.bind_to_gpu_node(local_rank) if not args.no_numa else {"bound": False}
     if world > 1:
         # NCCL may print a version banner on stdout at its first collective: route fd 1 to stderr until then, so that
         # stdout carries the one JSON line only
@@ -301,48 +403,60 @@ def run_ours(args):
     total_bp = N * G * world * args.steps
     value = total_bp / (ms_max / 1e3) / 1e6
 
-    # a cheap result check inside the bench: density of the first filter is what the oracle says
-    pc = int(ctx.bf_popcount([filters[0]], m).cpu()[0])
+    # ---- result check inside the bench (a mismatch fails the run): this rank's first filter, bit for bit, against the
+    # oracle's makebf of the same genome's FASTA text -- on every rank, so the check also covers the sharded case
+    w = ops.filter_words(m)
+    got0 = filters[0, :w].cpu().numpy().view(np.uint64).copy()
+    check = {"filter0_popcount": int(ctx.bf_popcount([filters[0]], m).cpu()[0])}
+    if not args.no_check:
+        from oracle import oracle as O   # the checker, outside every timed region
+        O.build()
+        fa0 = _cpu_genome_fasta(0x5EED0000 + rank * N, G)
+        want0 = O.makebf(fa0, k, m, 1, rolling=(k <= 32))
+        ok = bool(np.array_equal(got0, want0)) and check["filter0_popcount"] == int(O.bf_popcount(want0))
+        flag = torch.tensor([0 if ok else 1], dtype=torch.int64, device=device)
+        if world > 1:
+            dist.all_reduce(flag)
+        if int(flag.item()):
+            raise SystemExit("bench.py: the first filter of %d rank(s) differs from the oracle's makebf -- results invalid" % int(flag.item()))
+        check["filter0_equals_oracle_makebf"] = True
+        check["filter0_word_checksum"] = int(np.bitwise_xor.reduce(want0))
+        check["ranks_checked"] = world
+
+    def check_filter0(words0) -> bool:
+        return bool(np.array_equal(np.asarray(words0).view(np.uint64)[:w], got0))
+
+    del filters, batch
+    torch.cuda.empty_cache()
 
     # ---- end to end through the public API with host buffers
-    e2e = None
+    e2e = e2e_alt = None
     if not args.no_e2e:
-        ne = min(args.e2e_genomes, N)
-        sub_words = [batch.d_words[i * (batch.d_words.numel() // N): (i + 1) * (batch.d_words.numel() // N)] for i in range(ne)]
-        sub = ops.GenomeBatch.from_device_words(sub_words, [G] * ne, device, keep_host_copy=True)
-        d_out = ctx.alloc_filters(ne, m)
-        h_out = torch.empty(d_out.shape, dtype=torch.int64, pin_memory=True)
-        e2e_steps = max(2, min(args.steps, 5))
+        e2e, e2e_alt = run_e2e(args, ctx, rank, world, device, barrier, dist, check_filter0)
+        if numa_info:
+            e2e["numa"] = numa_info
 
-        def e2e_step():
-            sub.to_device(non_blocking=True)                     # pinned host -> device
-            ctx.build_filters(sub, k, m, out=d_out, variant=args.variant)
-            h_out.copy_(d_out, non_blocking=True)                # every filter device -> host
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            e2e_step()
-        barrier()
-        dt = time.perf_counter() - t0
-        te = torch.tensor([dt], dtype=torch.float64, device=device)
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": ne * G * world * e2e_steps / float(te.item()) / 1e6, "unit": UNIT,
-               "h2d_bytes_per_step": int(sub.h2d_bytes), "d2h_bytes_per_step": int(h_out.numel() * 8),
-               "genomes_per_step": ne, "steps": e2e_steps,
-               "pcie_gbs": (int(sub.h2d_bytes) + int(h_out.numel() * 8)) * e2e_steps / float(te.item()) / 1e9,
-               "note": "packed genomes pinned-host->device + build + every filter device->pinned-host each step; "
-                       "PCIe-bound by the %d MiB/filter output (27x the input)" % (m // 8 // 2 ** 20)}
-        assert int(h_out[0, 0].item()) == int(filters[0, 0].item()) or rank != 0 or True
-        del d_out, h_out, sub
+    peak, peak_src = measured_peak_gbs()
+    # ---- BASELINE's second metric, MAG queries/s, at this N (configs[3])
+    mag_queries = None
+    if not args.no_query:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_query
+        with contextlib.redirect_stdout(sys.stderr):
+            mag_queries = bench_query.run(ctx, rank, world, leaves=args.query_leaves, filter_bits=args.query_bits, mags=args.query_mags,
+                                          steps=max(2, min(args.steps, 5)), warmup=1, peak_gbs=peak)
+            if world >= 8 and args.query_bits_full and args.query_bits_full != args.query_bits:
+                full = bench_query.run(ctx, rank, world, leaves=args.query_leaves, filter_bits=args.query_bits_full, mags=args.query_mags,
+                                       steps=2, warmup=1, peak_gbs=peak)
+                if rank == 0:
+                    mag_queries["at_config_filter_size"] = full
+        torch.cuda.empty_cache()
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    peak, peak_src = measured_peak_gbs()
     algo_bytes_genome = (G + 3) // 4 + m // 8
     per_genome_us = ms / args.steps / N * 1e3
     achieved = algo_bytes_genome / (per_genome_us * 1e-6) / 1e9
@@ -352,7 +466,7 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64", "data": "synthetic", "config": config_dict(args, world),
-        "e2e": e2e, "gpu_launches": int(launches),
+        "e2e": e2e, "e2e_alt": e2e_alt, "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": (traffic_genome * N if traffic_genome else None), "peak_source": peak_src,
                      "kernel": "kmer_bloom_fused_kernel (msbt_kmer_bloom_build, one launch per %d-genome batch; "
@@ -362,19 +476,26 @@ def run_ours(args):
                      "traffic_source": traffic_src},
         "clocks": clocks.summary(),
         "lib": os.path.relpath(_lib.loaded_path(), ROOT),
-        "check": {"filter0_popcount": pc},
+        "check": check,
+        "mag_queries": mag_queries,
     }
     if not args.no_secondary and world == 1:
-        # the other rows of SURVEY.md 8a (union, popcount distances, MAG queries/s) at 1,024 leaves, 2^28-bit filters
-        try:
-            del filters, batch
-            torch.cuda.empty_cache()
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import bench_ops
-            line["secondary"] = bench_ops.run(ctx, peak_gbs=peak)
-        except Exception as exc:  # the headline line must survive a failure here
-            line["secondary"] = {"error": repr(exc)}
+        # the other rows of SURVEY.md 8a (union, popcount distances, MAG queries/s) at 1,024 leaves, 2^28-bit filters,
+        # and `metasbt profile` through the Database API (profile_many)
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        with contextlib.redirect_stdout(sys.stderr):
+            try:
+                import bench_ops
+                line["secondary"] = bench_ops.run(ctx, peak_gbs=peak)
+            except Exception as exc:  # the headline line must survive a failure here
+                line["secondary"] = {"error": repr(exc)}
+            try:
+                import bench_profile
+                line["secondary"]["profile_many"] = bench_profile.run(ctx)
+            except Exception as exc:
+                line["secondary"]["profile_many"] = {"error": repr(exc)}
     if not args.no_cpu_baseline and world == 1:
+        os.sched_setaffinity(0, affinity0)  # the CPU arm gets every host core again
         cores = os.cpu_count() or 1
         n_cpu = args.cpu_genomes or 8 * cores
         v, dt = cpu_makebf_throughput(args, n_cpu, cores)

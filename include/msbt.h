@@ -115,6 +115,13 @@ int msbt_bf_and_popcount_1vN(msbt_ctx *ctx, const uint64_t *d_focus,
                              const uint64_t *const *h_targets, uint32_t n, uint64_t words,
                              uint64_t *d_intersect, uint64_t *d_union, void *stream);
 
+/* An arbitrary list of pairs in one launch: d_intersect[p] = popc(a_p & b_p), d_union[p] = popc(a_p | b_p).
+ * The batch form of Database.dist for `profile_many`: every MAG of a batch against its own few cluster
+ * representatives / species centroids (core.py:2106-2198 calls dist once per MAG and level).
+ * h_a / h_b are host arrays of n_pairs device pointers, consumed before the call returns. */
+int msbt_bf_and_popcount_pairs(msbt_ctx *ctx, const uint64_t *const *h_a, const uint64_t *const *h_b, uint32_t n_pairs,
+                               uint64_t words, uint64_t *d_intersect, uint64_t *d_union, void *stream);
+
 /* All pairs among n filters (Entry.get_boundaries, core.py:4036-4081, which calls dist once
  * per source).  d_intersect is a dense n*n row-major u64 matrix; the diagonal holds
  * popcount(filter i), so union(i,j) = I[i][i] + I[j][j] - I[i][j]. */
@@ -135,12 +142,25 @@ int msbt_bf_extract_positions(msbt_ctx *ctx, const uint64_t *d_filter, uint64_t 
 int msbt_bf_extract_positions_batch(msbt_ctx *ctx, const uint64_t *const *h_filters, uint32_t n, uint64_t words,
                                     uint32_t *d_positions, uint64_t cap, uint64_t *d_offsets, void *stream);
 
+/* HOST side of a sparse filter transfer (no GPU, synchronous): the ascending positions msbt_bf_extract_positions*
+ * produced, copied device -> host by the caller, -> the dense filter `words` (ceil(num_bits/64) u64, fully written).
+ * A 0.5 %-dense filter travels as 4 bytes per set bit instead of num_bits/8 bytes (makebf's output side, core.py:3929
+ * `--out=<bf>`).  MSBT_EINVAL if the positions are not ascending or reach num_bits. */
+int msbt_positions_expand(const uint32_t *positions, uint64_t n, uint64_t num_bits, uint64_t *words);
+
 /* Step 2: hits[q][l] = #{p in positions of query q : bit p of leaf filter l is set}.
  * d_positions holds all queries back to back; h_query_offsets (host, n_queries+1 entries)
  * delimits them.  d_hits is n_queries * n_leaves u32, row-major. */
 int msbt_query_batch(msbt_ctx *ctx, const uint64_t *const *h_leaves, uint32_t n_leaves,
                      const uint32_t *d_positions, const uint64_t *h_query_offsets,
                      uint32_t n_queries, uint32_t *d_hits, void *stream);
+
+/* The same with an explicit [begin, end) range of d_positions per query (h_query_ranges: 2 * n_queries entries,
+ * begin_0, end_0, begin_1, ...): the queries of a call may be any subset, in any order, of a packed batch of position
+ * lists -- `profile_many` probes every flat tree with just the MAGs that reached it, without copying their positions. */
+int msbt_query_batch_ranges(msbt_ctx *ctx, const uint64_t *const *h_leaves, uint32_t n_leaves,
+                            const uint32_t *d_positions, const uint64_t *h_query_ranges,
+                            uint32_t n_queries, uint32_t *d_hits, void *stream);
 
 /* Bit-sliced leaf matrix for large leaf counts: row p holds bit p of every
  * leaf, msbt_sliced_row_words(n_leaves) u32 words per row (ceil(n_leaves/32) rounded up to a
@@ -157,6 +177,12 @@ int msbt_query_batch_sliced(msbt_ctx *ctx, const uint32_t *d_sliced, uint32_t n_
                             uint64_t row_begin, uint64_t row_end,
                             const uint32_t *d_positions, const uint64_t *h_query_offsets,
                             uint32_t n_queries, uint32_t *d_hits, void *stream);
+
+/* msbt_query_batch_sliced with explicit per-query ranges (see msbt_query_batch_ranges). */
+int msbt_query_batch_sliced_ranges(msbt_ctx *ctx, const uint32_t *d_sliced, uint32_t n_leaves,
+                                   uint64_t row_begin, uint64_t row_end,
+                                   const uint32_t *d_positions, const uint64_t *h_query_ranges,
+                                   uint32_t n_queries, uint32_t *d_hits, void *stream);
 
 #ifdef __cplusplus
 }

@@ -13,7 +13,10 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_PKG)
 SO_PATH = os.environ.get("MSBT_LIB") or os.path.join(_PKG, "libmsbt.so")  # MSBT_LIB: kernel-tuning builds only
 SOURCES = [os.path.join(_PKG, "csrc", "msbt_kernels.cu")]
-HEADERS = [os.path.join(_PKG, "csrc", "msbt_spec.h"), os.path.join(_PKG, "csrc", "msbt_kmer.h"), os.path.join(_ROOT, "include", "msbt.h")]
+import glob as _glob
+# every header the translation unit includes (a stale libmsbt.so must never survive an edit of a kernel header)
+HEADERS = sorted(_glob.glob(os.path.join(_PKG, "csrc", "*.cuh")) + _glob.glob(os.path.join(_PKG, "csrc", "*.h"))) \
+    + [os.path.join(_ROOT, "include", "msbt.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -25,7 +28,8 @@ NVCC_FLAGS = [
 SYMBOLS = [
     "msbt_abi_version", "msbt_ctx_create", "msbt_ctx_destroy", "msbt_last_error", "msbt_sync",
     "msbt_launch_count", "msbt_fasta_pack", "msbt_fasta_pack_device", "msbt_kmer_bloom_build", "msbt_bf_or_reduce",
-    "msbt_bf_popcount", "msbt_bf_and_popcount_1vN", "msbt_bf_and_popcount_allpairs",
+    "msbt_bf_popcount", "msbt_bf_and_popcount_1vN", "msbt_bf_and_popcount_pairs", "msbt_bf_and_popcount_allpairs",
+    "msbt_query_batch_ranges", "msbt_query_batch_sliced_ranges", "msbt_positions_expand",
     "msbt_bf_extract_positions", "msbt_bf_extract_positions_batch", "msbt_query_batch", "msbt_bitslice_build", "msbt_query_batch_sliced", "msbt_sliced_row_words",
 ]
 
@@ -100,6 +104,8 @@ def lib() -> ctypes.CDLL:
     L.msbt_bf_popcount.restype = i32
     L.msbt_bf_and_popcount_1vN.argtypes = [vp, vp, P(vp), u32, u64, vp, vp, vp]
     L.msbt_bf_and_popcount_1vN.restype = i32
+    L.msbt_bf_and_popcount_pairs.argtypes = [vp, P(vp), P(vp), u32, u64, vp, vp, vp]
+    L.msbt_bf_and_popcount_pairs.restype = i32
     L.msbt_bf_and_popcount_allpairs.argtypes = [vp, P(vp), u32, u64, vp, vp]
     L.msbt_bf_and_popcount_allpairs.restype = i32
     L.msbt_bf_extract_positions.argtypes = [vp, vp, u64, vp, u64, vp, vp]
@@ -112,6 +118,12 @@ def lib() -> ctypes.CDLL:
     L.msbt_bitslice_build.restype = i32
     L.msbt_query_batch_sliced.argtypes = [vp, vp, u32, u64, u64, vp, P(u64), u32, vp, vp]
     L.msbt_query_batch_sliced.restype = i32
+    L.msbt_query_batch_ranges.argtypes = [vp, P(vp), u32, vp, P(u64), u32, vp, vp]
+    L.msbt_query_batch_ranges.restype = i32
+    L.msbt_query_batch_sliced_ranges.argtypes = [vp, vp, u32, u64, u64, vp, P(u64), u32, vp, vp]
+    L.msbt_query_batch_sliced_ranges.restype = i32
+    L.msbt_positions_expand.argtypes = [vp, u64, u64, vp]
+    L.msbt_positions_expand.restype = i32
     L.msbt_sliced_row_words.argtypes = [u32]
     L.msbt_sliced_row_words.restype = u32
     _LIB = L

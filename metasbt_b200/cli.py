@@ -144,11 +144,11 @@ class MetaSBT(object):
         args = parser.parse_known_args(argv)[0] if parse_known_args else parser.parse_args(argv)
         genomes = self._open(args)
         sketches = self.sketch(argv, parse_known_args=True)
-        out = []
-        for genome_filepath, sketch_filepath in zip(genomes, sketches):
-            out.append(Database._profile(self.database, genome_filepath, sketch_filepath, args.uncertainty,
-                                         args.pruning_threshold))
-        return out
+        # the reference fans `Database._profile` out over a process pool, one job per genome (metasbt.py:1124-1143);
+        # here all genomes descend the trees together (Database.profile_many)
+        tables = self.database.profile_many(genomes, sketches, uncertainty=args.uncertainty,
+                                            pruning_threshold=args.pruning_threshold)
+        return list(zip(genomes, tables))
 
 
     # ------------------------------------------------------------------ update (metasbt.py:1730-1920)

@@ -288,6 +288,10 @@ class Database(object):
             seen.add(filename)
             prepared.append((filepath, filename, Entry(self, filename, filename, "genome", taxonomy=taxonomy, known=reference), taxonomy))
         Entry.sketch_many([p[2] for p in prepared], [p[0] for p in prepared])
+        unknown = [p for p in prepared if not p[3]]
+        if unknown:
+            # MAGs with no species close enough (core.py:972-980): their profiles in one batch
+            self.profile_many([p[0] for p in unknown], [p[2].sketch_filepath for p in unknown])
 
         for filepath, filename, genome_obj, taxonomy in prepared:
             if not taxonomy:
@@ -451,16 +455,21 @@ class Database(object):
         return (genome_filepath, instance.profile(genome_filepath, sketch_filepath, uncertainty=uncertainty,
                                                   pruning_threshold=pruning_threshold))
 
-    def _query_tree(self, tree_filepath: str, query, threshold: float) -> "OrderedDict[str, Tuple[int, int]]":
-        """`howdesbt query --sort --distinctkmers --tree=<flat tree> --threshold=T` for one query:
-        {leaf name: (hits, total)} in output order (hits descending, ties in tree order; App. A6)."""
+    @staticmethod
+    def _tree_leaves(tree_filepath: str) -> List[str]:
+        """Leaf filter paths of a flat `index.detbrief.sbt` (core.py:3870-3875: root line, then one `*`-prefixed line per leaf)."""
         leaves = []
         with open(tree_filepath) as handle:
             for line in handle:
                 line = line.strip()
                 if line.startswith("*"):
                     leaves.append(line.lstrip("*"))
-        hits, total = self.backend.query_hits(query, leaves)
+        return leaves
+
+    @staticmethod
+    def _tree_matches(leaves: Sequence[str], hits: Sequence[int], total: int, threshold: float) -> "OrderedDict[str, Tuple[int, int]]":
+        """What `howdesbt query --sort --distinctkmers --threshold=T` prints for one query against one flat tree:
+        {leaf name: (hits, total)} in output order (hits descending, ties in tree order; App. A6)."""
         needed = math.ceil(threshold * total)
         order = sorted(range(len(leaves)), key=lambda i: -int(hits[i]))
         out: "OrderedDict[str, Tuple[int, int]]" = OrderedDict()
@@ -471,93 +480,186 @@ class Database(object):
 
     def profile(self, genome_filepath: str, sketch_filepath: str, uncertainty: float = 50.0,
                 pruning_threshold: float = 0.0) -> Dict[str, Dict[str, float]]:
+        """core.py:1870-2211 for one genome: a batch of one through profile_many."""
+        return self.profile_many([genome_filepath], [sketch_filepath], uncertainty=uncertainty,
+                                 pruning_threshold=pruning_threshold)[0]
+
+    def _load_profile_table(self, result_filepath: str) -> Optional[Dict[str, Dict[str, float]]]:
+        """Memoised table (core.py:1932-1960); a corrupted file is removed and recomputed."""
+        if not os.path.isfile(result_filepath):
+            return None
+        profiles: Dict[str, Dict[str, float]] = {level: OrderedDict() for level in LEVELS + ["genome"]}
+        try:
+            with open(result_filepath) as handle:
+                for line in handle:
+                    line = line.strip()
+                    if line and not line.startswith("#"):
+                        level, label, ani = line.split("\t")[:3]
+                        profiles[level][label] = float(ani)
+            return profiles
+        except Exception:
+            os.unlink(result_filepath)
+            return None
+
+    def profile_many(self, genome_filepaths: Sequence[str], sketch_filepaths: Sequence[str], uncertainty: float = 50.0,
+                     pruning_threshold: float = 0.0) -> List[Dict[str, Dict[str, float]]]:
+        """`profile` for a batch of genomes -- the process pool of metasbt.py:1124-1143 (one `_profile` job per genome, each
+        spawning >= 7 `howdesbt query` and as many `bfdistance` pairs, core.py:2039-2051, 2106-2198) as batch calls:
+
+        * ONE FASTA ingest + ONE K1 launch + one batched position extraction for all genomes of a batch
+          (backend.query_positions_many);
+        * the descent db -> kingdom -> ... -> species is level-synchronous: at every level each flat tree is probed ONCE with
+          all the genomes that reached it (backend.query_hits_many) and all hit matrices of the level come back in ONE
+          device->host copy (backend.fetch_hits) -- the descent only needs the hits;
+        * every ANI distance the tables report (Database.dist at core.py:2106, 2133, 2172) is deferred and computed by ONE
+          pair-list launch at the end (backend.dist_pairs).
+
+        Results, memoisation (tmp/profiles/<genome>.txt) and exceptions are those of the per-genome method."""
+        if len(genome_filepaths) != len(sketch_filepaths):
+            raise ValueError("One sketch file path per genome file path is required!")
         levels = ["db"] + LEVELS + ["genome"]
-        profiles: Dict[str, Dict[str, float]] = {level: OrderedDict() for level in levels[1:]}
-        genome_filename = os.path.splitext(os.path.basename(genome_filepath))[0]
         profiles_dir = os.path.join(self.tmp, "profiles")
         os.makedirs(profiles_dir, exist_ok=True)
-        result_filepath = os.path.join(profiles_dir, f"{genome_filename}.txt")
+        results: List[Optional[Dict[str, Dict[str, float]]]] = [None] * len(genome_filepaths)
+        result_paths: List[str] = []
+        todo: List[int] = []
+        for g, genome_filepath in enumerate(genome_filepaths):
+            genome_filename = os.path.splitext(os.path.basename(genome_filepath))[0]
+            result_paths.append(os.path.join(profiles_dir, f"{genome_filename}.txt"))
+            results[g] = self._load_profile_table(result_paths[g])
+            if results[g] is None:
+                if not os.path.isfile(sketch_filepaths[g]):
+                    raise FileNotFoundError(errno.ENOENT, os.strerror(errno.ENOENT), sketch_filepaths[g])
+                todo.append(g)
+        if not todo:
+            return results  # type: ignore[return-value]
 
-        if os.path.isfile(result_filepath):
-            # memoised table (core.py:1932-1960); a corrupted file is removed and recomputed
-            try:
-                with open(result_filepath) as handle:
-                    for line in handle:
-                        line = line.strip()
-                        if line and not line.startswith("#"):
-                            level, label, ani = line.split("\t")[:3]
-                            profiles[level][label] = float(ani)
-                return profiles
-            except Exception:
-                os.unlink(result_filepath)
-                profiles = {level: OrderedDict() for level in levels[1:]}
-
-        # The reference joins multi-record FASTA with "N" (core.py:1974-1996) because howdesbt treats records
-        # as separate queries; k-mers never span records or Ns, so the distinct-position set of the whole
-        # file is the same thing and is computed once for the whole descent.
-        query = self.backend.query_positions(genome_filepath)
+        backend = self.backend
         kmer_size = self.metadata["kmer_size"]
-        dists: Dict[str, float] = dict()
-        first_iter = True
-        clusters: List[str] = []
-        for pos, level in enumerate(levels):
-            if level == "genome":
-                break
-            next_level = levels[pos + 1]
-            if level == "db":
-                clusters = ["db"]
-            best_level_matches: "OrderedDict[str, float]" = OrderedDict()
-            for cluster in clusters:
-                cluster_id = "MSBT0" if level == "db" else self.clusters[level][cluster].identifier
+        # batches bounded by the memory their packed positions may take (a file of n bytes has fewer than n k-mers)
+        budget = max(int(getattr(backend, "position_bytes", 1 << 62)) // 4, 1)
+        batches: List[List[int]] = [[]]
+        size = 0
+        for g in todo:
+            nbytes = os.path.getsize(genome_filepaths[g])
+            if batches[-1] and size + nbytes > budget:
+                batches.append([])
+                size = 0
+            batches[-1].append(g)
+            size += nbytes
+
+        leaves_of: Dict[str, List[str]] = dict()
+
+        def tree_leaves(cluster_id: str) -> List[str]:
+            if cluster_id not in leaves_of:
                 tree_filepath = os.path.join(self.root, "clusters", self._get_cluster_batch(cluster_id), cluster_id,
                                              "tree", "index.detbrief.sbt")
                 if not os.path.isfile(tree_filepath):
                     raise FileNotFoundError(errno.ENOENT, os.strerror(errno.ENOENT), tree_filepath)
+                leaves_of[cluster_id] = self._tree_leaves(tree_filepath)
+            return leaves_of[cluster_id]
+
+        for members in batches:
+            # The reference joins multi-record FASTA with "N" (core.py:1974-1996) because howdesbt treats records as
+            # separate queries; k-mers never span records or Ns, so the distinct-position set of the whole file is the
+            # same thing and is computed once for the whole descent.
+            qb = backend.query_positions_many([genome_filepaths[g] for g in members])
+            totals = backend.query_totals(qb)
+            n = len(members)
+            reached: List[List[str]] = [["db"] for _ in range(n)]           # clusters each genome queries at this level
+            matched: List[Dict[str, "OrderedDict[str, float]"]] = [dict() for _ in range(n)]  # level -> best matches
+            for pos, level in enumerate(levels[:-1]):
+                # every tree of this level once, with all the genomes that reached it
+                by_tree: "OrderedDict[str, List[int]]" = OrderedDict()
+                for q in range(n):
+                    for cluster in reached[q]:
+                        cluster_id = "MSBT0" if level == "db" else self.clusters[level][cluster].identifier
+                        by_tree.setdefault(cluster_id, []).append(q)
+                tree_ids = list(by_tree.keys())
+                pending = [backend.query_hits_many(qb, by_tree[t], tree_leaves(t)) for t in tree_ids]
+                fetched = backend.fetch_hits(pending)  # the level's only synchronisation
+                hits_of: Dict[Tuple[str, int], Any] = dict()
+                for t, rows in zip(tree_ids, fetched):
+                    for r, q in enumerate(by_tree[t]):
+                        hits_of[(t, q)] = rows[r]
                 threshold = pruning_threshold if level == "kingdom" else 0.0
-                matches = self._query_tree(tree_filepath, query, threshold)
-                if not matches:
-                    continue
-                scores = OrderedDict((node, common / total) for node, (common, total) in matches.items())
-                best_match = sorted(scores.keys(), key=lambda m: scores[m])[-1]
-                best_score = scores[best_match]
-                score_threshold = float((best_score * uncertainty) / 100.0)
-                for node, score in scores.items():
-                    if score >= best_score - score_threshold:
-                        best_level_matches[node] = score
+                for q in range(n):
+                    best_level_matches: "OrderedDict[str, float]" = OrderedDict()
+                    for cluster in reached[q]:
+                        cluster_id = "MSBT0" if level == "db" else self.clusters[level][cluster].identifier
+                        matches = self._tree_matches(tree_leaves(cluster_id), hits_of[(cluster_id, q)], totals[q], threshold)
+                        if not matches:
+                            continue
+                        scores = OrderedDict((node, common / total) for node, (common, total) in matches.items())
+                        best_match = sorted(scores.keys(), key=lambda m: scores[m])[-1]
+                        best_score = scores[best_match]
+                        score_threshold = float((best_score * uncertainty) / 100.0)
+                        for node, score in scores.items():
+                            if score >= best_score - score_threshold:
+                                best_level_matches[node] = score
+                    matched[q][level] = best_level_matches
+                    reached[q] = list(best_level_matches.keys())
 
-            if level == "db":
-                names = list(best_level_matches.keys())
-                sketches = [self.clusters[next_level][n].sketch_filepath for n in names]
-                _, kingdom_dists = self.dist(sketch_filepath, sketches, kmer_size, tmp=self.tmp, resume=False)
-                for name, sk in zip(names, sketches):
-                    profiles[next_level][self.clusters[next_level][name].get_full_taxonomy()] = round(kingdom_dists[sk], 5)
-            elif level == "species":
-                top = sorted(best_level_matches.keys(), key=lambda m: best_level_matches[m])[-1]
-                top_sketch = self.genomes[top].sketch_filepath
-                _, d = self.dist(sketch_filepath, [top_sketch], kmer_size, tmp=self.tmp, resume=False)
-                best_obj = self.genomes[os.path.splitext(os.path.basename(top_sketch))[0]]
-                label = f"{best_obj.get_full_taxonomy()}|t__{best_obj.name}"
-                profiles[next_level][label] = round(d[best_obj.sketch_filepath], 5)
-            else:
-                for name in best_level_matches:
-                    obj = self.clusters[next_level][name]
-                    species_entries = [obj.name] if next_level == "species" else sorted(obj.get_children(up_to="species"))
-                    centroids = [self.report[self.clusters["species"][s].identifier]["centroid"] for s in species_entries]
-                    centroid_sketches = [self.genomes[c].sketch_filepath for c in centroids]
-                    if first_iter:
-                        _, found = self.dist(sketch_filepath, centroid_sketches, kmer_size, tmp=self.tmp, resume=False)
-                        dists.update(found)
-                    profiles[next_level][obj.get_full_taxonomy()] = round(statistics.mean(dists[s] for s in centroid_sketches), 5)
-                if first_iter:
-                    first_iter = False
-            clusters = list(best_level_matches.keys())
-
-        with open(result_filepath, "w+") as table:
-            table.write("# level\tclosest\tani\n")
-            for level in LEVELS + ["genome"]:
-                for match in profiles[level]:
-                    table.write(f"{level}\t{match}\t{profiles[level][match]}\n")
-        return profiles
+            # every distance the tables report, in one pair-list call (the descent above never needed them)
+            pairs: List[Tuple[str, str]] = []
+            plan: List[List[Tuple[str, Any]]] = [[] for _ in range(n)]  # per genome: (kind, payload) in table order
+            for q, g in enumerate(members):
+                sketch_filepath = sketch_filepaths[g]
+                wanted: "OrderedDict[str, None]" = OrderedDict()
+                first_iter = True
+                for pos, level in enumerate(levels[:-1]):
+                    next_level = levels[pos + 1]
+                    best_level_matches = matched[q][level]
+                    if level == "db":
+                        for name in best_level_matches:
+                            obj = self.clusters[next_level][name]
+                            wanted[obj.sketch_filepath] = None
+                            plan[q].append(("single", (next_level, obj.get_full_taxonomy(), obj.sketch_filepath)))
+                    elif level == "species":
+                        top = sorted(best_level_matches.keys(), key=lambda m: best_level_matches[m])[-1]
+                        best_obj = self.genomes[top]
+                        wanted[best_obj.sketch_filepath] = None
+                        label = f"{best_obj.get_full_taxonomy()}|t__{best_obj.name}"
+                        plan[q].append(("single", (next_level, label, best_obj.sketch_filepath)))
+                    else:
+                        for name in best_level_matches:
+                            obj = self.clusters[next_level][name]
+                            species_entries = [obj.name] if next_level == "species" else sorted(obj.get_children(up_to="species"))
+                            centroids = [self.report[self.clusters["species"][s].identifier]["centroid"] for s in species_entries]
+                            centroid_sketches = [self.genomes[c].sketch_filepath for c in centroids]
+                            if first_iter:
+                                # the reference computes centroid distances at the first cluster level only and looks the
+                                # lower levels up in the same dictionary (core.py:2160-2185)
+                                for sk in centroid_sketches:
+                                    wanted[sk] = None
+                            plan[q].append(("mean", (next_level, obj.get_full_taxonomy(), centroid_sketches)))
+                        first_iter = False
+                plan[q].insert(0, ("targets", list(wanted.keys())))
+                pairs.extend((sketch_filepath, target) for target in wanted)
+            counts = backend.dist_pairs(pairs)
+            cursor = 0
+            for q, g in enumerate(members):
+                targets = plan[q][0][1]
+                dists: Dict[str, float] = dict()
+                for target in targets:
+                    intersect, union = counts[cursor]
+                    cursor += 1
+                    dists[target] = ani_distance(intersect, union, kmer_size)
+                profiles: Dict[str, Dict[str, float]] = {level: OrderedDict() for level in levels[1:]}
+                for kind, payload in plan[q][1:]:
+                    if kind == "single":
+                        level, label, target = payload
+                        profiles[level][label] = round(dists[target], 5)
+                    else:
+                        level, label, centroid_sketches = payload
+                        profiles[level][label] = round(statistics.mean(dists[s] for s in centroid_sketches), 5)
+                with open(result_paths[g], "w+") as table:
+                    table.write("# level\tclosest\tani\n")
+                    for level in LEVELS + ["genome"]:
+                        for match in profiles[level]:
+                            table.write(f"{level}\t{match}\t{profiles[level][match]}\n")
+                results[g] = profiles
+        return results  # type: ignore[return-value]
 
     # ------------------------------------------------------------------ outside the hot path
     def _unsupported(self, *a, **k):
@@ -618,7 +720,9 @@ class Database(object):
             if filename not in self.genomes:
                 todo.append((Entry(self, filename, filename, "genome", taxonomy=None, known=False), filepath))
         if todo and self._validate_metadata(self.metadata):
-            Entry.sketch_many([t[0] for t in todo], [t[1] for t in todo])
+            sketches = Entry.sketch_many([t[0] for t in todo], [t[1] for t in todo])
+            if self.report:
+                self.profile_many([t[1] for t in todo], sketches)  # one batch; is_known() below reads the memoised tables
         return OrderedDict((filepath, self.is_known(filepath)) for filepath in filepaths)
 
     def _estimate_boundaries(self, taxonomy: str) -> Tuple[float, float]:

@@ -62,6 +62,27 @@ static int fail(msbt_ctx *ctx, int code, const char *fmt, ...) {
             return fail(ctx, MSBT_ECUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
     } while (0)
 
+// Every entry point runs on the context's device and puts the caller's current device back on return (a process that
+// drives several contexts, or whose torch current device is another GPU, keeps its own bookkeeping intact).
+struct DeviceGuard {
+    int prev = -1;
+    bool changed = false;
+    cudaError_t enter(int device) {
+        cudaError_t e = cudaGetDevice(&prev);
+        if (e != cudaSuccess) return e;
+        if (prev == device) return cudaSuccess;
+        e = cudaSetDevice(device);
+        changed = e == cudaSuccess;
+        return e;
+    }
+    ~DeviceGuard() {
+        if (changed) cudaSetDevice(prev);
+    }
+};
+#define CTX_DEVICE(ctx)      \
+    DeviceGuard dev_guard__; \
+    CU_TRY(ctx, dev_guard__.enter((ctx)->device))
+
 static int ensure_scratch(msbt_ctx *ctx, size_t bytes) {
     if (bytes <= ctx->scratch_bytes) return MSBT_OK;
     if (ctx->d_scratch) {
@@ -124,7 +145,8 @@ extern "C" int msbt_ctx_create(int device, msbt_ctx **out) {
     if (!ctx) return MSBT_ENOMEM;
     memset(ctx, 0, sizeof(*ctx));
     ctx->device = device;
-    cudaError_t e = cudaSetDevice(device);
+    DeviceGuard guard;
+    cudaError_t e = guard.enter(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->stage_free, cudaEventDisableTiming);
     if (e != cudaSuccess) {
@@ -139,7 +161,8 @@ extern "C" int msbt_ctx_create(int device, msbt_ctx **out) {
 
 extern "C" void msbt_ctx_destroy(msbt_ctx *ctx) {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    DeviceGuard guard;
+    guard.enter(ctx->device);
     cudaDeviceSynchronize();
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -1263,7 +1286,7 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
     if (!d_packed || !d_run_ends || !h_descs || !d_filters) return fail(ctx, MSBT_EINVAL, "null pointer argument");
     if (min_abund >= 2 && k > 32) return fail(ctx, MSBT_EINVAL, "min_abund >= 2 supports k <= 32 only (k=%u)", k);
     if (variant < 0 || variant > 4) return fail(ctx, MSBT_EINVAL, "unknown variant %d", variant);
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CTX_DEVICE(ctx);
 
     KmerSpec spec;
     spec.pos = msbt_make_pos_spec(modulus, num_bits, seed);
@@ -1453,7 +1476,7 @@ extern "C" int msbt_fasta_pack_device(msbt_ctx *ctx, const char *d_text, const u
     if (n_files == 0) return MSBT_OK;
     if (!h_offsets || !h_descs || !d_packed || !d_run_ends) return fail(ctx, MSBT_EINVAL, "fasta_pack_device: null argument");
     if (min_run > 64) return fail(ctx, MSBT_EINVAL, "fasta_pack_device: min_run > 64");
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CTX_DEVICE(ctx);
     std::vector<FpFile> files(n_files);
     uint64_t chunks = 0, words = 0, runs = 0;
     const uint64_t need = std::max<uint32_t>(min_run, 1);
@@ -1645,6 +1668,32 @@ bf_dist_1vN_kernel(const uint64_t *__restrict__ focus, const uint64_t *const *__
     }
 }
 
+// Arbitrary pair list: pair p = (a[p], b[p]); grid = (chunks, pairs).  The batched `dist` requests of profile_many (every MAG
+// against its own handful of cluster representatives / centroids) -- one launch for all of them.
+__global__ void __launch_bounds__(256)
+bf_dist_pairs_kernel(const uint64_t *const *__restrict__ as, const uint64_t *const *__restrict__ bs, uint64_t words,
+                     unsigned long long *__restrict__ out_and, unsigned long long *__restrict__ out_or) {
+    const uint64_t *__restrict__ a = as[blockIdx.y], *__restrict__ b = bs[blockIdx.y];
+    const uint64_t vec = words >> 1;
+    const uint4 *av = (const uint4 *)a, *bv = (const uint4 *)b;
+    uint64_t ca = 0, co = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < vec; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint4 x = ld_stream(av + i), y = ld_stream(bv + i);
+        ca += __popc(x.x & y.x) + __popc(x.y & y.y) + __popc(x.z & y.z) + __popc(x.w & y.w);
+        co += __popc(x.x | y.x) + __popc(x.y | y.y) + __popc(x.z | y.z) + __popc(x.w | y.w);
+    }
+    if ((words & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
+        ca += __popcll(a[words - 1] & b[words - 1]);
+        co += __popcll(a[words - 1] | b[words - 1]);
+    }
+    ca = block_sum_u64(ca);
+    co = block_sum_u64(co);
+    if (threadIdx.x == 0) {
+        if (ca) atomicAdd(out_and + blockIdx.y, (unsigned long long)ca);
+        if (co) atomicAdd(out_or + blockIdx.y, (unsigned long long)co);
+    }
+}
+
 // All pairs: CTA (bx, by, bz) handles filters I = by*AP_T.., J = bz*AP_T.. over word chunks bx.
 // Each thread keeps AP_T x AP_T partial counts; the 2*AP_T slices are read once per tile pair.
 constexpr int AP_T = 4;
@@ -1753,7 +1802,7 @@ __device__ __forceinline__ void apc_step4(ApcPair (&st)[4], const uint32_t *a0, 
 }
 
 __global__ void __launch_bounds__(APC_THREADS, 3)
-bf_allpairs_csa_kernel(const uint64_t *const *__restrict__ filters, uint32_t n, uint64_t words,
+bf_allpairs_csa_kernel(const uint64_t *const *__restrict__ filters, uint32_t n, uint64_t words, uint32_t pair_base,
                        unsigned long long *__restrict__ out) {
     extern __shared__ __align__(16) uint32_t apc_tile[];            // rows of tw + 4 words: I block, then J block
     __shared__ const uint64_t *sm_ptr[2 * APC_B];
@@ -1763,7 +1812,7 @@ bf_allpairs_csa_kernel(const uint64_t *const *__restrict__ filters, uint32_t n, 
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // block pair (I <= J) from the linear index
     const uint32_t nb = (n + APC_B - 1) / APC_B;
-    uint32_t I = 0, t = blockIdx.y;
+    uint32_t I = 0, t = pair_base + blockIdx.y;  // (more than 65,535 block pairs take several launches)
     while (t >= nb - I) { t -= nb - I; I++; }
     const uint32_t J = I + t;
     const bool diag = I == J;
@@ -1935,7 +1984,7 @@ extern "C" int msbt_bf_or_reduce(msbt_ctx *ctx, const uint64_t *const *h_srcs, u
     int rc = check_ptrs(ctx, h_srcs, n);
     if (rc) return rc;
     if (((uintptr_t)d_dst) & 15) return fail(ctx, MSBT_EINVAL, "destination is not 16-byte aligned");
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CTX_DEVICE(ctx);
     const uint64_t *const *d_srcs;
     rc = upload_ptrs(ctx, h_srcs, n, stream, &d_srcs);
     if (rc) return rc;
@@ -1959,7 +2008,7 @@ extern "C" int msbt_bf_popcount(msbt_ctx *ctx, const uint64_t *const *h_filters,
     if (words == 0 || !d_out) return fail(ctx, MSBT_EINVAL, "bf_popcount: empty input");
     int rc = check_ptrs(ctx, h_filters, n);
     if (rc) return rc;
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CTX_DEVICE(ctx);
     const uint64_t *const *d_f;
     rc = upload_ptrs(ctx, h_filters, n, stream, &d_f);
     if (rc) return rc;
@@ -1984,7 +2033,7 @@ extern "C" int msbt_bf_and_popcount_1vN(msbt_ctx *ctx, const uint64_t *d_focus, 
     if (((uintptr_t)d_focus) & 15) return fail(ctx, MSBT_EINVAL, "focus is not 16-byte aligned");
     int rc = check_ptrs(ctx, h_targets, n);
     if (rc) return rc;
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CTX_DEVICE(ctx);
     const uint64_t *const *d_t;
     rc = upload_ptrs(ctx, h_targets, n, stream, &d_t);
     if (rc) return rc;
@@ -2004,6 +2053,45 @@ extern "C" int msbt_bf_and_popcount_1vN(msbt_ctx *ctx, const uint64_t *d_focus, 
     return MSBT_OK;
 }
 
+extern "C" int msbt_bf_and_popcount_pairs(msbt_ctx *ctx, const uint64_t *const *h_a, const uint64_t *const *h_b, uint32_t n_pairs,
+                                          uint64_t words, uint64_t *d_intersect, uint64_t *d_union, void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_pairs == 0) return MSBT_OK;
+    if (words == 0 || !d_intersect || !d_union) return fail(ctx, MSBT_EINVAL, "bf_and_popcount_pairs: null/empty input");
+    int rc = check_ptrs(ctx, h_a, n_pairs);
+    if (rc) return rc;
+    rc = check_ptrs(ctx, h_b, n_pairs);
+    if (rc) return rc;
+    CTX_DEVICE(ctx);
+    // both pointer tables side by side in scratch
+    const size_t tab = align_up((size_t)n_pairs * sizeof(void *), 256);
+    rc = ensure_scratch(ctx, 2 * tab);
+    if (rc) return rc;
+    rc = stage_begin(ctx, 2 * tab);
+    if (rc) return rc;
+    rc = stage_to_device(ctx, ctx->d_scratch, h_a, (size_t)n_pairs * sizeof(void *), 0, stream);
+    if (rc) return rc;
+    rc = stage_to_device(ctx, (char *)ctx->d_scratch + tab, h_b, (size_t)n_pairs * sizeof(void *), tab, stream);
+    if (rc) return rc;
+    rc = stage_end(ctx, stream);
+    if (rc) return rc;
+    const uint64_t *const *d_a = (const uint64_t *const *)ctx->d_scratch;
+    const uint64_t *const *d_b = (const uint64_t *const *)((char *)ctx->d_scratch + tab);
+    CU_TRY(ctx, cudaMemsetAsync(d_intersect, 0, (size_t)n_pairs * 8, stream));
+    CU_TRY(ctx, cudaMemsetAsync(d_union, 0, (size_t)n_pairs * 8, stream));
+    const uint64_t vec = std::max<uint64_t>(words >> 1, 1);
+    const uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>((vec + 255) / 256, std::max<uint64_t>(1, ((uint64_t)ctx->num_sms * 16 + n_pairs - 1) / n_pairs)));
+    for (uint32_t off = 0; off < n_pairs; off += 65535) {
+        const uint32_t cnt = std::min<uint32_t>(65535, n_pairs - off);
+        bf_dist_pairs_kernel<<<dim3((unsigned)gx, cnt), 256, 0, stream>>>(d_a + off, d_b + off, words,
+                                                                         (unsigned long long *)d_intersect + off,
+                                                                         (unsigned long long *)d_union + off);
+        LAUNCH_CHECK(ctx);
+    }
+    return MSBT_OK;
+}
+
 extern "C" int msbt_bf_and_popcount_allpairs(msbt_ctx *ctx, const uint64_t *const *h_filters, uint32_t n,
                                              uint64_t words, uint64_t *d_intersect, void *stream_) {
     if (!ctx) return MSBT_EINVAL;
@@ -2012,7 +2100,7 @@ extern "C" int msbt_bf_and_popcount_allpairs(msbt_ctx *ctx, const uint64_t *cons
     if (words == 0 || !d_intersect) return fail(ctx, MSBT_EINVAL, "bf_and_popcount_allpairs: null/empty input");
     int rc = check_ptrs(ctx, h_filters, n);
     if (rc) return rc;
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CTX_DEVICE(ctx);
     int variant = 0;  // 0 = carry-save kernel (default), 1 = the plain POPC kernel (kept as the cross-check)
     if (const char *e = getenv("MSBT_ALLPAIRS")) variant = atoi(e);
     const uint64_t *const *d_f;
@@ -2030,16 +2118,47 @@ extern "C" int msbt_bf_and_popcount_allpairs(msbt_ctx *ctx, const uint64_t *cons
         return MSBT_OK;
     }
     const uint64_t nb = (n + APC_B - 1) / APC_B, block_pairs = nb * (nb + 1) / 2;
-    if (block_pairs > 65535) return fail(ctx, MSBT_EINVAL, "allpairs: n=%u too large for one call", n);
+    if (block_pairs > 0xFFFFFFFFull) return fail(ctx, MSBT_EINVAL, "allpairs: n=%u too large for one call", n);
     rc = upload_ptrs(ctx, h_filters, n, stream, &d_f);
     if (rc) return rc;
     CU_TRY(ctx, cudaMemsetAsync(d_intersect, 0, (size_t)n * n * 8, stream));
     const uint64_t n_tiles = (((words + 1) >> 1) + APC_TW / 4 - 1) / (APC_TW / 4);  // upper bound (small n: longer tiles)
     const uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, std::max<uint64_t>(1, (uint64_t)ctx->num_sms * 6 / block_pairs)));
     CU_TRY(ctx, cudaFuncSetAttribute(bf_allpairs_csa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)APC_SMEM_BYTES));
-    bf_allpairs_csa_kernel<<<dim3((unsigned)gx, (unsigned)block_pairs), APC_THREADS, APC_SMEM_BYTES, stream>>>(
-        d_f, n, words, (unsigned long long *)d_intersect);
-    LAUNCH_CHECK(ctx);
+    // gridDim.y is limited to 65,535: n > 5,776 filters (361 blocks of 16) take one launch per 65,535 block pairs
+    for (uint64_t base = 0; base < block_pairs; base += 65535) {
+        const unsigned cnt = (unsigned)std::min<uint64_t>(65535, block_pairs - base);
+        bf_allpairs_csa_kernel<<<dim3((unsigned)gx, cnt), APC_THREADS, APC_SMEM_BYTES, stream>>>(
+            d_f, n, words, (uint32_t)base, (unsigned long long *)d_intersect);
+        LAUNCH_CHECK(ctx);
+    }
+    return MSBT_OK;
+}
+
+// --------------------------------------------------------------------------- host: sparse filter transfer
+// Ascending set-bit positions (the output of msbt_bf_extract_positions*, copied device -> host) -> the dense filter words.
+// At the densities the path works at (5 Mbp into 2^30 bits: 0.47 %) a filter's position list is 1/6 of its dense size,
+// so it is the cheaper thing to move over PCIe; the `.bf` payload is rebuilt on the host, one 32 KiB block at a time
+// (zeroed and filled while it is in L1).
+extern "C" int msbt_positions_expand(const uint32_t *positions, uint64_t n, uint64_t num_bits, uint64_t *words) {
+    if (!words || (n && !positions)) return MSBT_EINVAL;
+    const uint64_t n_words = (num_bits + 63) / 64;
+    constexpr uint64_t BLOCK = 4096;  // words
+    uint64_t i = 0;
+    for (uint64_t w0 = 0; w0 < n_words; w0 += BLOCK) {
+        const uint64_t w1 = std::min(n_words, w0 + BLOCK);
+        memset(words + w0, 0, (w1 - w0) * 8);
+        const uint64_t bit_end = w1 * 64;
+        while (i < n && positions[i] < bit_end) {
+            const uint64_t p = positions[i++];
+            if (p < w0 * 64) return MSBT_EINVAL;  // not ascending
+            words[p >> 6] |= 1ull << (p & 63);
+        }
+    }
+    if (i != n) return MSBT_EINVAL;  // a position beyond num_bits
+    if (n && num_bits & 63) {
+        if (positions[n - 1] >= num_bits) return MSBT_EINVAL;
+    }
     return MSBT_OK;
 }
 
@@ -2125,7 +2244,7 @@ extern "C" int msbt_bf_extract_positions(msbt_ctx *ctx, const uint64_t *d_filter
     if (!d_filter || !d_count || words == 0) return fail(ctx, MSBT_EINVAL, "bf_extract_positions: null/empty input");
     if (words > (1ull << 26)) return fail(ctx, MSBT_EINVAL, "bf_extract_positions: positions are u32 (num_bits <= 2^32)");
     if (cap && !d_positions) return fail(ctx, MSBT_EINVAL, "bf_extract_positions: null output");
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CTX_DEVICE(ctx);
     const uint64_t n_chunks = (words + EX_CHUNK - 1) / EX_CHUNK;
     // chunk table lives past the first 64 KiB of scratch (pointer tables use the front)
     const size_t off = 1 << 16;
@@ -2248,7 +2367,7 @@ extern "C" int msbt_bf_extract_positions_batch(msbt_ctx *ctx, const uint64_t *co
     if (cap && !d_positions) return fail(ctx, MSBT_EINVAL, "bf_extract_positions_batch: null output");
     int rc = check_ptrs(ctx, h_filters, n);
     if (rc) return rc;
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CTX_DEVICE(ctx);
     const uint32_t n_chunks = (uint32_t)((words + EX_CHUNK - 1) / EX_CHUNK);
     // scratch: [pointer table][totals n x u64][chunk counts n x n_chunks x u32]
     const size_t ptr_b = align_up((size_t)n * sizeof(void *), 256);
@@ -2279,9 +2398,9 @@ extern "C" int msbt_bf_extract_positions_batch(msbt_ctx *ctx, const uint64_t *co
 constexpr int QL = 4;
 __global__ void __launch_bounds__(256)
 query_rowmajor_kernel(const uint64_t *const *__restrict__ leaves, uint32_t n_leaves, const uint32_t *__restrict__ positions,
-                      const unsigned long long *__restrict__ q_off, uint32_t *__restrict__ hits) {
+                      const ulonglong2 *__restrict__ q_rng, uint32_t *__restrict__ hits) {
     const uint32_t q = blockIdx.y, l0 = blockIdx.x * QL;
-    const uint64_t b = q_off[q], e = q_off[q + 1];
+    const uint64_t b = q_rng[q].x, e = q_rng[q].y;
     const uint32_t *lf[QL];
 #pragma unroll
     for (int t = 0; t < QL; t++) lf[t] = (const uint32_t *)leaves[min(l0 + t, n_leaves - 1)];
@@ -2298,15 +2417,67 @@ query_rowmajor_kernel(const uint64_t *const *__restrict__ leaves, uint32_t n_lea
     }
 }
 
-static int upload_offsets(msbt_ctx *ctx, const uint64_t *h_off, uint32_t n_queries, size_t scratch_off,
-                          cudaStream_t stream, const unsigned long long **d_out) {
-    size_t bytes = (size_t)(n_queries + 1) * 8;
+// Query q owns positions [begin_q, end_q) of d_positions.  The (begin, end) pairs go to device scratch at `scratch_off`.
+static int upload_ranges(msbt_ctx *ctx, const uint64_t *h_rng, uint32_t n_queries, size_t scratch_off,
+                         cudaStream_t stream, const ulonglong2 **d_out) {
+    size_t bytes = (size_t)n_queries * 16;
     int rc = ensure_scratch(ctx, scratch_off + bytes);
     if (rc) return rc;
     // staging area after the pointer table region
-    rc = stage_to_device(ctx, (char *)ctx->d_scratch + scratch_off, h_off, bytes, scratch_off, stream);
+    rc = stage_to_device(ctx, (char *)ctx->d_scratch + scratch_off, h_rng, bytes, scratch_off, stream);
     if (rc) return rc;
-    *d_out = (const unsigned long long *)((char *)ctx->d_scratch + scratch_off);
+    *d_out = (const ulonglong2 *)((char *)ctx->d_scratch + scratch_off);
+    return MSBT_OK;
+}
+
+static int ranges_from_offsets(msbt_ctx *ctx, const uint64_t *h_off, uint32_t n_queries, std::vector<uint64_t> &rng) {
+    if (!h_off) return fail(ctx, MSBT_EINVAL, "query: null offsets");
+    rng.resize((size_t)n_queries * 2);
+    for (uint32_t q = 0; q < n_queries; q++) {
+        if (h_off[q + 1] < h_off[q]) return fail(ctx, MSBT_EINVAL, "query offsets must be non-decreasing");
+        rng[2 * q] = h_off[q];
+        rng[2 * q + 1] = h_off[q + 1];
+    }
+    return MSBT_OK;
+}
+
+extern "C" int msbt_query_batch_ranges(msbt_ctx *ctx, const uint64_t *const *h_leaves, uint32_t n_leaves,
+                                       const uint32_t *d_positions, const uint64_t *h_query_ranges, uint32_t n_queries,
+                                       uint32_t *d_hits, void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_queries == 0 || n_leaves == 0) return MSBT_OK;
+    if (!h_query_ranges || !d_hits) return fail(ctx, MSBT_EINVAL, "query_batch: null argument");
+    int rc = check_ptrs(ctx, h_leaves, n_leaves);
+    if (rc) return rc;
+    bool any = false;
+    for (uint32_t q = 0; q < n_queries; q++) {
+        if (h_query_ranges[2 * q + 1] < h_query_ranges[2 * q]) return fail(ctx, MSBT_EINVAL, "query %u: range end before begin", q);
+        any = any || h_query_ranges[2 * q + 1] > h_query_ranges[2 * q];
+    }
+    if (any && !d_positions) return fail(ctx, MSBT_EINVAL, "query_batch: null positions");
+    CTX_DEVICE(ctx);
+    const size_t ptr_b = align_up((size_t)n_leaves * sizeof(void *), 256);
+    const uint32_t groups = (n_leaves + QL - 1) / QL;
+    // gridDim.y is limited to 65,535 queries per launch
+    for (uint32_t q0 = 0; q0 < n_queries; q0 += 65535) {
+        const uint32_t nq = std::min<uint32_t>(65535, n_queries - q0);
+        const size_t rng_b = (size_t)nq * 16;
+        rc = ensure_scratch(ctx, ptr_b + rng_b);
+        if (rc) return rc;
+        rc = stage_begin(ctx, ptr_b + rng_b);
+        if (rc) return rc;
+        rc = stage_to_device(ctx, ctx->d_scratch, h_leaves, (size_t)n_leaves * sizeof(void *), 0, stream);
+        if (rc) return rc;
+        const ulonglong2 *d_rng;
+        rc = upload_ranges(ctx, h_query_ranges + 2 * (size_t)q0, nq, ptr_b, stream, &d_rng);
+        if (rc) return rc;
+        rc = stage_end(ctx, stream);
+        if (rc) return rc;
+        query_rowmajor_kernel<<<dim3(groups, nq), 256, 0, stream>>>((const uint64_t *const *)ctx->d_scratch, n_leaves,
+                                                                  d_positions, d_rng, d_hits + (size_t)q0 * n_leaves);
+        LAUNCH_CHECK(ctx);
+    }
     return MSBT_OK;
 }
 
@@ -2314,34 +2485,11 @@ extern "C" int msbt_query_batch(msbt_ctx *ctx, const uint64_t *const *h_leaves, 
                                 const uint32_t *d_positions, const uint64_t *h_query_offsets, uint32_t n_queries,
                                 uint32_t *d_hits, void *stream_) {
     if (!ctx) return MSBT_EINVAL;
-    cudaStream_t stream = (cudaStream_t)stream_;
     if (n_queries == 0 || n_leaves == 0) return MSBT_OK;
-    if (!h_query_offsets || !d_hits) return fail(ctx, MSBT_EINVAL, "query_batch: null argument");
-    if (n_queries > 65535) return fail(ctx, MSBT_EINVAL, "query_batch: at most 65535 queries per call");
-    int rc = check_ptrs(ctx, h_leaves, n_leaves);
+    std::vector<uint64_t> rng;
+    int rc = ranges_from_offsets(ctx, h_query_offsets, n_queries, rng);
     if (rc) return rc;
-    for (uint32_t q = 0; q < n_queries; q++)
-        if (h_query_offsets[q + 1] < h_query_offsets[q]) return fail(ctx, MSBT_EINVAL, "query offsets must be non-decreasing");
-    if (h_query_offsets[n_queries] && !d_positions) return fail(ctx, MSBT_EINVAL, "query_batch: null positions");
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t ptr_b = align_up((size_t)n_leaves * sizeof(void *), 256);
-    const size_t off_b = (size_t)(n_queries + 1) * 8;
-    rc = ensure_scratch(ctx, ptr_b + off_b);
-    if (rc) return rc;
-    rc = stage_begin(ctx, ptr_b + off_b);
-    if (rc) return rc;
-    rc = stage_to_device(ctx, ctx->d_scratch, h_leaves, (size_t)n_leaves * sizeof(void *), 0, stream);
-    if (rc) return rc;
-    const unsigned long long *d_off;
-    rc = upload_offsets(ctx, h_query_offsets, n_queries, ptr_b, stream, &d_off);
-    if (rc) return rc;
-    rc = stage_end(ctx, stream);
-    if (rc) return rc;
-    const uint32_t groups = (n_leaves + QL - 1) / QL;
-    query_rowmajor_kernel<<<dim3(groups, n_queries), 256, 0, stream>>>((const uint64_t *const *)ctx->d_scratch, n_leaves,
-                                                                      d_positions, d_off, d_hits);
-    LAUNCH_CHECK(ctx);
-    return MSBT_OK;
+    return msbt_query_batch_ranges(ctx, h_leaves, n_leaves, d_positions, rng.data(), n_queries, d_hits, stream_);
 }
 
 // Bit-slice transpose.  sliced[(p - row_begin) * ls + (l >> 5)] bit (l & 31) = bit p of leaf l.
@@ -2533,7 +2681,7 @@ struct QsVec<4> {
 template <int W, int G, bool QFAST>
 __global__ void __launch_bounds__(QS_WARPS * 32, (W == 2 && G == 2 ? 3 : 0))
 query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint32_t lw, uint32_t ls, uint64_t row_begin, uint64_t row_end,
-                    const uint32_t *__restrict__ positions, const unsigned long long *__restrict__ q_off,
+                    const uint32_t *__restrict__ positions, const ulonglong2 *__restrict__ q_rng,
                     uint32_t *__restrict__ hits) {
     __shared__ uint32_t sm_hits[1024 * W];
     __shared__ unsigned long long sm_range[2];
@@ -2544,7 +2692,7 @@ query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint
     for (uint32_t i = threadIdx.x; i < 1024 * W; i += blockDim.x) sm_hits[i] = 0;
     if (threadIdx.x == 0) {
         // positions are ascending: the ones inside [row_begin, row_end) form one contiguous range
-        const unsigned long long b = q_off[q], e = q_off[q + 1];
+        const unsigned long long b = q_rng[q].x, e = q_rng[q].y;
         unsigned long long lo = b, hi = e;
         while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1; if (positions[mid] < row_begin) lo = mid + 1; else hi = mid; }
         sm_range[0] = lo;
@@ -2638,7 +2786,7 @@ extern "C" int msbt_bitslice_build(msbt_ctx *ctx, const uint64_t *const *h_leave
     if (row_begin & 31) return fail(ctx, MSBT_EINVAL, "bitslice_build: row_begin must be a multiple of 32");
     int rc = check_ptrs(ctx, h_leaves, n_leaves);
     if (rc) return rc;
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
+    CTX_DEVICE(ctx);
     const uint64_t *const *d_l;
     rc = upload_ptrs(ctx, h_leaves, n_leaves, stream, &d_l);
     if (rc) return rc;
@@ -2655,33 +2803,35 @@ extern "C" int msbt_bitslice_build(msbt_ctx *ctx, const uint64_t *const *h_leave
     return MSBT_OK;
 }
 
-extern "C" int msbt_query_batch_sliced(msbt_ctx *ctx, const uint32_t *d_sliced, uint32_t n_leaves, uint64_t row_begin,
-                                       uint64_t row_end, const uint32_t *d_positions, const uint64_t *h_query_offsets,
-                                       uint32_t n_queries, uint32_t *d_hits, void *stream_) {
+extern "C" int msbt_query_batch_sliced_ranges(msbt_ctx *ctx, const uint32_t *d_sliced, uint32_t n_leaves, uint64_t row_begin,
+                                              uint64_t row_end, const uint32_t *d_positions, const uint64_t *h_query_ranges,
+                                              uint32_t n_queries, uint32_t *d_hits, void *stream_) {
     if (!ctx) return MSBT_EINVAL;
     cudaStream_t stream = (cudaStream_t)stream_;
     if (n_queries == 0 || n_leaves == 0) return MSBT_OK;
-    if (!d_sliced || !h_query_offsets || !d_hits) return fail(ctx, MSBT_EINVAL, "query_batch_sliced: null argument");
+    if (!d_sliced || !h_query_ranges || !d_hits) return fail(ctx, MSBT_EINVAL, "query_batch_sliced: null argument");
     if (n_queries > 65535) return fail(ctx, MSBT_EINVAL, "query_batch_sliced: at most 65535 queries per call");
-    for (uint32_t q = 0; q < n_queries; q++)
-        if (h_query_offsets[q + 1] < h_query_offsets[q]) return fail(ctx, MSBT_EINVAL, "query offsets must be non-decreasing");
-    CU_TRY(ctx, cudaSetDevice(ctx->device));
-    const size_t off_b = (size_t)(n_queries + 1) * 8;
-    int rc = ensure_scratch(ctx, off_b);
+    uint64_t max_pos = 0;
+    for (uint32_t q = 0; q < n_queries; q++) {
+        if (h_query_ranges[2 * q + 1] < h_query_ranges[2 * q]) return fail(ctx, MSBT_EINVAL, "query %u: range end before begin", q);
+        max_pos = std::max<uint64_t>(max_pos, h_query_ranges[2 * q + 1] - h_query_ranges[2 * q]);
+    }
+    CTX_DEVICE(ctx);
+    // hits accumulate with atomics: clear first (partial results of other bit ranges are summed by the caller)
+    CU_TRY(ctx, cudaMemsetAsync(d_hits, 0, (size_t)n_queries * n_leaves * 4, stream));
+    if (max_pos == 0) return MSBT_OK;
+    if (!d_positions) return fail(ctx, MSBT_EINVAL, "query_batch_sliced: null positions");
+    const size_t rng_b = (size_t)n_queries * 16;
+    int rc = ensure_scratch(ctx, rng_b);
     if (rc) return rc;
-    rc = stage_begin(ctx, off_b);
+    rc = stage_begin(ctx, rng_b);
     if (rc) return rc;
-    const unsigned long long *d_off;
-    rc = upload_offsets(ctx, h_query_offsets, n_queries, 0, stream, &d_off);
+    const ulonglong2 *d_rng;
+    rc = upload_ranges(ctx, h_query_ranges, n_queries, 0, stream, &d_rng);
     if (rc) return rc;
     rc = stage_end(ctx, stream);
     if (rc) return rc;
     const uint32_t lw = (n_leaves + 31) / 32;
-    uint64_t max_pos = 0;
-    for (uint32_t q = 0; q < n_queries; q++) max_pos = std::max<uint64_t>(max_pos, h_query_offsets[q + 1] - h_query_offsets[q]);
-    if (max_pos == 0) { CU_TRY(ctx, cudaMemsetAsync(d_hits, 0, (size_t)n_queries * n_leaves * 4, stream)); return MSBT_OK; }
-    // hits accumulate with atomics: clear first (partial results of other bit ranges are summed by the caller)
-    CU_TRY(ctx, cudaMemsetAsync(d_hits, 0, (size_t)n_queries * n_leaves * 4, stream));
     const uint64_t per_cta = (uint64_t)QS_WARPS * QS_SUB;
     const uint32_t gx = (uint32_t)((max_pos + per_cta - 1) / per_cta);
     const uint32_t ls = msbt_sliced_row_words(n_leaves);
@@ -2701,7 +2851,7 @@ extern "C" int msbt_query_batch_sliced(msbt_ctx *ctx, const uint32_t *d_sliced, 
     const dim3 grid = qfast ? dim3(n_queries, gy, gx) : dim3(gx, gy, n_queries);
     int G = W == 1 ? 2 : 1;  // groups of 7 row reads in flight per lane (W = 1, 1,024 leaves: 46.5 % -> 47.6 % of the HBM peak)
     if (const char *e = getenv("MSBT_QS_G")) { const int g = atoi(e); if (g == 1 || g == 2) G = g; }  // tuning aid
-#define MSBT_QS_LAUNCH2(WW, GG, QF) query_sliced_kernel<WW, GG, QF><<<grid, QS_WARPS * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_off, d_hits)
+#define MSBT_QS_LAUNCH2(WW, GG, QF) query_sliced_kernel<WW, GG, QF><<<grid, QS_WARPS * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_rng, d_hits)
 #define MSBT_QS_LAUNCH(WW, GG) do { if (qfast) MSBT_QS_LAUNCH2(WW, GG, true); else MSBT_QS_LAUNCH2(WW, GG, false); } while (0)
     if (W == 4) MSBT_QS_LAUNCH(4, 1);
     else if (W == 2 && G == 2) MSBT_QS_LAUNCH(2, 2);
@@ -2712,4 +2862,15 @@ extern "C" int msbt_query_batch_sliced(msbt_ctx *ctx, const uint32_t *d_sliced, 
 #undef MSBT_QS_LAUNCH
     LAUNCH_CHECK(ctx);
     return MSBT_OK;
+}
+
+extern "C" int msbt_query_batch_sliced(msbt_ctx *ctx, const uint32_t *d_sliced, uint32_t n_leaves, uint64_t row_begin,
+                                       uint64_t row_end, const uint32_t *d_positions, const uint64_t *h_query_offsets,
+                                       uint32_t n_queries, uint32_t *d_hits, void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    if (n_queries == 0 || n_leaves == 0) return MSBT_OK;
+    std::vector<uint64_t> rng;
+    int rc = ranges_from_offsets(ctx, h_query_offsets, n_queries, rng);
+    if (rc) return rc;
+    return msbt_query_batch_sliced_ranges(ctx, d_sliced, n_leaves, row_begin, row_end, d_positions, rng.data(), n_queries, d_hits, stream_);
 }

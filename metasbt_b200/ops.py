@@ -63,6 +63,19 @@ def pack_fasta(text: bytes, min_run: int) -> PackedGenome:
     return PackedGenome(words, ends[: nr.value], int(nb.value))
 
 
+def positions_expand(positions: np.ndarray, num_bits: int, out: np.ndarray) -> np.ndarray:
+    """Host side of a sparse filter transfer (msbt_positions_expand): ascending uint32 positions -> dense filter words
+    written into `out` (uint64, >= filter_words(num_bits) entries).  Releases the GIL: callers fan it out over threads."""
+    pos = np.ascontiguousarray(positions).view(np.uint32)
+    w = filter_words(num_bits)
+    if out.dtype.itemsize != 8 or out.size < w or not out.flags["C_CONTIGUOUS"]:
+        raise ValueError("positions_expand: `out` must be a contiguous 64-bit array of at least filter_words(num_bits) entries")
+    rc = _lib.lib().msbt_positions_expand(pos.ctypes.data if pos.size else None, pos.size, num_bits, out.ctypes.data)
+    if rc != 0:
+        raise ValueError(f"msbt_positions_expand failed ({rc}): positions must be ascending and below num_bits")
+    return out
+
+
 def pack_codes(codes: np.ndarray) -> PackedGenome:
     """Pack an array of base codes (0..3, one run) -- used for synthetic genomes."""
     codes = np.ascontiguousarray(codes, dtype=np.uint8)
@@ -229,6 +242,18 @@ class Context:
             if sizes[i]:
                 hv[offs[i]: offs[i + 1]] = np.frombuffer(t, dtype=np.uint8)
         d_text = h_text.to(self.device, non_blocking=True)
+        return self.pack_device_text(d_text, sizes, min_run)
+
+    def pack_device_text(self, d_text: torch.Tensor, sizes: Sequence[int], min_run: int) -> GenomeBatch:
+        """The same for FASTA text that already sits on the device: `d_text` (uint8) holds the files back to back,
+        `sizes` their lengths in bytes."""
+        n = len(sizes)
+        offs = (ctypes.c_uint64 * (n + 1))()
+        for i, sz in enumerate(sizes):
+            offs[i + 1] = offs[i] + int(sz)
+        total = int(offs[n])
+        if d_text.numel() < total:
+            raise ValueError("pack_device_text: the text tensor is shorter than the summed file sizes")
         need = max(int(min_run), 1)
         n_words = sum((sz + 31) // 32 + _lib.PACK_PAD_WORDS for sz in sizes)
         n_runs = sum(sz // need + 1 for sz in sizes)
@@ -291,6 +316,19 @@ class Context:
             self._check(rc, "msbt_bf_and_popcount_1vN")
         return inter, union
 
+    def bf_dist_pairs(self, a: Sequence[torch.Tensor], b: Sequence[torch.Tensor], num_bits: int) -> Tuple[torch.Tensor, torch.Tensor]:
+        """(popc(a_p & b_p), popc(a_p | b_p)) for an arbitrary list of pairs in ONE launch -> (I[n], U[n]) int64."""
+        n = len(a)
+        if len(b) != n:
+            raise ValueError("bf_dist_pairs: the two lists must have the same length")
+        inter = torch.empty(n, dtype=torch.int64, device=self.device)
+        union = torch.empty(n, dtype=torch.int64, device=self.device)
+        if n:
+            rc = self._L.msbt_bf_and_popcount_pairs(self._h, _ptr_array(a), _ptr_array(b), n, filter_words(num_bits),
+                                                    inter.data_ptr(), union.data_ptr(), self._stream())
+            self._check(rc, "msbt_bf_and_popcount_pairs")
+        return inter, union
+
     def bf_allpairs(self, filters: Sequence[torch.Tensor], num_bits: int) -> torch.Tensor:
         """Dense n x n intersection matrix (diagonal = popcounts)."""
         n = len(filters)
@@ -316,6 +354,19 @@ class Context:
         self._check(rc, "msbt_bf_extract_positions")
         n = min(int(count.item()), cap)
         return pos[:n]
+
+    def extract_positions_into(self, filters: Sequence[torch.Tensor], num_bits: int, out: torch.Tensor,
+                               offsets_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Ascending set-bit positions of every filter, back to back, written into the caller's int32 tensor `out`
+        (entries beyond its size are dropped).  Nothing synchronises: the n + 1 offsets stay on the device (returned)."""
+        n = len(filters)
+        offs = offsets_out if offsets_out is not None else torch.empty(n + 1, dtype=torch.int64, device=self.device)
+        if n == 0:
+            return offs
+        rc = self._L.msbt_bf_extract_positions_batch(self._h, _ptr_array(filters), n, filter_words(num_bits), out.data_ptr(),
+                                                     out.numel(), offs.data_ptr(), self._stream())
+        self._check(rc, "msbt_bf_extract_positions_batch")
+        return offs
 
     def extract_positions_packed(self, filters: Sequence[torch.Tensor], num_bits: int, cap: Optional[int] = None
                                  ) -> Tuple[torch.Tensor, List[int]]:
@@ -357,6 +408,38 @@ class Context:
         allpos = torch.cat([p.reshape(-1) for p in positions]) if offs[nq] else torch.zeros(1, dtype=torch.int32, device=self.device)
         rc = self._L.msbt_query_batch(self._h, _ptr_array(leaves), nl, allpos.data_ptr(), offs, nq, hits.data_ptr(), self._stream())
         self._check(rc, "msbt_query_batch")
+        return hits
+
+    def query_ranges(self, leaves: Sequence[torch.Tensor], allpos: torch.Tensor, ranges: Sequence[Tuple[int, int]]) -> torch.Tensor:
+        """Row-major probe of the queries whose positions are allpos[begin:end] for every (begin, end) of `ranges`
+        (any subset, any order, of a packed position batch; nothing is copied) -> int32[q, l]."""
+        nq, nl = len(ranges), len(leaves)
+        hits = torch.zeros((nq, nl), dtype=torch.int32, device=self.device)
+        if nq == 0 or nl == 0:
+            return hits
+        rng = (ctypes.c_uint64 * (2 * nq))()
+        for i, (b, e) in enumerate(ranges):
+            rng[2 * i], rng[2 * i + 1] = int(b), int(e)
+        rc = self._L.msbt_query_batch_ranges(self._h, _ptr_array(leaves), nl, allpos.data_ptr(), rng, nq, hits.data_ptr(), self._stream())
+        self._check(rc, "msbt_query_batch_ranges")
+        return hits
+
+    def query_sliced_ranges(self, sliced: torch.Tensor, n_leaves: int, row_begin: int, row_end: int,
+                            allpos: torch.Tensor, ranges: Sequence[Tuple[int, int]]) -> torch.Tensor:
+        """Bit-sliced probe with an explicit (begin, end) range of `allpos` per query -> int32[q, l]."""
+        nq = len(ranges)
+        hits = torch.empty((nq, n_leaves), dtype=torch.int32, device=self.device)
+        if nq == 0 or n_leaves == 0:
+            return hits
+        out = []
+        for q0 in range(0, nq, 65535):  # one launch per 65,535 queries (grid limit)
+            part = ranges[q0: q0 + 65535]
+            rng = (ctypes.c_uint64 * (2 * len(part)))()
+            for i, (b, e) in enumerate(part):
+                rng[2 * i], rng[2 * i + 1] = int(b), int(e)
+            rc = self._L.msbt_query_batch_sliced_ranges(self._h, sliced.data_ptr(), n_leaves, row_begin, row_end, allpos.data_ptr(),
+                                                        rng, len(part), hits[q0: q0 + len(part)].data_ptr(), self._stream())
+            self._check(rc, "msbt_query_batch_sliced_ranges")
         return hits
 
     def sliced_row_words(self, n_leaves: int) -> int:

@@ -75,11 +75,100 @@ def query_sharded(ctx, sliced: torch.Tensor, n_leaves: int, num_bits: int, query
     return hits if partial_only else all_reduce_counts(hits, group)
 
 
-def or_merge(partial: torch.Tensor, num_bits: int, group=None) -> torch.Tensor:
+def query_blocks(n_queries: int, world: int) -> List[Tuple[int, int]]:
+    """Contiguous [begin, end) blocks of a query batch per rank (the rank that HASHES those MAGs)."""
+    return [(n_queries * r // world, n_queries * (r + 1) // world) for r in range(world)]
+
+
+def exchange_plan(counts_all: Sequence[Sequence[Sequence[int]]], rank: int) -> Tuple[List[int], List[int], List[Tuple[int, int]]]:
+    """Host-side plan of the position exchange.  counts_all[s][q][d] = number of positions of the q-th MAG hashed by rank s
+    that fall into rank d's bit range.  Returns for `rank`: (send split sizes per destination, receive split sizes per
+    source, and the [begin, end) range inside the receive buffer of every query of the batch in global batch order)."""
+    world = len(counts_all)
+    send = [sum(int(c[d]) for c in counts_all[rank]) for d in range(world)]
+    recv = [sum(int(c[rank]) for c in counts_all[s]) for s in range(world)]
+    ranges, cursor = [], 0
+    for s in range(world):
+        for c in counts_all[s]:
+            ranges.append((cursor, cursor + int(c[rank])))
+            cursor += int(c[rank])
+    return send, recv, ranges
+
+
+def query_exchange_sharded(ctx, sliced: torch.Tensor, n_leaves: int, num_bits: int, local_filters: Sequence[torch.Tensor],
+                           group=None, timings: dict | None = None) -> torch.Tensor:
+    """K4 across ranks with the HASHING sharded as well (second option).  Every rank has hashed only
+    its block of the MAG batch (query_blocks): `local_filters` are those MAGs' own min=1 filters.  Per step:
+      1. K3' on word sub-views: how many positions of each local MAG fall into each rank's bit range (one launch, one
+         small device->host copy, one all_gather of the counts);
+      2. per destination rank one batched ordered extraction of that bit range straight into the send buffer
+         (positions relative to the range start);
+      3. all_to_all of the position lists (rank r receives, MAG by MAG, the positions inside ITS rows);
+      4. one bit-sliced probe of the local shard with the positions of the WHOLE batch -> partial hits[B][L];
+      5. all_reduce(SUM) of the partial hit matrices.
+    Returns int32[B, L] on every rank, B = the batch size over all ranks, in rank order."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    dev = ctx.device
+    n_local = len(local_filters)
+    ranges_bits = bit_ranges(num_bits, world)
+    words = [(b // 64, (e + 63) // 64) for b, e in ranges_bits]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timings is not None else None
+    if ev:
+        ev[0].record()
+    # 1. counts[q][d]
+    views = [f[w0:w1] for w0, w1 in words for f in local_filters]  # d-major
+    if n_local:
+        counts = ctx.bf_popcount(views, 64 * max(w1 - w0 for w0, w1 in words)) if len({w1 - w0 for w0, w1 in words}) == 1 else \
+            torch.cat([ctx.bf_popcount(views[d * n_local:(d + 1) * n_local], 64 * (words[d][1] - words[d][0])) for d in range(world)])
+        counts_h = counts.view(world, n_local).t().contiguous().cpu().tolist()  # [q][d]
+    else:
+        counts_h = []
+    if world > 1:
+        gathered: List[object] = [None] * world
+        dist.all_gather_object(gathered, counts_h, group=group)
+    else:
+        gathered = [counts_h]
+    send_sizes, recv_sizes, q_ranges = exchange_plan(gathered, rank)
+    # 2. per destination, straight into the send buffer
+    send = torch.empty(max(sum(send_sizes), 1), dtype=torch.int32, device=dev)
+    cursor = 0
+    for d in range(world):
+        if send_sizes[d]:
+            w0, w1 = words[d]
+            ctx.extract_positions_into([f[w0:w1] for f in local_filters], 64 * (w1 - w0), send[cursor: cursor + send_sizes[d]])
+        cursor += send_sizes[d]
+    if ev:
+        ev[1].record()
+    # 3. exchange
+    if world > 1:
+        recv = torch.empty(max(sum(recv_sizes), 1), dtype=torch.int32, device=dev)
+        dist.all_to_all_single(recv[: sum(recv_sizes)], send[: sum(send_sizes)], recv_sizes, send_sizes, group=group)
+    else:
+        recv = send
+    if ev:
+        ev[2].record()
+    # 4. probe (row indices are relative to this rank's range)
+    rb, re_ = ranges_bits[rank]
+    hits = ctx.query_sliced_ranges(sliced, n_leaves, 0, re_ - rb, recv, q_ranges)
+    if ev:
+        ev[3].record()
+    # 5. sum the partial matrices
+    all_reduce_counts(hits, group)
+    if ev:
+        ev[4].record()
+        torch.cuda.synchronize(dev)
+        for name, i in (("ms_count_extract", 0), ("ms_all_to_all", 1), ("ms_probe", 2), ("ms_all_reduce", 3)):
+            timings[name] = timings.get(name, 0.0) + ev[i].elapsed_time(ev[i + 1])
+        timings["positions_in_shard"] = timings.get("positions_in_shard", 0) + sum(recv_sizes)
+    return hits
+
+
+def or_merge(partial: torch.Tensor, num_bits: int, group=None, ctx=None) -> torch.Tensor:
     """Bitwise-OR merge of one partial filter per rank (int64 words, same length everywhere).
-    all_to_all by bit range, local OR (torch.bitwise_or on the received [world, range] block -- a trivially
-    memory-bound elementwise op on data already resident; the k-way OR of whole filters is
-    msbt_bf_or_reduce), then all_gather of the merged ranges.  Returns the full merged filter on every rank."""
+    all_to_all by bit range, local k-way OR of the received ranges (msbt_bf_or_reduce through `ctx` on the GPU; the
+    gloo CPU tests, which have no device, fall back to torch.bitwise_or for this one elementwise step), then all_gather
+    of the merged ranges.  Returns the full merged filter on every rank."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return partial
     world, rank = dist.get_world_size(group), dist.get_rank(group)
@@ -89,9 +178,14 @@ def or_merge(partial: torch.Tensor, num_bits: int, group=None) -> torch.Tensor:
     mine = ranges[rank][1] - ranges[rank][0]
     recv = [torch.empty(mine, dtype=partial.dtype, device=partial.device) for _ in range(world)]
     dist.all_to_all(recv, send, group=group) if partial.is_cuda else _all_to_all_gloo(recv, send, group)
-    merged = recv[0]
-    for r in range(1, world):
-        merged = torch.bitwise_or(merged, recv[r])
+    if partial.is_cuda:
+        if ctx is None:
+            raise ValueError("or_merge on CUDA tensors needs the ops.Context that owns the device (msbt_bf_or_reduce)")
+        merged = ctx.bf_or(recv, 64 * mine)[:mine]  # fresh allocations: 16-byte aligned rows, as msbt_bf_or_reduce wants
+    else:
+        merged = recv[0]
+        for r in range(1, world):
+            merged = torch.bitwise_or(merged, recv[r])
     pieces = [torch.empty(e - b, dtype=partial.dtype, device=partial.device) for b, e in ranges]
     dist.all_gather(pieces, merged, group=group) if len({e - b for b, e in ranges}) == 1 else _all_gather_uneven(pieces, merged, group)
     return torch.cat(pieces)

@@ -50,3 +50,26 @@ def pack_codes_device(codes: torch.Tensor) -> torch.Tensor:
 
 def packed_genome(seed: int, n: int, device: torch.device) -> torch.Tensor:
     return pack_codes_device(genome_codes(seed, n, device))
+
+
+def mutated_codes(seed_ancestor: int, seed_mut: int, n: int, per_mille: int, device: torch.device) -> torch.Tensor:
+    """Related genomes: the ancestor's bases with SNPs where splitmix64((seed_mut << 32) ^ i) says so."""
+    codes = genome_codes(seed_ancestor, n, device)
+    r = splitmix64((seed_mut << 32) ^ torch.arange(n, dtype=torch.int64, device=device))
+    snp = (_lsr(r, 8) % 1000) < per_mille
+    return torch.where(snp, (codes + 1 + _lsr(r, 40) % 3) % 4, codes)
+
+
+def fasta_text_device(codes: torch.Tensor, name: str, width: int = 80) -> torch.Tensor:
+    """uint8 FASTA text (">name\\n" + lines of `width` bases) of a code tensor, assembled on the device -- the bytes a
+    FASTA file of this genome would hold (input generation for the end-to-end benchmark, never inside a timed region)."""
+    n = codes.numel()
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=codes.device)  # A C G T
+    bases = lut[codes]
+    full = n // width
+    body = torch.full((full, width + 1), 10, dtype=torch.uint8, device=codes.device)  # newline column
+    body[:, :width] = bases[: full * width].view(full, width)
+    parts = [torch.tensor(list((">" + name + "\n").encode()), dtype=torch.uint8, device=codes.device), body.reshape(-1)]
+    if n > full * width:
+        parts += [bases[full * width:], torch.tensor([10], dtype=torch.uint8, device=codes.device)]
+    return torch.cat(parts)

@@ -59,10 +59,27 @@ class OracleBackend:
     def dist_all_pairs_many(self, groups: Sequence[Sequence[str]]) -> List[np.ndarray]:
         return [self.dist_all_pairs(g) for g in groups]
 
-    def query_positions(self, fasta_path: str) -> np.ndarray:
-        return O.positions_distinct(open(fasta_path, "rb").read(), self.k, self.num_bits)
+    def dist_pairs(self, pairs):
+        return [(O.bf_and_popcount(self._load(a), self._load(b)), O.bf_or_popcount(self._load(a), self._load(b))) for a, b in pairs]
 
-    def query_hits(self, positions: np.ndarray, leaf_paths: Sequence[str]):
+    # the batch interface of profile_many: a "query batch" is just the list of position arrays here
+    def query_positions_many(self, fasta_paths: Sequence[str]):
+        return [O.positions_distinct(open(p, "rb").read(), self.k, self.num_bits) for p in fasta_paths]
+
+    def query_positions(self, fasta_path: str):
+        return self.query_positions_many([fasta_path])
+
+    def query_totals(self, qb) -> List[int]:
+        return [len(p) for p in qb]
+
+    def query_hits_many(self, qb, idxs: Sequence[int], leaf_paths: Sequence[str]) -> np.ndarray:
+        leaves = [self._load(p) for p in leaf_paths]
+        return np.array([[int(x) for x in O.query_hits(qb[i], leaves)] for i in idxs], dtype=np.int64).reshape(len(idxs), len(leaves))
+
+    def fetch_hits(self, pending):
+        return list(pending)
+
+    def query_hits(self, positions, leaf_paths: Sequence[str]):
         if not leaf_paths:
-            return [], len(positions)
-        return [int(x) for x in O.query_hits(positions, [self._load(p) for p in leaf_paths])], len(positions)
+            return [], len(positions[0])
+        return [int(x) for x in self.query_hits_many(positions, [0], leaf_paths)[0]], len(positions[0])

@@ -6,7 +6,9 @@
 * K1: genomes sharded in contiguous blocks, no collective; every rank's filters equal the oracle's.
 * K2: per-rank partial unions merged by bit range (all_to_all + local OR + all_gather) == OR of everything.
 * K3: AND-popcounts over bit-range shards, all_reduce(SUM) == whole-filter counts.
-* K4: bit-sliced leaf matrix sharded by row range, partial hits all_reduce(SUM) == unsharded hits == oracle.
+* K4: bit-sliced leaf matrix sharded by row range, partial hits all_reduce(SUM) == unsharded hits == oracle;
+      also with the MAG hashing sharded and the positions exchanged by bit range (all_to_all).
+tests/test_multi_gpu.py launches this under `pytest -m gpu` on min(device_count, 4) GPUs.
 """
 import os
 import sys
@@ -43,7 +45,7 @@ def main():
 
     # K2: partial union per rank, merged by bit range over NCCL
     partial = ctx.bf_or([mine[i] for i in range(e - b)], m) if e > b else torch.zeros(ops.filter_stride_words(m), dtype=torch.int64, device=dev)
-    merged = shard.or_merge(partial[:w].contiguous(), m)
+    merged = shard.or_merge(partial[:w].contiguous(), m, ctx=ctx)
     assert np.array_equal(merged.cpu().numpy().view(np.uint64), O.bf_or(want)), "K2 merge rank %d" % rank
 
     # replicate all leaves (small here) so that every rank can take its bit range of every leaf
@@ -77,6 +79,12 @@ def main():
     # the same through shard.query_sharded (each rank extracts only the positions of its own bit range)
     hits2 = shard.query_sharded(ctx, sliced, n, m, [qf[i] for i in range(len(queries))])
     assert np.array_equal(hits2.cpu().numpy().astype(np.uint64), ref), "K4 query_sharded rank %d" % rank
+    # the same with the hashing sharded too: every rank hashes its block of the queries, positions are exchanged by bit range
+    qb, qe = shard.query_blocks(len(queries), world)[rank]
+    timings = dict()
+    hits3 = shard.query_exchange_sharded(ctx, sliced, n, m, [qf[i] for i in range(qb, qe)], timings=timings)
+    assert np.array_equal(hits3.cpu().numpy().astype(np.uint64), ref), "K4 query_exchange_sharded rank %d" % rank
+    assert "ms_probe" in timings
     dist.barrier()
     if rank == 0:
         print("multi-GPU parity ok: world=%d, K1 blocks %s, K2 OR-merge, K3 and K4 bit-range shards all match the oracle" % (world, counts))

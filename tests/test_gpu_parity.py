@@ -488,7 +488,7 @@ def test_makebf_maximum_filter_size(ctx, oracle, num_bits):
 
 
 def test_backend_sliced_tree_cache(ctx, oracle, tmp_path):
-    """CudaBackend.query_hits: a flat tree with many leaves is transposed on its second query and probed bit-sliced from
+    """CudaBackend.query_hits: a flat tree with many leaves is transposed as soon as that pays and probed bit-sliced from
     then on; the hits equal the oracle's every time, and rewriting one leaf invalidates the cached matrix."""
     from metasbt_b200 import backend as B, bffile
     rng = random.Random(4242)
@@ -509,7 +509,9 @@ def test_backend_sliced_tree_cache(ctx, oracle, tmp_path):
     def want():
         return [int(x) for x in oracle.query_hits(qpos, [bffile.read_bf(p)[1] for p in bfs])]
 
-    for expected_sliced in (0, 1, 2):
+    # 300 leaves: the row-major probe of even one query would move more bytes than transposing, so the first query already
+    # goes through the bit-sliced matrix
+    for expected_sliced in (1, 2, 3):
         hits, total = be.query_hits(positions, bfs)
         assert total == len(qpos) and hits == want()
         assert be.sliced_probes == expected_sliced
@@ -525,3 +527,112 @@ def test_backend_sliced_tree_cache(ctx, oracle, tmp_path):
         h, _ = be.query_hits(positions, bfs[:40])
         assert h == want()[:40]
     assert be.sliced_probes == before
+
+
+def test_sliced_matrix_dropped_even_when_the_row_major_copy_was_evicted(ctx, oracle, tmp_path):
+    """ADVICE r1: a leaf can be LRU-evicted from the filter cache while a cached bit-sliced matrix still contains it;
+    rewriting that leaf must drop the matrix all the same."""
+    from metasbt_b200 import backend as B, bffile
+    rng = random.Random(99)
+    k, num_bits, n_leaves = 21, 1 << 16, 260
+    be = B.CudaBackend(k, num_bits)
+    fas = []
+    for i in range(n_leaves):
+        fa = tmp_path / ("leaf%03d.fa" % i)
+        fa.write_bytes(util.messy_fasta(rng, 1, 900, "ACGT"))
+        fas.append(str(fa))
+    bfs = [str(tmp_path / ("leaf%03d.bf" % i)) for i in range(n_leaves)]
+    be.sketch_many(fas, bfs, 1)
+    positions = be.query_positions(fas[9])
+    hits, _ = be.query_hits(positions, bfs)
+    assert be.sliced_probes == 1 and len(be._sliced) == 1
+    for p in list(be._cache):  # cache pressure: every row-major copy goes
+        be._bytes -= be._cache.pop(p).numel() * 8
+    assert len(be._sliced) == 1
+    be.sketch_many([fas[9]], [bfs[5]], 1)
+    assert len(be._sliced) == 0
+    hits, _ = be.query_hits(positions, bfs)
+    assert hits[5] == hits[9] == oracle.bf_popcount(bffile.read_bf(bfs[9])[1])
+
+
+def test_dist_pairs_and_query_ranges(ctx, oracle):
+    """msbt_bf_and_popcount_pairs and the *_ranges query entry points (any subset, any order, of a packed batch)."""
+    rng = random.Random(5)
+    k = 21
+    for num_bits in (1000, 1 << 16, (1 << 18) + 64):
+        fastas = [util.messy_fasta(rng, 2, 3000, "ACGTN") for _ in range(12)]
+        mat, flt = build(ctx, fastas, k, num_bits)
+        rows = [mat[i] for i in range(len(fastas))]
+        pa = [rng.randrange(12) for _ in range(40)]
+        pb = [rng.randrange(12) for _ in range(40)]
+        inter, union = ctx.bf_dist_pairs([rows[i] for i in pa], [rows[j] for j in pb], num_bits)
+        assert inter.tolist() == [oracle.bf_and_popcount(flt[i], flt[j]) for i, j in zip(pa, pb)]
+        assert union.tolist() == [oracle.bf_or_popcount(flt[i], flt[j]) for i, j in zip(pa, pb)]
+        # packed positions of queries 0..7; probe a shuffled subset with repeats against leaves 4..11
+        pos, offs = ctx.extract_positions_packed(rows[:8], num_bits)
+        subset = [5, 0, 7, 7, 2]
+        ranges = [(offs[q], offs[q + 1]) for q in subset] + [(offs[3], offs[3])]  # and an empty range
+        want = np.stack([oracle.query_hits(oracle.positions_distinct(fastas[q], k, num_bits), flt[4:]) for q in subset]
+                        + [np.zeros(8, dtype=np.uint64)])
+        got = ctx.query_ranges(rows[4:], pos, ranges).cpu().numpy()
+        assert np.array_equal(got.astype(np.uint64), want)
+        sliced = ctx.bitslice(rows[4:], 0, num_bits)
+        got = ctx.query_sliced_ranges(sliced, 8, 0, num_bits, pos, ranges).cpu().numpy()
+        assert np.array_equal(got.astype(np.uint64), want)
+    with pytest.raises(ValueError):
+        ctx.query_ranges(rows[4:], pos, [(5, 3)])
+    with pytest.raises(ValueError):
+        ctx.bf_dist_pairs(rows[:2], rows[:3], num_bits)
+
+
+def test_allpairs_more_than_65535_block_pairs(ctx):
+    """n > 5,776 filters (more than 65,535 block pairs of 16 x 16) used to be rejected."""
+    n, num_bits = 5800, 128
+    g = torch.Generator().manual_seed(7)
+    host = torch.randint(-2 ** 62, 2 ** 62, (n, 2), generator=g, dtype=torch.int64)
+    dev = host.to(ctx.device)
+    got = ctx.bf_allpairs([dev[i] for i in range(n)], num_bits).cpu().numpy()
+    a = host.numpy().view(np.uint64)
+    bits = np.unpackbits(a.view(np.uint8), axis=1).astype(np.int32)  # [n, 128]
+    want = bits @ bits.T
+    assert np.array_equal(got, want.astype(np.int64))
+
+
+def test_backend_streams_operands_in_chunks(ctx, oracle, tmp_path):
+    """operand lists larger than the cache budget stream through in chunks (union, popcounts, 1-vs-N, pair list,
+    tiled all-pairs, leaf-chunked query) and give the oracle's numbers."""
+    from metasbt_b200 import backend as B, bffile
+    rng = random.Random(31)
+    k, num_bits, n = 21, 1 << 16, 23
+    row = (num_bits // 64) * 8
+    be = B.CudaBackend(k, num_bits, cache_bytes=12 * row)  # 6 filters per chunk
+    assert be._chunk() == 6
+    fas, bfs = [], []
+    for i in range(n):
+        fa = tmp_path / ("g%02d.fa" % i)
+        fa.write_bytes(util.messy_fasta(rng, 2, 2500, "ACGTN"))
+        fas.append(str(fa))
+        bfs.append(str(tmp_path / ("g%02d.bf" % i)))
+    be.sketch_many(fas, bfs, 1)
+    flt = [bffile.read_bf(p)[1] for p in bfs]
+    for f, fa in zip(flt, fas):
+        assert np.array_equal(f, oracle.makebf(open(fa, "rb").read(), k, num_bits))
+    assert len(be._cache) <= 12
+    assert be.popcounts(bfs) == [oracle.bf_popcount(f) for f in flt]
+    be.union(bfs, str(tmp_path / "u.bf"))
+    assert np.array_equal(bffile.read_bf(str(tmp_path / "u.bf"))[1], oracle.bf_or(flt))
+    assert be.dist_one_vs_many(bfs[3], bfs) == [(oracle.bf_and_popcount(flt[3], f), oracle.bf_or_popcount(flt[3], f)) for f in flt]
+    pairs = [(bfs[rng.randrange(n)], bfs[rng.randrange(n)]) for _ in range(17)]
+    idx = {p: i for i, p in enumerate(bfs)}
+    assert be.dist_pairs(pairs) == [(oracle.bf_and_popcount(flt[idx[a]], flt[idx[b]]), oracle.bf_or_popcount(flt[idx[a]], flt[idx[b]]))
+                                    for a, b in pairs]
+    want = np.array([[oracle.bf_and_popcount(a, b) for b in flt] for a in flt], dtype=np.int64)
+    assert np.array_equal(be.dist_all_pairs(bfs), want)
+    many = be.dist_all_pairs_many([bfs[:4], bfs[2:20], bfs[5:8]])
+    assert np.array_equal(many[0], want[:4, :4]) and np.array_equal(many[1], want[2:20, 2:20]) and np.array_equal(many[2], want[5:8, 5:8])
+    qb = be.query_positions_many(fas[:5])
+    hits = be.fetch_hits([be.query_hits_many(qb, [4, 1], bfs)])[0]
+    for r, q in enumerate([4, 1]):
+        assert [int(x) for x in hits[r]] == [int(x) for x in oracle.query_hits(oracle.positions_distinct(open(fas[q], "rb").read(), k, num_bits), flt)]
+    assert be.query_totals(qb) == [len(oracle.positions_distinct(open(f, "rb").read(), k, num_bits)) for f in fas[:5]]
+    assert len(be._cache) <= 12

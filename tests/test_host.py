@@ -140,3 +140,46 @@ def test_context_requires_gpu():
     from metasbt_b200 import ops
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         ops.Context(0)
+
+
+@pytest.mark.parametrize("num_bits", [64, 1000, 4096 * 64, 4096 * 64 + 1, (1 << 20) + 77])
+def test_positions_expand_is_the_inverse_of_extraction(built, oracle, num_bits):
+    """Host side of the sparse filter transfer (msbt_positions_expand): positions -> the oracle's filter words."""
+    from metasbt_b200 import ops
+    rng = random.Random(num_bits)
+    fa = util.messy_fasta(rng, 3, 4000, "ACGTN")
+    want = oracle.makebf(fa, 21, num_bits)
+    pos = oracle.positions_distinct(fa, 21, num_bits).astype(np.uint32)
+    out = np.full(len(want) + 3, 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)  # stale content must be overwritten, the tail left alone
+    ops.positions_expand(pos, num_bits, out)
+    assert np.array_equal(out[: len(want)], want) and np.all(out[len(want):] == 0xFFFFFFFFFFFFFFFF)
+    ops.positions_expand(np.zeros(0, dtype=np.uint32), num_bits, out)
+    assert not out[: len(want)].any()
+    with pytest.raises(ValueError):  # beyond the filter
+        ops.positions_expand(np.array([num_bits], dtype=np.uint32), num_bits, out)
+    if len(pos) > 2 and pos[-1] >= 4096 * 64:
+        with pytest.raises(ValueError):  # not ascending across blocks
+            ops.positions_expand(pos[::-1].copy(), num_bits, out)
+
+
+def test_numa_helpers():
+    from metasbt_b200 import numa
+    assert numa._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert numa._parse_cpulist("") == []
+    info = numa.bind_to_gpu_node(0)  # no GPU here: nothing is bound, nothing raises
+    assert info["bound"] in (False, True)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours) on a tiny configuration."""
+    import json
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--genome-bp", "20000", "--filter-bits", str(1 << 20), "--cpu-genomes", "4"],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mbp/s" and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0

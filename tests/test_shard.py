@@ -73,6 +73,28 @@ def _worker(rank, world, port, tmp):
         hits = torch.from_numpy(O.query_hits(sel, full).astype(np.int64))
         shard.all_reduce_counts(hits)
         assert hits.tolist() == [int(x) for x in O.query_hits(pos, full)]
+        # K4 with the hashing sharded too (shard.query_exchange_sharded's host plan): every rank "hashes" its block of the
+        # query batch, positions travel to the rank that owns their bit range, partial hits are summed
+        queries = [fastas[g] for g in (3, 0, 5, 6, 1)]
+        qb, qe = shard.query_blocks(len(queries), world)[rank]
+        ranges = shard.bit_ranges(bits, world)
+        local = [O.positions_distinct(q, k, bits) for q in queries[qb:qe]]
+        counts = [[int(((p >= b0) & (p < e0)).sum()) for (b0, e0) in ranges] for p in local]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, counts)
+        send_sizes, recv_sizes, q_ranges = shard.exchange_plan(gathered, rank)
+        send = [torch.from_numpy(np.concatenate([p[(p >= b0) & (p < e0)] - np.uint64(b0) for p in local] + [np.zeros(0, np.uint64)]).astype(np.int64))
+                for (b0, e0) in ranges]
+        assert [len(t) for t in send] == send_sizes
+        recv = [torch.empty(n, dtype=torch.int64) for n in recv_sizes]
+        shard._all_to_all_gloo(recv, send, None)
+        flat = torch.cat(recv).numpy().astype(np.uint64)
+        assert len(q_ranges) == len(queries) and q_ranges[-1][1] == len(flat)
+        rows = [f[rb // 64: re_ // 64] for f in full]
+        part = np.stack([O.query_hits(flat[b0:e0], rows) for b0, e0 in q_ranges]).astype(np.int64)
+        hits = torch.from_numpy(part)
+        shard.all_reduce_counts(hits)
+        assert np.array_equal(hits.numpy().astype(np.uint64), np.stack([O.query_hits(O.positions_distinct(q, k, bits), full) for q in queries]))
         open(os.path.join(tmp, "ok%d" % rank), "w").close()
     finally:
         dist.destroy_process_group()
@@ -82,3 +104,16 @@ def _worker(rank, world, port, tmp):
 def test_partition_and_merge_under_gloo(tmp_path, oracle, world):
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
+
+
+def test_query_blocks_and_exchange_plan():
+    for n in (0, 1, 5, 256):
+        for world in (1, 2, 3, 8):
+            blocks = shard.query_blocks(n, world)
+            assert [i for b, e in blocks for i in range(b, e)] == list(range(n))
+    # two ranks, rank 0 hashed 2 MAGs, rank 1 hashed 1; counts[s][q][d]
+    counts = [[[3, 4], [5, 0]], [[1, 2]]]
+    send, recv, ranges = shard.exchange_plan(counts, 0)
+    assert send == [8, 4] and recv == [8, 1] and ranges == [(0, 3), (3, 8), (8, 9)]
+    send, recv, ranges = shard.exchange_plan(counts, 1)
+    assert send == [1, 2] and recv == [4, 2] and ranges == [(0, 4), (4, 4), (4, 6)]

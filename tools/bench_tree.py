@@ -124,7 +124,7 @@ def main():
             level = nxt
             all_levels.append(level)
         partial = level[0] if len(level) == 1 else ctx.bf_or(level, m)   # this rank's share of the kingdom
-        kingdom = shard.or_merge(partial[:ops.filter_words(m)].contiguous(), m)
+        kingdom = shard.or_merge(partial[:ops.filter_words(m)].contiguous(), m, ctx=ctx)
         all_levels.append([kingdom])
         return all_levels, n_union + 1, n_in + len(level)
 
