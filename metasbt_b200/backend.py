@@ -350,7 +350,8 @@ class CudaBackend:
             cap = min(sum(len(t) for t in texts), len(texts) * self.num_bits)
             pos, offs = self.ctx.extract_positions_packed([filt[i] for i in range(len(texts))], self.num_bits, cap=max(cap, 1))
             chunks.append(pos[: offs[-1]])
-            offsets.extend(offsets[-1] + o for o in offs[1:])
+            base = offsets[-1]
+            offsets.extend(base + o for o in offs[1:])
         if not chunks:
             return QueryBatch(torch.zeros(1, dtype=torch.int32, device=self.ctx.device), [0])
         positions = chunks[0] if len(chunks) == 1 else torch.cat(chunks)
