@@ -7,8 +7,8 @@ What is deliberately different from the reference CLI:
   release lookup (metasbt.py:100-121): none of those programs is used by this path;
 * the per-genome loops (metasbt.py:542-543, 1231-1242) and the `mp.Pool` fan-out (metasbt.py:1124-1143)
   are batch calls: forking after CUDA initialisation is not possible and not needed;
-* `--dereplicate`, `--completeness`, `--contamination`, `--pack` are parsed for compatibility and
-  rejected when they would do something (they belong to subsystems outside SURVEY.md 8).
+* `--completeness`, `--contamination`, `--pack` are parsed for compatibility and rejected when they would do
+  something (they belong to subsystems outside SURVEY.md 8).
 """
 
 from __future__ import annotations
@@ -94,8 +94,6 @@ class MetaSBT(object):
             raise Exception(f"A database named '{args.database}' already exist under {args.workdir}")
         if args.completeness > 0.0 or args.contamination < 100.0:
             raise NotImplementedError("quality control (checkm/checkv/busco) is outside the B200 hot path")
-        if args.dereplicate > 0.0:
-            raise NotImplementedError("--dereplicate is outside the B200 hot path in this version")
         if args.pack:
             raise NotImplementedError("--pack (tar + sha256sum) is outside the B200 hot path")
         tmp_dir = os.path.join(args.workdir, "tmp")
@@ -113,6 +111,10 @@ class MetaSBT(object):
         self.database.set_configs(genomes, min_kmer_occurrence=args.min_kmer_occurrences, kmer_size=args.kmer_size,
                                   kmer_max=args.limit_kmer_size, filter_size=args.filter_size,
                                   filter_expand_by=args.increase_filter_size)
+        if args.dereplicate > 0.0:
+            # metasbt.py:533-535: input genomes against themselves (one all-pairs launch)
+            kept = self.database.dereplicate(set(genomes), threshold=args.dereplicate)
+            genomes = [genome for genome in genomes if genome in kept]
         self.database.add_many([(genome, True, references[genome]) for genome in genomes])
         self.database.update()
 
@@ -170,14 +172,20 @@ class MetaSBT(object):
         args = parser.parse_args(argv)
         if args.completeness > 0.0 or args.contamination < 100.0:
             raise NotImplementedError("quality control (checkm/checkv/busco) is outside the B200 hot path")
-        if args.dereplicate > 0.0:
-            raise NotImplementedError("--dereplicate is outside the B200 hot path in this version")
         if args.pack:
             raise NotImplementedError("--pack (tar + sha256sum) is outside the B200 hot path")
         # the reference holds the paths in a set (metasbt.py:1845): sorted here, so runs are reproducible
         genomes = sorted(set(self._open(args)))
+        if args.dereplicate > 0.0:
+            # metasbt.py:1858-1862: the input genomes against themselves first
+            kept = self.database.dereplicate(set(genomes), threshold=args.dereplicate)
+            genomes = [genome for genome in genomes if genome in kept]
         # profiles (and sketches) first: is_known / add read the memoised tables (metasbt.py:1866)
         self.profile(argv, parse_known_args=True)
+        if args.dereplicate > 0.0:
+            # metasbt.py:1870-1872: ... then against the genomes of the database
+            kept = self.database.dereplicate(set(genomes), threshold=args.dereplicate, compare_with="database")
+            genomes = [genome for genome in genomes if genome in kept]
         species_assignments = self.database.is_known_many(genomes)
         self.database.add_many([(genome, False, species_assignments[genome]) for genome in genomes])
         characterized, unassigned = dict(), set()

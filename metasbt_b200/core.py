@@ -6,8 +6,9 @@ update, dist, profile}, Entry.{sketch, index, get_density, get_boundaries, get_c
 get_full_taxonomy, is_known, add_children} -- with the same signatures, exceptions, on-disk layout
 and result files (`clusters.tsv`, `genomes.tsv`, `metadata.json`, `<name>.txt`,
 `tree/index.detbrief.sbt`, `tmp/profiles/<genome>.txt`) as /root/reference/metasbt/core.py.
-Out of scope and raising NotImplementedError: kitsune/ntcard estimation (pass --kmer-size and
---filter-size), flat=False trees (howdesbt cluster/build), qc/dereplicate/merge/remove.
+flat=False databases get their tree topology from cluster.py (`howdesbt cluster`: greedy Hamming agglomeration over
+K3 / K2) with plain union nodes; the determined/brief RRR node files of `howdesbt build --howde` are out of scope.
+Out of scope and raising NotImplementedError: kitsune k-mer size estimation (pass --kmer-size), qc/merge/remove.
 The `update` consumers of the same kernels (is_known, characterize, _estimate_boundaries) are included.
 
 Differences that are deliberate (documented in DESIGN.md):
@@ -91,8 +92,6 @@ class Database(object):
 
         if not os.path.isdir(self.root):
             # new database (core.py:134-158)
-            if not flat:
-                raise NotImplementedError("flat=False (howdesbt cluster/build trees) is outside the B200 hot path")
             self.flat = flat
             os.makedirs(self.root)
             os.makedirs(os.path.join(self.root, "clusters"))
@@ -117,8 +116,6 @@ class Database(object):
             if not self._validate_metadata(self.metadata):
                 raise Exception("Database metadata did not pass the validation!")
             self.flat = self.metadata["flat"]
-            if not self.flat:
-                raise NotImplementedError("flat=False databases are outside the B200 hot path")
             report_filepath = os.path.join(self.root, "clusters.tsv")
             if not os.path.isfile(report_filepath):
                 raise FileNotFoundError(errno.ENOENT, os.strerror(errno.ENOENT), report_filepath)
@@ -457,14 +454,12 @@ class Database(object):
 
     @staticmethod
     def _tree_leaves(tree_filepath: str) -> List[str]:
-        """Leaf filter paths of a flat `index.detbrief.sbt` (core.py:3870-3875: root line, then one `*`-prefixed line per leaf)."""
-        leaves = []
-        with open(tree_filepath) as handle:
-            for line in handle:
-                line = line.strip()
-                if line.startswith("*"):
-                    leaves.append(line.lstrip("*"))
-        return leaves
+        """Leaf filter paths of an `index.detbrief.sbt`: the nodes without children.  Flat trees (core.py:3870-3875) have
+        the cluster's own filter as root and one `*`-prefixed line per leaf; clustered trees (flat=False, cluster.py) nest
+        deeper.  `howdesbt query` reports leaves only, and with union nodes above them the internal nodes never change a
+        leaf's hit count -- so every tree is probed as the flat list of its leaves."""
+        from . import cluster
+        return cluster.topology_leaves(cluster.read_topology(tree_filepath))
 
     @staticmethod
     def _tree_matches(leaves: Sequence[str], hits: Sequence[int], total: int, threshold: float) -> "OrderedDict[str, Tuple[int, int]]":
@@ -665,7 +660,48 @@ class Database(object):
     def _unsupported(self, *a, **k):
         raise NotImplementedError("outside the B200 hot path (SURVEY.md 8: index / profile only)")
 
-    qc = dereplicate = merge = remove = cluster = _unsupported
+    qc = merge = remove = cluster = _unsupported
+
+    # ------------------------------------------------------------------ dereplicate (core.py:2535-2741)
+    def dereplicate(self, genomes: Set[str], threshold: float = 0.01, compare_with: str = "self") -> Set[str]:
+        """Drop input genomes that have a replica (ANI distance <= threshold) among the input genomes ("self") or in the
+        database ("database").  "self": ONE all-pairs AND-popcount launch over the input sketches instead of a pool of
+        `dist` jobs (core.py:2611-2640); "database": one profile_many batch with uncertainty 1.0 (core.py:2660-2700), whose
+        genome level names the closest genome and its distance.
+
+        The reference cannot get past its last loop once a replica exists (core.py:2735 indexes `replicas`, which is keyed
+        by genome NAME, with a file PATH, and :2689 reads the profile with the bare genome name where the key is the full
+        label): what is implemented here is what that code sets out to do -- walking the genomes in input order, a genome
+        that has not been excluded excludes all of its replicas."""
+        if not genomes:
+            raise Exception("There are no genomes to dereplicate!")
+        if threshold < 0.0 or threshold >= 1.0:
+            raise ValueError("The ANI threshold must be >0.0 and <1.0!")
+        if compare_with not in ["self", "database"]:
+            raise ValueError("The dereplication can be performed against the input itself or the genomes in the database!")
+        ordered = sorted(genomes)  # the reference iterates the input set (hash order)
+        names = [os.path.splitext(os.path.basename(path))[0] for path in ordered]
+        entries = [Entry(self, name, name, "genome") for name in names]
+        sketches = Entry.sketch_many(entries, ordered)
+        excluded: Set[str] = set()
+        if compare_with == "self":
+            if len(sketches) > 1:
+                inter = self.backend.dist_all_pairs(sketches)
+                k = self.metadata["kmer_size"]
+                for i, path in enumerate(ordered):
+                    if path in excluded:
+                        continue
+                    for j in range(i + 1, len(ordered)):
+                        union = int(inter[i][i]) + int(inter[j][j]) - int(inter[i][j])
+                        if ani_distance(int(inter[i][j]), union, k) <= threshold:
+                            excluded.add(ordered[j])
+        else:
+            tables = self.profile_many(ordered, sketches, uncertainty=1.0, pruning_threshold=0.0)
+            for path, table in zip(ordered, tables):
+                closest = list(table["genome"].keys())[0]
+                if table["genome"][closest] <= threshold:
+                    excluded.add(path)
+        return set(genomes).difference(excluded)
 
     # ------------------------------------------------------------------ N2: the `update` consumers of K1/K3/K4
     @staticmethod
@@ -1013,8 +1049,6 @@ class Entry(object):
             raise Exception("Genome entries cannot be indexed!")
         if not self.children:
             raise Exception("This entry is empty!")
-        if not db.flat:
-            raise NotImplementedError("flat=False (howdesbt cluster/build) is outside the B200 hot path")
         if os.path.isdir(self.folder):
             shutil.rmtree(os.path.join(self.folder, "tree"), ignore_errors=True)
             os.makedirs(os.path.join(self.folder, "tree"), exist_ok=True)
@@ -1035,10 +1069,19 @@ class Entry(object):
             db.backend.copy(ordered[0], target)
         else:
             db.backend.union(ordered, target)
-        with open(os.path.join(self.folder, "tree", "index.detbrief.sbt"), "w+") as flat_tree:
-            flat_tree.write(f"{target}\n")
-            for path in ordered:
-                flat_tree.write(f"*{path}\n")
+        index_filepath = os.path.join(self.folder, "tree", "index.detbrief.sbt")
+        if db.flat:
+            with open(index_filepath, "w+") as flat_tree:
+                flat_tree.write(f"{target}\n")
+                for path in ordered:
+                    flat_tree.write(f"*{path}\n")
+        else:
+            # howdesbt cluster --list --bits=<filter size> --tree=union.sbt --nodename=tree/node{number} --keepallnodes
+            # (core.py:3800-3808) followed by howdesbt build (core.py:3822-3828): greedy Hamming agglomeration over
+            # K3 / K2 (cluster.py); the internal nodes are plain union filters, not determined/brief RRR files (N4)
+            from . import cluster
+            topology = cluster.cluster_tree(db.backend, ordered, os.path.join(self.folder, "tree", "node{number}"))
+            cluster.write_topology(index_filepath, topology)
         self.sketch_filepath = target
 
     # ------------------------------------------------------------------ K3': density (core.py:3576-3607)

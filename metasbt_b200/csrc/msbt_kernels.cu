@@ -17,6 +17,7 @@
 #include <stdio.h>
 #include <math.h>
 #include <string.h>
+#include <emmintrin.h>
 
 #include <algorithm>
 #include <vector>
@@ -2143,22 +2144,29 @@ extern "C" int msbt_bf_and_popcount_allpairs(msbt_ctx *ctx, const uint64_t *cons
 extern "C" int msbt_positions_expand(const uint32_t *positions, uint64_t n, uint64_t num_bits, uint64_t *words) {
     if (!words || (n && !positions)) return MSBT_EINVAL;
     const uint64_t n_words = (num_bits + 63) / 64;
-    constexpr uint64_t BLOCK = 4096;  // words
-    uint64_t i = 0;
+    constexpr uint64_t BLOCK = 4096;  // words: one 32 KiB block is assembled in an L1-resident scratch buffer ...
+    alignas(64) uint64_t scratch[BLOCK];
+    const bool stream_out = (((uintptr_t)words) & 15) == 0;  // ... and leaves with non-temporal stores (no read-for-ownership:
+    uint64_t i = 0;                                           // the host memory traffic is the filter's size, written once)
     for (uint64_t w0 = 0; w0 < n_words; w0 += BLOCK) {
-        const uint64_t w1 = std::min(n_words, w0 + BLOCK);
-        memset(words + w0, 0, (w1 - w0) * 8);
+        const uint64_t w1 = std::min(n_words, w0 + BLOCK), nw = w1 - w0;
+        memset(scratch, 0, nw * 8);
         const uint64_t bit_end = w1 * 64;
         while (i < n && positions[i] < bit_end) {
             const uint64_t p = positions[i++];
             if (p < w0 * 64) return MSBT_EINVAL;  // not ascending
-            words[p >> 6] |= 1ull << (p & 63);
+            scratch[(p >> 6) - w0] |= 1ull << (p & 63);
         }
+        uint64_t *dst = words + w0;
+        uint64_t k = 0;
+        if (stream_out) {
+            for (; k + 2 <= nw; k += 2) _mm_stream_si128((__m128i *)(dst + k), _mm_load_si128((const __m128i *)(scratch + k)));
+        }
+        for (; k < nw; k++) dst[k] = scratch[k];
     }
-    if (i != n) return MSBT_EINVAL;  // a position beyond num_bits
-    if (n && num_bits & 63) {
-        if (positions[n - 1] >= num_bits) return MSBT_EINVAL;
-    }
+    _mm_sfence();
+    if (i != n) return MSBT_EINVAL;  // a position beyond the last word
+    if (n && (num_bits & 63) && positions[n - 1] >= num_bits) return MSBT_EINVAL;
     return MSBT_OK;
 }
 

@@ -174,6 +174,40 @@ def ani_distance(intersect: int, union: int, kmer_size: int) -> float:
     return 1.0 if d > 1.0 else d
 
 
+def cluster_topology(filters: Sequence[np.ndarray]) -> List[Tuple[int, int]]:
+    """howdesbt cluster --bits=<all> --keepallnodes (core.py:3800-3808), brute force: while more than one
+    node is active, recompute ALL pairwise Hamming distances between active nodes, merge the closest pair (ties: smaller
+    node ids; leaves are 0..n-1, new nodes follow in creation order) into their OR.  -> [(depth, node id)] in pre-order,
+    first child = the lower id of a merged pair.  Tie-breaking and numbering are UNPINNED (no howdesbt binary)."""
+    nodes = {i: np.asarray(f, dtype=np.uint64) for i, f in enumerate(filters)}
+    n = len(nodes)
+    if n == 0:
+        return []
+    children = {}
+    nxt = n
+    while len(nodes) > 1:
+        ids = sorted(nodes)
+        best = None
+        for a in range(len(ids)):
+            for b in range(a + 1, len(ids)):
+                d = bf_popcount(np.bitwise_xor(nodes[ids[a]], nodes[ids[b]]))
+                if best is None or (d, ids[a], ids[b]) < best:
+                    best = (d, ids[a], ids[b])
+        _, u, v = best
+        nodes[nxt] = np.bitwise_or(nodes.pop(u), nodes.pop(v))
+        children[nxt] = (u, v)
+        nxt += 1
+    out: List[Tuple[int, int]] = []
+
+    def walk(node: int, depth: int) -> None:
+        out.append((depth, node))
+        if node in children:
+            walk(children[node][0], depth + 1)
+            walk(children[node][1], depth + 1)
+    walk(next(iter(nodes)), 0)
+    return out
+
+
 # ------------------------------------------------------------------ pure-Python twin (tiny cases)
 
 

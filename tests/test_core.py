@@ -111,7 +111,7 @@ def test_cli_rejects_what_is_out_of_scope(tmp_path):
     base = ["index", "--workdir", str(tmp_path / "w"), "--database", "db", "--references", refs, "--kmer-size", "31",
             "--filter-size", "4096"]
     with pytest.raises(NotImplementedError):
-        cli.MetaSBT(base + ["--dereplicate", "0.01"], backend=object())
+        cli.MetaSBT(base + ["--pack"], backend=object())
     with pytest.raises(NotImplementedError):
         cli.MetaSBT(["index", "--workdir", str(tmp_path / "w2"), "--database", "db", "--references", refs,
                      "--filter-size", "4096"], backend=object())  # k-mer size estimation = kitsune

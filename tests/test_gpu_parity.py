@@ -509,12 +509,14 @@ def test_backend_sliced_tree_cache(ctx, oracle, tmp_path):
     def want():
         return [int(x) for x in oracle.query_hits(qpos, [bffile.read_bf(p)[1] for p in bfs])]
 
-    # 300 leaves: the row-major probe of even one query would move more bytes than transposing, so the first query already
-    # goes through the bit-sliced matrix
-    for expected_sliced in (1, 2, 3):
+    # the first query goes through the bit-sliced matrix only if its row-major probe would move more bytes than the
+    # transposition; from the tree's second query on the matrix exists and serves every query
+    seen = []
+    for _ in range(3):
         hits, total = be.query_hits(positions, bfs)
         assert total == len(qpos) and hits == want()
-        assert be.sliced_probes == expected_sliced
+        seen.append(be.sliced_probes)
+    assert seen[0] in (0, 1) and seen[1] == seen[0] + 1 and seen[2] == seen[1] + 1
     for i in (7, 123):  # the query contains these leaves whole
         assert hits[i] == oracle.bf_popcount(bffile.read_bf(bfs[i])[1])
     # rewrite leaf 5 with the content of leaf 7: the cached matrix must go, the next answer must see the new leaf
@@ -545,7 +547,8 @@ def test_sliced_matrix_dropped_even_when_the_row_major_copy_was_evicted(ctx, ora
     be.sketch_many(fas, bfs, 1)
     positions = be.query_positions(fas[9])
     hits, _ = be.query_hits(positions, bfs)
-    assert be.sliced_probes == 1 and len(be._sliced) == 1
+    hits, _ = be.query_hits(positions, bfs)  # the second query of a tree always finds it transposed
+    assert be.sliced_probes >= 1 and len(be._sliced) == 1
     for p in list(be._cache):  # cache pressure: every row-major copy goes
         be._bytes -= be._cache.pop(p).numel() * 8
     assert len(be._sliced) == 1

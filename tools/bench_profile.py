@@ -28,7 +28,9 @@ def run(ctx, species: int = 128, per_species: int = 4, genome_bp: int = 200_000,
         mag_bp: int = 100_000, single_sample: int = 32, workdir: str = None):
     import torch
     from metasbt_b200 import cli, core, synth
+    from metasbt_b200 import ops
     dev = ctx.device
+    ctx = ops.default_context(dev.index)  # the context the Database's backend launches on (bench.py holds its own)
     own = workdir is None
     workdir = workdir or tempfile.mkdtemp(prefix="msbt_profile_bench_")
     try:
