@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define MSBT_ABI_VERSION 1
+#define MSBT_ABI_VERSION 2
 
 #define MSBT_OK 0
 #define MSBT_EINVAL (-22)  /* bad argument */
@@ -34,8 +34,32 @@ extern "C" {
 
 typedef struct msbt_ctx msbt_ctx;
 
-/* One context per GPU per host thread.  Owns library scratch (tile tables, counters). */
-int msbt_ctx_create(int device, msbt_ctx **out);
+/* Everything this path takes from HowDeSBT rather than from MetaSBT and that could not be pinned against a real
+ * `howdesbt` binary (the binary and its sources are not part of the reference tree), as DATA: a context
+ * created with another spec hashes, canonicalises and labels files that way without a rebuild -- the day a binary is at
+ * hand, re-pinning is a configuration change (tests/pin_against_howdesbt.py finds the matching spec).  The default
+ * (msbt_hash_spec_default) is App. A as written; it is the one the tuned K1 kernels have compiled in, any other spec is
+ * served by a generic K1 kernel (min_abund >= 2 needs the default).  The oracle mirrors the same switches. */
+#define MSBT_KEY_BYTES_CEIL_QUARTER 0u /* key = the low (k+3)/4 bytes of the packed canonical k-mer (default) */
+#define MSBT_KEY_BYTES_WHOLE_WORDS 1u  /* key = whole 64-bit words: 8 bytes for k <= 32, 16 beyond */
+#define MSBT_CANONICAL_MIN_FIRST_BASE_MSB 0u /* min(k-mer, reverse complement) as integers, first base most significant (default) */
+#define MSBT_CANONICAL_FORWARD_ONLY 1u       /* the k-mer as read, no reverse complement */
+typedef struct msbt_hash_spec {
+    uint32_t struct_size;    /* sizeof(msbt_hash_spec), for forward compatibility */
+    uint32_t key_bytes;      /* MSBT_KEY_BYTES_* : how many bytes of the packed k-mer MurmurHash3_x64_128 digests */
+    uint32_t digest_half;    /* 0 = first 64 bits of the 128-bit digest (default), 1 = second */
+    uint32_t canonical;      /* MSBT_CANONICAL_* */
+    uint64_t bf_magic;       /* `.bf` header constants (App. A2); carried for the host-side file writer */
+    uint32_t bf_version;
+    uint32_t bf_header_size;
+} msbt_hash_spec;
+void msbt_hash_spec_default(msbt_hash_spec *spec);
+
+/* One context per GPU per host thread.  Owns library scratch (tile tables, counters).  spec == NULL: the default spec.
+ * A context must be driven from one stream at a time (its scratch and staging buffers are shared by its calls); every
+ * entry point runs on the context's device and restores the caller's current device before it returns. */
+int msbt_ctx_create(int device, const msbt_hash_spec *spec, msbt_ctx **out);
+int msbt_ctx_get_spec(const msbt_ctx *ctx, msbt_hash_spec *out);
 void msbt_ctx_destroy(msbt_ctx *ctx);
 const char *msbt_last_error(const msbt_ctx *ctx);
 int msbt_abi_version(void);

@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 
 # every symbol include/msbt.h declares; tests check that the library exports all of them
 SYMBOLS = [
-    "msbt_abi_version", "msbt_ctx_create", "msbt_ctx_destroy", "msbt_last_error", "msbt_sync",
+    "msbt_abi_version", "msbt_hash_spec_default", "msbt_ctx_create", "msbt_ctx_get_spec", "msbt_ctx_destroy", "msbt_last_error", "msbt_sync",
     "msbt_launch_count", "msbt_fasta_pack", "msbt_fasta_pack_device", "msbt_kmer_bloom_build", "msbt_bf_or_reduce",
     "msbt_bf_popcount", "msbt_bf_and_popcount_1vN", "msbt_bf_and_popcount_pairs", "msbt_bf_and_popcount_allpairs",
     "msbt_query_batch_ranges", "msbt_query_batch_sliced_ranges", "msbt_positions_expand",
@@ -45,6 +45,19 @@ class GenomeDesc(ctypes.Structure):
         ("run_off", ctypes.c_uint64),
         ("n_runs", ctypes.c_uint32),
         ("filter_index", ctypes.c_uint32),
+    ]
+
+
+class HashSpecStruct(ctypes.Structure):
+    """msbt_hash_spec"""
+    _fields_ = [
+        ("struct_size", ctypes.c_uint32),
+        ("key_bytes", ctypes.c_uint32),
+        ("digest_half", ctypes.c_uint32),
+        ("canonical", ctypes.c_uint32),
+        ("bf_magic", ctypes.c_uint64),
+        ("bf_version", ctypes.c_uint32),
+        ("bf_header_size", ctypes.c_uint32),
     ]
 
 
@@ -82,8 +95,12 @@ def lib() -> ctypes.CDLL:
     P = ctypes.POINTER
     L.msbt_abi_version.argtypes = []
     L.msbt_abi_version.restype = i32
-    L.msbt_ctx_create.argtypes = [i32, P(vp)]
+    L.msbt_hash_spec_default.argtypes = [P(HashSpecStruct)]
+    L.msbt_hash_spec_default.restype = None
+    L.msbt_ctx_create.argtypes = [i32, P(HashSpecStruct), P(vp)]
     L.msbt_ctx_create.restype = i32
+    L.msbt_ctx_get_spec.argtypes = [vp, P(HashSpecStruct)]
+    L.msbt_ctx_get_spec.restype = i32
     L.msbt_ctx_destroy.argtypes = [vp]
     L.msbt_ctx_destroy.restype = None
     L.msbt_last_error.argtypes = [vp]

@@ -38,6 +38,29 @@ _HDR = struct.Struct("<QIIIIIIQQQQIIQIIQQQ")  # 0x70 bytes
 assert _HDR.size == BF_HEADER_SIZE
 
 
+def configure(magic: Optional[int] = None, version: Optional[int] = None) -> None:
+    """Re-pin the unpinned header constants (ops.HashSpec.bf_magic / bf_version, e.g. from MSBT_HASH_SPEC) without
+    touching the code: files are written with, and expected to carry, these values from now on."""
+    global BF_MAGIC, BF_VERSION
+    if magic is not None:
+        BF_MAGIC = int(magic)
+    if version is not None:
+        BF_VERSION = int(version)
+
+
+def _configure_from_env() -> None:
+    text = os.environ.get("MSBT_HASH_SPEC", "")
+    for item in text.split(","):
+        key, _, value = item.partition("=")
+        if key.strip() == "bf_magic":
+            configure(magic=int(value, 0))
+        elif key.strip() == "bf_version":
+            configure(version=int(value, 0))
+
+
+_configure_from_env()
+
+
 @dataclass
 class BloomHeader:
     kmer_size: int

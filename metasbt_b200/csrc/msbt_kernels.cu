@@ -41,6 +41,8 @@ struct msbt_ctx {
     size_t stage_bytes;
     cudaEvent_t stage_free;  // recorded after the last H2D that read h_stage
     bool stage_busy;
+    msbt_hash_spec spec;
+    bool spec_is_default;
     bool tiled_attr_set;  // dynamic-smem opt-in done for this device
     bool fused_attr_set;
     bool phased_attr_set;
@@ -139,13 +141,39 @@ static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; 
 
 extern "C" int msbt_abi_version(void) { return MSBT_ABI_VERSION; }
 
-extern "C" int msbt_ctx_create(int device, msbt_ctx **out) {
+extern "C" void msbt_hash_spec_default(msbt_hash_spec *spec) {
+    if (!spec) return;
+    memset(spec, 0, sizeof(*spec));
+    spec->struct_size = (uint32_t)sizeof(*spec);
+    spec->key_bytes = MSBT_KEY_BYTES_CEIL_QUARTER;
+    spec->digest_half = 0;
+    spec->canonical = MSBT_CANONICAL_MIN_FIRST_BASE_MSB;
+    spec->bf_magic = MSBT_BF_MAGIC;
+    spec->bf_version = MSBT_BF_VERSION;
+    spec->bf_header_size = MSBT_BF_HEADER_SIZE;
+}
+
+extern "C" int msbt_ctx_get_spec(const msbt_ctx *ctx, msbt_hash_spec *out) {
+    if (!ctx || !out) return MSBT_EINVAL;
+    *out = ctx->spec;
+    return MSBT_OK;
+}
+
+extern "C" int msbt_ctx_create(int device, const msbt_hash_spec *spec, msbt_ctx **out) {
     if (!out) return MSBT_EINVAL;
     *out = nullptr;
+    if (spec && (spec->struct_size != sizeof(msbt_hash_spec) || spec->key_bytes > 1 || spec->digest_half > 1 || spec->canonical > 1)) {
+        fprintf(stderr, "msbt_ctx_create: invalid msbt_hash_spec\n");
+        return MSBT_EINVAL;
+    }
     msbt_ctx *ctx = new (std::nothrow) msbt_ctx();
     if (!ctx) return MSBT_ENOMEM;
     memset(ctx, 0, sizeof(*ctx));
     ctx->device = device;
+    msbt_hash_spec_default(&ctx->spec);
+    if (spec) ctx->spec = *spec;
+    ctx->spec_is_default = ctx->spec.key_bytes == MSBT_KEY_BYTES_CEIL_QUARTER && ctx->spec.digest_half == 0 &&
+                           ctx->spec.canonical == MSBT_CANONICAL_MIN_FIRST_BASE_MSB;
     DeviceGuard guard;
     cudaError_t e = guard.enter(device);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -350,6 +378,38 @@ kmer_bloom_direct_kernel(const uint64_t *__restrict__ packed, const uint32_t *__
             MSBT_DIRECT_STEP(0) MSBT_DIRECT_STEP(1) MSBT_DIRECT_STEP(2) MSBT_DIRECT_STEP(3)
             MSBT_DIRECT_STEP(4) MSBT_DIRECT_STEP(5) MSBT_DIRECT_STEP(6) MSBT_DIRECT_STEP(7)
             kb.advance8();
+        }
+    }
+}
+
+// Generic K1 kernel for contexts with a non-default msbt_hash_spec: the direct kernel's structure (memset + one RED per
+// k-mer) with the key length, the digest half and the canonical rule as run-time arguments.  Correctness path for
+// re-pinning against a real howdesbt; the tuned kernels keep the default spec compiled in.
+template <int KW>
+__global__ void __launch_bounds__(TILE_THREADS, 4)
+kmer_bloom_generic_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ run_ends,
+                          const DevGenome *__restrict__ genomes, uint32_t n_genomes, uint32_t n_tiles, KmerSpec spec,
+                          uint32_t key_len, uint32_t second_half, uint32_t forward_only, uint32_t *__restrict__ filters) {
+    const uint32_t k = spec.k;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const DevGenome g = genomes[find_genome(genomes, n_genomes, tile)];
+        const uint32_t w = (tile - g.tile_begin) * TILE_THREADS + threadIdx.x;
+        const uint32_t s0 = w * 32;
+        if (s0 >= g.n_bases) continue;
+        const uint32_t vm = valid_mask(run_ends + g.run_off, g.n_runs, s0, k);
+        if (vm == 0) continue;
+        KmerWalker<KW> kw;
+        kw.init(packed + g.packed_word_off + w, k);
+        uint32_t *__restrict__ out = filters + 2 * g.filter_word_off;
+        for (uint32_t j = 0; j < 32; j++) {
+            if ((vm >> j) & 1u) {
+                uint64_t lo, hi;
+                if (forward_only) { lo = kw.fl; hi = kw.fh; }
+                else kw.canonical(lo, hi);
+                const uint64_t pos = msbt_position(msbt_kmer_hash_generic(lo, hi, key_len, spec.pos.seed, second_half), spec.pos);
+                if (pos < spec.pos.num_bits) atomicOr(out + (pos >> 5), 1u << (pos & 31));
+            }
+            kw.roll(j);
         }
     }
 }
@@ -1310,6 +1370,28 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
         tiles += (d.n_bases + TILE_BASES - 1) / TILE_BASES;
         max_bases = std::max<uint64_t>(max_bases, d.n_bases);
         if (tiles >> 31) return fail(ctx, MSBT_EINVAL, "batch too large (%llu tiles)", (unsigned long long)tiles);
+    }
+
+    if (!ctx->spec_is_default) {
+        // a re-pinned spec (msbt_hash_spec): the generic kernel, whatever variant was asked for
+        if (min_abund >= 2) return fail(ctx, MSBT_EINVAL, "min_abund >= 2 needs the default msbt_hash_spec in this version");
+        size_t table_bytes = 0;
+        int rc = stage_genome_table(ctx, dg, &table_bytes, stream);
+        if (rc) return rc;
+        for (uint32_t i = 0; i < n_genomes; i++)
+            CU_TRY(ctx, cudaMemsetAsync(d_filters + dg[i].filter_word_off, 0, words * 8, stream));
+        const uint32_t key_len = ctx->spec.key_bytes == MSBT_KEY_BYTES_WHOLE_WORDS ? (k <= 32 ? 8u : 16u) : (k + 3u) / 4u;
+        const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * 8);
+        if (k <= 32)
+            kmer_bloom_generic_kernel<1><<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, (const DevGenome *)ctx->d_scratch, n_genomes,
+                                                                          (uint32_t)tiles, spec, key_len, ctx->spec.digest_half,
+                                                                          ctx->spec.canonical, (uint32_t *)d_filters);
+        else
+            kmer_bloom_generic_kernel<2><<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, (const DevGenome *)ctx->d_scratch, n_genomes,
+                                                                          (uint32_t)tiles, spec, key_len, ctx->spec.digest_half,
+                                                                          ctx->spec.canonical, (uint32_t *)d_filters);
+        LAUNCH_CHECK(ctx);
+        return MSBT_OK;
     }
 
     // variant choice: the tiled path needs distinct output filters and u32 positions

@@ -79,6 +79,35 @@ MSBT_HD uint64_t msbt_kmer_hash(uint64_t lo, uint64_t hi, uint32_t k, uint32_t s
     return h1 + h2;
 }
 
+// The same digest with every HowDeSBT-side choice that is NOT pinned against a real binary as a run-time argument
+// (include/msbt.h: msbt_hash_spec): `len` = number of key bytes hashed (1..16), `second_half` = which 64-bit half of the
+// 128-bit digest is the hash value.  msbt_kmer_hash(lo, hi, k, seed) == msbt_kmer_hash_generic(lo, hi, (k+3)/4, seed, 0).
+// Used by the generic K1 kernel that serves contexts created with a non-default spec; the tuned kernels keep the
+// default compiled in.
+MSBT_HD uint64_t msbt_kmer_hash_generic(uint64_t lo, uint64_t hi, uint32_t len, uint32_t seed, uint32_t second_half) {
+    const uint64_t c1 = 0x87c37b91114253d5ULL, c2 = 0x4cf5ad432745937fULL;
+    uint64_t h1 = seed, h2 = seed;
+    uint64_t k1 = lo, k2 = hi;
+    // bytes beyond `len` do not belong to the key
+    if (len < 8) k1 &= (1ULL << (8 * len)) - 1;
+    if (len <= 8) k2 = 0;
+    else if (len < 16) k2 &= (1ULL << (8 * (len - 8))) - 1;
+    k1 *= c1; k1 = msbt_rotl64(k1, 31); k1 *= c2;
+    if (len > 8) { k2 *= c2; k2 = msbt_rotl64(k2, 33); k2 *= c1; }
+    if (len == 16) {
+        h1 ^= k1; h1 = msbt_rotl64(h1, 27); h1 += h2; h1 = h1 * 5 + 0x52dce729;
+        h2 ^= k2; h2 = msbt_rotl64(h2, 31); h2 += h1; h2 = h2 * 5 + 0x38495ab5;
+    } else {
+        if (len > 8) h2 ^= k2;
+        if (len > 0) h1 ^= k1;
+    }
+    h1 ^= len; h2 ^= len;
+    h1 += h2; h2 += h1;
+    h1 = msbt_fmix64(h1); h2 = msbt_fmix64(h2);
+    h1 += h2; h2 += h1;
+    return second_half ? h2 : h1;
+}
+
 // ---- position (A1): pos = h % modulus; the bit is set/probed only if pos < num_bits.
 // `magic` = floor((2^64-1)/modulus) lets the device replace the 64-bit division by one
 // multiply-high and one correction (exact, see msbt_mod_magic); power-of-two moduli mask.

@@ -27,6 +27,56 @@ from . import _lib
 WORD_BITS = 64
 
 
+@dataclass(frozen=True)
+class HashSpec:
+    """msbt_hash_spec (include/msbt.h): the HowDeSBT-side conventions that are not pinned against a real binary, as data.
+    The default is SURVEY.md App. A as written.  A different spec is a configuration change, not a rebuild:
+    pass it to Context(...) or set MSBT_HASH_SPEC, e.g. "key_bytes=words,digest_half=1,canonical=forward,bf_version=1"."""
+    key_bytes: str = "quarter"     # "quarter": (k+3)/4 bytes of the packed k-mer; "words": whole 64-bit words
+    digest_half: int = 0           # which 64-bit half of MurmurHash3_x64_128 is the hash value
+    canonical: str = "min"         # "min": min(k-mer, reverse complement), first base most significant; "forward": as read
+    bf_magic: int = 0xD532006662544253
+    bf_version: int = 2
+    bf_header_size: int = 0x70
+
+    @classmethod
+    def parse(cls, text: str) -> "HashSpec":
+        kw = {}
+        for item in filter(None, (t.strip() for t in text.split(","))):
+            key, _, value = item.partition("=")
+            key, value = key.strip(), value.strip()
+            if key in ("key_bytes", "canonical"):
+                kw[key] = value
+            elif key in ("digest_half", "bf_magic", "bf_version", "bf_header_size"):
+                kw[key] = int(value, 0)
+            else:
+                raise ValueError(f"MSBT_HASH_SPEC: unknown field {key!r}")
+        spec = cls(**kw)
+        spec.to_struct()
+        return spec
+
+    def to_struct(self) -> "_lib.HashSpecStruct":
+        if self.key_bytes not in ("quarter", "words") or self.canonical not in ("min", "forward") or self.digest_half not in (0, 1):
+            raise ValueError(f"invalid hash spec: {self}")
+        st = _lib.HashSpecStruct()
+        st.struct_size = ctypes.sizeof(_lib.HashSpecStruct)
+        st.key_bytes = 0 if self.key_bytes == "quarter" else 1
+        st.digest_half = self.digest_half
+        st.canonical = 0 if self.canonical == "min" else 1
+        st.bf_magic, st.bf_version, st.bf_header_size = self.bf_magic, self.bf_version, self.bf_header_size
+        return st
+
+    @property
+    def is_default(self) -> bool:
+        return self == HashSpec()
+
+
+def env_hash_spec() -> Optional[HashSpec]:
+    import os
+    text = os.environ.get("MSBT_HASH_SPEC", "").strip()
+    return HashSpec.parse(text) if text else None
+
+
 def filter_words(num_bits: int) -> int:
     return (num_bits + 63) // 64
 
@@ -181,7 +231,7 @@ def _ptr_array(tensors: Sequence[torch.Tensor]):
 class Context:
     """One msbt_ctx (one GPU).  All methods are asynchronous on torch's current stream."""
 
-    def __init__(self, device: int | torch.device | None = None):
+    def __init__(self, device: int | torch.device | None = None, spec: Optional[HashSpec] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("metasbt_b200 needs a CUDA device: the hot path has no CPU fallback")
         if device is None:
@@ -189,7 +239,9 @@ class Context:
         self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
         self._L = _lib.lib()
         h = ctypes.c_void_p()
-        rc = self._L.msbt_ctx_create(self.device.index or 0, ctypes.byref(h))
+        self.spec = spec if spec is not None else (env_hash_spec() or HashSpec())
+        st = self.spec.to_struct()
+        rc = self._L.msbt_ctx_create(self.device.index or 0, None if self.spec.is_default else ctypes.byref(st), ctypes.byref(h))
         if rc != 0:
             raise RuntimeError(f"msbt_ctx_create(device={self.device.index}) failed with code {rc}")
         self._h = h

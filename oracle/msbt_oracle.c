@@ -103,6 +103,15 @@ static void mer_build(const int8_t *codes, int k, mer128 *fwd, mer128 *rc) {
     *fwd = f; *rc = r;
 }
 
+/* The unpinned HowDeSBT-side choices as switches (the mirror of msbt_hash_spec in include/msbt.h; defaults = App. A):
+ * key length rule (0: (k+3)/4 bytes, 1: whole 8-byte words), digest half (0: first, 1: second),
+ * canonical rule (0: min of k-mer and reverse complement, 1: forward strand as read). */
+static int g_key_rule = 0, g_digest_half = 0, g_forward_only = 0;
+void orc_set_spec(int key_rule, int digest_half, int forward_only) {
+    g_key_rule = key_rule; g_digest_half = digest_half; g_forward_only = forward_only;
+}
+static int spec_is_default(void) { return g_key_rule == 0 && g_digest_half == 0 && g_forward_only == 0; }
+
 /* Hash of a canonical k-mer: MurmurHash3_x64_128 over its 2-bit packed little-endian
  * bytes (last base in the two lowest bits of byte 0), length (k+3)/4 bytes, first half. */
 static uint64_t mer_hash(mer128 m, int k, uint64_t seed) {
@@ -112,9 +121,12 @@ static uint64_t mer_hash(mer128 m, int k, uint64_t seed) {
         bytes[8 + b] = (uint8_t)(m.hi >> (8 * b));
     }
     uint64_t out[2];
-    orc_murmur3_x64_128(bytes, (k + 3) / 4, (uint32_t)seed, out);
-    return out[0];
+    const int len = g_key_rule ? (k <= 32 ? 8 : 16) : (k + 3) / 4;
+    orc_murmur3_x64_128(bytes, len, (uint32_t)seed, out);
+    return out[g_digest_half ? 1 : 0];
 }
+
+static inline mer128 mer_pick(mer128 f, mer128 r) { return (!g_forward_only && mer_less(r, f)) ? r : f; }
 
 /* Hash of one k-mer given as text; returns 0 and sets *ok=0 if it holds a non-ACGT char. */
 uint64_t orc_kmer_hash(const char *kmer, int k, uint64_t seed, int *ok) {
@@ -129,7 +141,7 @@ uint64_t orc_kmer_hash(const char *kmer, int k, uint64_t seed, int *ok) {
     mer128 f, r;
     mer_build(codes, k, &f, &r);
     *ok = 1;
-    return mer_hash(mer_less(r, f) ? r : f, k, seed);
+    return mer_hash(mer_pick(f, r), k, seed);
 }
 
 /* Canonical k-mers of a FASTA text, in file order.  Records start at '>' lines; sequence
@@ -166,7 +178,7 @@ static size_t fasta_canonical_mers(const char *text, size_t n, int k, mer128 **o
             mer128 f, r;
             mer_build(win, k, &f, &r);
             if (cnt == cap) { cap *= 2; mers = (mer128 *)realloc(mers, cap * sizeof(mer128)); }
-            mers[cnt++] = mer_less(r, f) ? r : f;
+            mers[cnt++] = mer_pick(f, r);
         }
     }
     free(win);
@@ -299,7 +311,7 @@ uint64_t orc_bf_or_popcount(const uint64_t *a, const uint64_t *b, uint64_t words
  * that bench.py's cpu_baseline is not a strawman.  tests/ check it against orc_makebf. */
 int64_t orc_makebf_rolling(const char *text, size_t n, int k, uint64_t seed, uint64_t modulus,
                            uint64_t num_bits, uint64_t *words) {
-    if (k < 1 || k > 32 || modulus == 0) return -1;
+    if (k < 1 || k > 32 || modulus == 0 || !spec_is_default()) return -1;  /* the fast variant holds the default spec only */
     memset(words, 0, ((num_bits + 63) / 64) * 8);
     const uint64_t mask = (k == 32) ? ~0ULL : ((1ULL << (2 * k)) - 1);
     const int len = (k + 3) / 4;

@@ -103,6 +103,15 @@ def kmer_hash(kmer: str, seed: int = 0) -> int:
     return int(h)
 
 
+def set_spec(key_bytes: str = "quarter", digest_half: int = 0, canonical: str = "min") -> None:
+    """The oracle's mirror of msbt_hash_spec (include/msbt.h): switches for the HowDeSBT-side choices that are not pinned
+    against a real binary.  Process-wide; call set_spec() with no arguments to go back to the default (App. A)."""
+    L = lib()
+    L.orc_set_spec.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int]
+    L.orc_set_spec.restype = None
+    L.orc_set_spec({"quarter": 0, "words": 1}[key_bytes], int(digest_half), {"min": 0, "forward": 1}[canonical])
+
+
 def makebf(fasta: bytes, k: int, num_bits: int, min_abund: int = 1, seed: int = 0,
            modulus: int | None = None, rolling: bool = False) -> np.ndarray:
     """howdesbt makebf --k --min --bits --hashes=1 --seed=seed,0 -> u64 words of the filter."""
@@ -265,9 +274,17 @@ def py_canonical(kmer: str) -> int:
     return min(f, r)
 
 
-def py_kmer_hash(kmer: str, seed: int = 0) -> int:
+def py_kmer_hash(kmer: str, seed: int = 0, key_bytes: str = "quarter", digest_half: int = 0, canonical: str = "min") -> int:
+    """Independent pure-Python statement of the k-mer hash, with the spec switches of set_spec() as arguments."""
     k = len(kmer)
-    return py_murmur3_x64_128(py_canonical(kmer).to_bytes(16, "little")[: (k + 3) // 4], seed)[0]
+    if canonical == "min":
+        value = py_canonical(kmer)
+    else:
+        value = 0
+        for c in kmer.upper():
+            value = (value << 2) | _CODE[c]
+    length = (k + 3) // 4 if key_bytes == "quarter" else (8 if k <= 32 else 16)
+    return py_murmur3_x64_128(value.to_bytes(16, "little")[:length], seed)[digest_half]
 
 
 def py_fasta_records(fasta: bytes) -> List[str]:

@@ -82,3 +82,38 @@ extern "C" int emu_makebf(const uint64_t *packed, const uint32_t *ends, uint32_t
 #undef RUN
     return 0;
 }
+
+// The generic K1 kernel's per-thread code (run-time msbt_hash_spec switches), for the host.
+template <int KW>
+static void run_generic(const uint64_t *packed, const uint32_t *ends, uint32_t n_runs, uint32_t n_bases, uint32_t k,
+                        const msbt_pos_spec &ps, uint32_t key_len, uint32_t second_half, uint32_t forward_only, uint32_t *out32) {
+    const uint32_t n_words = (n_bases + 31) / 32;
+    for (uint32_t w = 0; w < n_words; w++) {
+        const uint32_t vm = valid_mask(ends, n_runs, w * 32, k);
+        if (!vm) continue;
+        KmerWalker<KW> kw;
+        kw.init(packed + w, k);
+        for (uint32_t j = 0; j < 32; j++) {
+            if ((vm >> j) & 1) {
+                uint64_t lo, hi;
+                if (forward_only) { lo = kw.fl; hi = kw.fh; }
+                else kw.canonical(lo, hi);
+                uint64_t pos = msbt_position(msbt_kmer_hash_generic(lo, hi, key_len, ps.seed, second_half), ps);
+                if (pos < ps.num_bits) out32[pos >> 5] |= 1u << (pos & 31);
+            }
+            kw.roll(j);
+        }
+    }
+}
+
+extern "C" int emu_makebf_generic(const uint64_t *packed, const uint32_t *ends, uint32_t n_runs, uint32_t n_bases, uint32_t k,
+                                  uint64_t seed, uint64_t modulus, uint64_t num_bits, uint64_t *words,
+                                  uint32_t key_rule, uint32_t second_half, uint32_t forward_only) {
+    if (k < 1 || k > 64) return -1;
+    memset(words, 0, ((num_bits + 63) / 64) * 8);
+    msbt_pos_spec ps = msbt_make_pos_spec(modulus, num_bits, seed);
+    const uint32_t key_len = key_rule ? (k <= 32 ? 8u : 16u) : (k + 3u) / 4u;
+    if (k <= 32) run_generic<1>(packed, ends, n_runs, n_bases, k, ps, key_len, second_half, forward_only, (uint32_t *)words);
+    else run_generic<2>(packed, ends, n_runs, n_bases, k, ps, key_len, second_half, forward_only, (uint32_t *)words);
+    return 0;
+}

@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Tier-3 pin: if a real `howdesbt` binary is on PATH, run the seven argv shapes MetaSBT spawns on the
 committed known-answer inputs and compare with the CPU oracle -- the moment this passes, parity is no longer "unpinned".
-If it fails, the first differing item says which line of csrc/msbt_spec.h + oracle/msbt_oracle.c to re-pin
-(hash input bytes, length, digest half, canonical rule, .bf header fields).  Without the binary it reports that and exits 0.
+If it fails, the script tries every msbt_hash_spec switch combination (key length rule, digest half, canonical rule) and
+prints the MSBT_HASH_SPEC setting that reproduces the binary's filters -- a configuration change, no rebuild; `.bf` header
+differences are reported field by field (bf_magic / bf_version are part of the same spec).  Without the binary it reports that and exits 0.
 
     python tests/pin_against_howdesbt.py [--keep DIR]
 """
@@ -72,6 +73,30 @@ def main():
         out = subprocess.run([exe, "dumpbf", bf, "--show:density"], capture_output=True, text=True).stdout
         hdr, words = bffile.read_bf(bf)
         print("dumpbf prints: %r   oracle density repr: %r" % (out.strip().split("\n")[0], O.bf_popcount(words) / hdr.num_bits))
+    if any(f.startswith("makebf") and "filter bits differ" in f for f in failures):
+        # which msbt_hash_spec (include/msbt.h) does this binary follow?  Try every switch combination on the inputs whose
+        # filters were read; a match is the configuration to run with (MSBT_HASH_SPEC=..., no rebuild).
+        matches = []
+        for key_bytes in ("quarter", "words"):
+            for half in (0, 1):
+                for canonical in ("min", "forward"):
+                    O.set_spec(key_bytes, half, canonical)
+                    ok = True
+                    for kat in kats:
+                        bf = os.path.join(work, kat["name"] + ".bf")
+                        if not os.path.isfile(bf):
+                            continue
+                        try:
+                            _h, words = bffile.read_bf(bf)
+                        except Exception:
+                            continue
+                        ok = ok and np.array_equal(words, O.makebf(kat["fasta"].encode(), kat["k"], kat["num_bits"], kat["min"]))
+                    if ok:
+                        matches.append("key_bytes=%s,digest_half=%d,canonical=%s" % (key_bytes, half, canonical))
+        O.set_spec()
+        print("hash specs that reproduce this binary's filters: %s" % (matches or "none of the 8 combinations -- the hash itself differs"))
+        if matches:
+            print("run with   MSBT_HASH_SPEC=%s" % matches[0])
     if failures:
         print("PIN FAILED (%d):" % len(failures))
         for f in failures:

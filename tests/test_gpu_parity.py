@@ -1,5 +1,6 @@
 """GPU parity: every C-ABI entry point against the oracle on the same seeded inputs.
 Integer work => bit-exact (np.array_equal), no tolerances anywhere."""
+import ctypes
 import random
 
 import numpy as np
@@ -639,3 +640,28 @@ def test_backend_streams_operands_in_chunks(ctx, oracle, tmp_path):
         assert [int(x) for x in hits[r]] == [int(x) for x in oracle.query_hits(oracle.positions_distinct(open(fas[q], "rb").read(), k, num_bits), flt)]
     assert be.query_totals(qb) == [len(oracle.positions_distinct(open(f, "rb").read(), k, num_bits)) for f in fas[:5]]
     assert len(be._cache) <= 12
+
+
+@pytest.mark.parametrize("key_bytes,digest_half,canonical", [("words", 0, "min"), ("quarter", 1, "min"), ("quarter", 0, "forward"), ("words", 1, "forward")])
+def test_context_with_a_repinned_hash_spec(oracle, key_bytes, digest_half, canonical):
+    """msbt_ctx_create(device, &spec): a context created with a non-default msbt_hash_spec builds the filters the oracle
+    builds under the same switches (generic K1 kernel) -- re-pinning against a real howdesbt is configuration, not a rebuild."""
+    from metasbt_b200 import ops
+    rng = random.Random(17)
+    spec = ops.HashSpec(key_bytes, digest_half, canonical)
+    ctx2 = ops.Context(0, spec=spec)
+    try:
+        oracle.set_spec(key_bytes, digest_half, canonical)
+        for k, num_bits in ((21, 1 << 16), (31, 200003), (33, 1 << 18), (64, 1 << 16)):
+            fastas = [util.messy_fasta(rng, 3, 3000, "ACGTN") for _ in range(5)] + [b">e\n"]
+            for variant in (0, 3):
+                _, got = build(ctx2, fastas, k, num_bits, variant=variant)
+                for f, g in zip(fastas, got):
+                    assert np.array_equal(g, oracle.makebf(f, k, num_bits))
+        with pytest.raises(ValueError):
+            build(ctx2, fastas, 21, 1 << 16, min_abund=2)
+        got_spec = __import__("metasbt_b200._lib", fromlist=["x"]).HashSpecStruct()
+        assert ctx2._L.msbt_ctx_get_spec(ctx2._h, ctypes.byref(got_spec)) == 0 and got_spec.digest_half == digest_half
+    finally:
+        oracle.set_spec()
+        ctx2.close()

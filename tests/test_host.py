@@ -33,6 +33,10 @@ def emu(built):
     L.emu_makebf.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
                              ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_int]
     L.emu_makebf.restype = ctypes.c_int
+    L.emu_makebf_generic.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+                                     ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_void_p,
+                                     ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32]
+    L.emu_makebf_generic.restype = ctypes.c_int
     return L
 
 
@@ -43,7 +47,7 @@ def test_library_exports_every_declared_symbol(built):
     assert declared, "no declarations found"
     assert declared == set(built.SYMBOLS)
     assert set(built.exported_symbols()) == declared
-    assert built.lib().msbt_abi_version() == 1
+    assert built.lib().msbt_abi_version() == 2
 
 
 def test_header_is_plain_c():
@@ -183,3 +187,74 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "Mbp/s" and d["value"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["e2e"]["h2d_bytes_per_step"] == 0 and d["gpu_launches"] == 0
+
+
+SPECS = [("quarter", 0, "min"), ("words", 0, "min"), ("quarter", 1, "min"), ("quarter", 0, "forward"), ("words", 1, "forward")]
+
+
+@pytest.mark.parametrize("key_bytes,digest_half,canonical", SPECS)
+def test_hash_spec_switches_oracle_c_vs_python_twin_vs_device_code(emu, oracle, key_bytes, digest_half, canonical):
+    """msbt_hash_spec: the unpinned HowDeSBT-side choices as run-time data.  For every switch combination the oracle's C
+    restatement, its independent pure-Python twin and the device's generic K1 code (compiled for the host) agree."""
+    from metasbt_b200 import ops
+    rng = random.Random(hash((key_bytes, digest_half, canonical)) & 0xFFFF)
+    try:
+        oracle.set_spec(key_bytes, digest_half, canonical)
+        for k in (1, 5, 21, 31, 32, 33, 47, 64):
+            kmer = "".join(rng.choice("ACGT") for _ in range(k))
+            assert oracle.kmer_hash(kmer, 7) == oracle.py_kmer_hash(kmer, 7, key_bytes, digest_half, canonical)
+            fa = util.messy_fasta(rng, 3, 400, "ACGTN") + util.codes_to_fasta(util.synthetic_codes(k, 300), "clean")
+            num_bits = rng.choice([1000, 1 << 14, (1 << 14) + 3])
+            want = oracle.makebf(fa, k, num_bits)
+            pg = ops.pack_fasta(fa, k)
+            w = np.zeros((num_bits + 63) // 64, dtype=np.uint64)
+            ends = pg.run_ends if len(pg.run_ends) else np.zeros(1, dtype=np.uint32)
+            assert emu.emu_makebf_generic(pg.words.ctypes.data, ends.ctypes.data, len(pg.run_ends), pg.n_bases, k, 0, num_bits, num_bits,
+                                          w.ctypes.data, {"quarter": 0, "words": 1}[key_bytes], digest_half,
+                                          {"min": 0, "forward": 1}[canonical]) == 0
+            assert np.array_equal(w, want), (k, num_bits)
+            same_key = key_bytes == "quarter" or (k + 3) // 4 == (8 if k <= 32 else 16)
+            changed = digest_half == 1 or canonical == "forward" or not same_key
+            if changed and k >= 5 and want.any():
+                oracle.set_spec()
+                assert not np.array_equal(oracle.makebf(fa, k, num_bits), want)  # the switch really changes the filter
+                oracle.set_spec(key_bytes, digest_half, canonical)
+    finally:
+        oracle.set_spec()
+
+
+def test_hash_spec_parsing_and_struct(built):
+    from metasbt_b200 import ops
+    d = built.HashSpecStruct()
+    built.lib().msbt_hash_spec_default(ctypes.byref(d))
+    s = ops.HashSpec().to_struct()
+    assert (d.struct_size, d.key_bytes, d.digest_half, d.canonical, d.bf_magic, d.bf_version, d.bf_header_size) == \
+        (s.struct_size, s.key_bytes, s.digest_half, s.canonical, s.bf_magic, s.bf_version, s.bf_header_size)
+    spec = ops.HashSpec.parse("key_bytes=words, digest_half=1,canonical=forward,bf_version=1,bf_magic=0x1234")
+    assert spec == ops.HashSpec("words", 1, "forward", 0x1234, 1) and not spec.is_default and ops.HashSpec.parse("").is_default
+    for bad in ("key_bytes=sevenths", "digest_half=2", "colour=blue"):
+        with pytest.raises(ValueError):
+            ops.HashSpec.parse(bad)
+    # no GPU here: a context cannot be made, but an invalid spec is rejected before the device is touched
+    bad = ops.HashSpec().to_struct()
+    bad.key_bytes = 9
+    h = ctypes.c_void_p()
+    assert built.lib().msbt_ctx_create(0, ctypes.byref(bad), ctypes.byref(h)) == built.MSBT_EINVAL
+
+
+def test_bf_header_constants_follow_the_spec(tmp_path, monkeypatch):
+    from metasbt_b200 import bffile
+    words = np.arange(4, dtype=np.uint64)
+    old = (bffile.BF_MAGIC, bffile.BF_VERSION)
+    try:
+        bffile.configure(magic=0x1122334455667788, version=7)
+        p = str(tmp_path / "x.bf")
+        bffile.write_bf(p, bffile.BloomHeader(kmer_size=21, num_bits=256), words)
+        raw = open(p, "rb").read()
+        assert int.from_bytes(raw[:8], "little") == 0x1122334455667788 and int.from_bytes(raw[12:16], "little") == 7
+        assert np.array_equal(bffile.read_bf(p)[1], words)
+        bffile.configure(magic=old[0], version=old[1])
+        with pytest.raises(ValueError):
+            bffile.read_bf(p)  # another magic: not one of ours
+    finally:
+        bffile.configure(magic=old[0], version=old[1])

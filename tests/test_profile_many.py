@@ -98,15 +98,17 @@ def test_cli_profile_batch_of_72_mags_cuda_vs_oracle(tmp_path, ctx, oracle):
     from metasbt_b200 import ops
     core._BACKENDS.clear()
     want_dir, got_dir = str(tmp_path / "oracle"), str(tmp_path / "cuda")
-    _index(want_dir, cpu_backend.OracleBackend(dataset.K, dataset.FILTER_BITS))
-    _index(got_dir, None)  # CudaBackend -> libmsbt.so
     mags = _extra_mags(str(tmp_path / "mags"), 72)
     listing = str(tmp_path / "mags.txt")
     with open(listing, "w") as f:
         f.write("\n".join(mags) + "\n")
+    _index(got_dir, None)  # CudaBackend -> libmsbt.so
     before = ops.default_context().launch_count
     got = cli.MetaSBT(["profile", "--workdir", got_dir, "--database", "db", "--genomes", listing, "--nproc", "1"])
     launches = ops.default_context().launch_count - before
+    assert type(got.database.backend).__name__ == "CudaBackend"
+    core._BACKENDS.clear()  # an injected backend registers itself for the static Database.dist: keep the two runs apart
+    _index(want_dir, cpu_backend.OracleBackend(dataset.K, dataset.FILTER_BITS))
     want = cli.MetaSBT(["profile", "--workdir", want_dir, "--database", "db", "--genomes", listing, "--nproc", "1"],
                        backend=cpu_backend.OracleBackend(dataset.K, dataset.FILTER_BITS))
     assert len(got.result) == 72 and [t for _, t in got.result] == [t for _, t in want.result]
