@@ -48,7 +48,9 @@ def get_backend(kmer_size: int, num_bits: int):
     key = (int(kmer_size), int(num_bits))
     if key not in _BACKENDS:
         from .backend import CudaBackend  # fails loudly without libmsbt.so / a CUDA device
-        _BACKENDS[key] = CudaBackend(*key)
+        from .multigpu import MultiGpuBackend, devices_from_env
+        devices = devices_from_env()      # MSBT_DEVICES="0,1,..." | "all": one context, cache and host thread per GPU
+        _BACKENDS[key] = MultiGpuBackend(*key, devices=devices) if devices else CudaBackend(*key)
     return _BACKENDS[key]
 
 

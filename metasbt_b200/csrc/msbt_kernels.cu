@@ -1380,6 +1380,7 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
         if (rc) return rc;
         for (uint32_t i = 0; i < n_genomes; i++)
             CU_TRY(ctx, cudaMemsetAsync(d_filters + dg[i].filter_word_off, 0, words * 8, stream));
+        if (tiles == 0) return MSBT_OK;  // no genome holds a k-mer: the zeroed filters are the result
         const uint32_t key_len = ctx->spec.key_bytes == MSBT_KEY_BYTES_WHOLE_WORDS ? (k <= 32 ? 8u : 16u) : (k + 3u) / 4u;
         const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * 8);
         if (k <= 32)
