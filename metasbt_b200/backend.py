@@ -123,8 +123,10 @@ class CudaBackend:
 
     def filter(self, path: str) -> torch.Tensor:
         """Device tensor (int64[stride]) of the filter stored at `path` (cached)."""
-        path = os.path.abspath(path)
-        t = self._cache.get(path)
+        t = self._cache.get(path)  # callers nearly always pass the absolute path the cache is keyed by
+        if t is None:
+            path = os.path.abspath(path)
+            t = self._cache.get(path)
         if t is not None:
             self._cache.move_to_end(path)
             return t

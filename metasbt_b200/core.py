@@ -68,6 +68,20 @@ def ani_distance(intersect: int, union: int, kmer_size: int) -> float:
     return 1.0 if ani > 1.0 else ani
 
 
+def mean_rounded(values: Sequence[float], digits: int = 5) -> float:
+    """round(statistics.mean(values), digits), as core.py:2185-2188 computes it, without paying for exact rational
+    arithmetic on every call: statistics.mean is the exactly rounded mean; fsum(values) / n is within one ulp of it, so
+    the two can only round differently when a `digits` rounding boundary lies within a few ulps -- checked, and only
+    then is statistics.mean consulted."""
+    n = len(values)
+    if n == 0:
+        raise statistics.StatisticsError("mean requires at least one data point")
+    approx = math.fsum(values) / n
+    spread = 4.0 * math.ulp(approx)
+    lo, hi = round(approx - spread, digits), round(approx + spread, digits)
+    return lo if lo == hi else round(statistics.mean(values), digits)
+
+
 class Database(object):
     """Database object (reference: core.py:44-3341)."""
 
@@ -464,15 +478,21 @@ class Database(object):
         return cluster.topology_leaves(cluster.read_topology(tree_filepath))
 
     @staticmethod
-    def _tree_matches(leaves: Sequence[str], hits: Sequence[int], total: int, threshold: float) -> "OrderedDict[str, Tuple[int, int]]":
+    def _leaf_names(leaves: Sequence[str]) -> List[str]:
+        """Node names as `howdesbt query` prints them: the `.bf` basename without directory and suffix (App. A6)."""
+        return [os.path.splitext(os.path.basename(leaf))[0] for leaf in leaves]
+
+    @staticmethod
+    def _tree_matches(names: Sequence[str], hits: Sequence[int], total: int, threshold: float) -> "OrderedDict[str, Tuple[int, int]]":
         """What `howdesbt query --sort --distinctkmers --threshold=T` prints for one query against one flat tree:
         {leaf name: (hits, total)} in output order (hits descending, ties in tree order; App. A6)."""
         needed = math.ceil(threshold * total)
-        order = sorted(range(len(leaves)), key=lambda i: -int(hits[i]))
+        counts = [int(h) for h in hits]
+        order = sorted(range(len(names)), key=lambda i: -counts[i])
         out: "OrderedDict[str, Tuple[int, int]]" = OrderedDict()
         for i in order:
-            if int(hits[i]) >= needed:
-                out[os.path.splitext(os.path.basename(leaves[i]))[0]] = (int(hits[i]), total)
+            if counts[i] >= needed:
+                out[names[i]] = (counts[i], total)
         return out
 
     def profile(self, genome_filepath: str, sketch_filepath: str, uncertainty: float = 50.0,
@@ -546,6 +566,7 @@ class Database(object):
             size += nbytes
 
         leaves_of: Dict[str, List[str]] = dict()
+        names_of: Dict[str, List[str]] = dict()
 
         def tree_leaves(cluster_id: str) -> List[str]:
             if cluster_id not in leaves_of:
@@ -554,7 +575,29 @@ class Database(object):
                 if not os.path.isfile(tree_filepath):
                     raise FileNotFoundError(errno.ENOENT, os.strerror(errno.ENOENT), tree_filepath)
                 leaves_of[cluster_id] = self._tree_leaves(tree_filepath)
+                names_of[cluster_id] = self._leaf_names(leaves_of[cluster_id])
             return leaves_of[cluster_id]
+
+        cluster_ids: Dict[Tuple[str, str], str] = dict()  # (level, cluster name) -> MSBT id
+        # per call, every genome of the batch sees the same database: labels and centroid lists are resolved once
+        label_of: Dict[Tuple[str, str], Tuple[str, str]] = dict()            # (level, name) -> (taxonomy, sketch path)
+        centroids_of: Dict[Tuple[str, str], Tuple[str, List[str]]] = dict()  # (level, name) -> (taxonomy, centroid sketches)
+
+        def cluster_label(level: str, name: str) -> Tuple[str, str]:
+            key = (level, name)
+            if key not in label_of:
+                obj = self.clusters[level][name]
+                label_of[key] = (obj.get_full_taxonomy(), obj.sketch_filepath)
+            return label_of[key]
+
+        def cluster_centroids(level: str, name: str) -> Tuple[str, List[str]]:
+            key = (level, name)
+            if key not in centroids_of:
+                obj = self.clusters[level][name]
+                species_entries = [obj.name] if level == "species" else sorted(obj.get_children(up_to="species"))
+                centroids = [self.report[self.clusters["species"][s].identifier]["centroid"] for s in species_entries]
+                centroids_of[key] = (obj.get_full_taxonomy(), [self.genomes[c].sketch_filepath for c in centroids])
+            return centroids_of[key]
 
         for members in batches:
             # The reference joins multi-record FASTA with "N" (core.py:1974-1996) because howdesbt treats records as
@@ -570,7 +613,9 @@ class Database(object):
                 by_tree: "OrderedDict[str, List[int]]" = OrderedDict()
                 for q in range(n):
                     for cluster in reached[q]:
-                        cluster_id = "MSBT0" if level == "db" else self.clusters[level][cluster].identifier
+                        cluster_id = cluster_ids.get((level, cluster))
+                        if cluster_id is None:
+                            cluster_id = cluster_ids[(level, cluster)] = "MSBT0" if level == "db" else self.clusters[level][cluster].identifier
                         by_tree.setdefault(cluster_id, []).append(q)
                 tree_ids = list(by_tree.keys())
                 pending = [backend.query_hits_many(qb, by_tree[t], tree_leaves(t)) for t in tree_ids]
@@ -583,8 +628,8 @@ class Database(object):
                 for q in range(n):
                     best_level_matches: "OrderedDict[str, float]" = OrderedDict()
                     for cluster in reached[q]:
-                        cluster_id = "MSBT0" if level == "db" else self.clusters[level][cluster].identifier
-                        matches = self._tree_matches(tree_leaves(cluster_id), hits_of[(cluster_id, q)], totals[q], threshold)
+                        cluster_id = cluster_ids[(level, cluster)]
+                        matches = self._tree_matches(names_of[cluster_id], hits_of[(cluster_id, q)], totals[q], threshold)
                         if not matches:
                             continue
                         scores = OrderedDict((node, common / total) for node, (common, total) in matches.items())
@@ -609,9 +654,9 @@ class Database(object):
                     best_level_matches = matched[q][level]
                     if level == "db":
                         for name in best_level_matches:
-                            obj = self.clusters[next_level][name]
-                            wanted[obj.sketch_filepath] = None
-                            plan[q].append(("single", (next_level, obj.get_full_taxonomy(), obj.sketch_filepath)))
+                            taxonomy_label, cluster_sketch = cluster_label(next_level, name)
+                            wanted[cluster_sketch] = None
+                            plan[q].append(("single", (next_level, taxonomy_label, cluster_sketch)))
                     elif level == "species":
                         top = sorted(best_level_matches.keys(), key=lambda m: best_level_matches[m])[-1]
                         best_obj = self.genomes[top]
@@ -620,16 +665,13 @@ class Database(object):
                         plan[q].append(("single", (next_level, label, best_obj.sketch_filepath)))
                     else:
                         for name in best_level_matches:
-                            obj = self.clusters[next_level][name]
-                            species_entries = [obj.name] if next_level == "species" else sorted(obj.get_children(up_to="species"))
-                            centroids = [self.report[self.clusters["species"][s].identifier]["centroid"] for s in species_entries]
-                            centroid_sketches = [self.genomes[c].sketch_filepath for c in centroids]
+                            taxonomy_label, centroid_sketches = cluster_centroids(next_level, name)
                             if first_iter:
                                 # the reference computes centroid distances at the first cluster level only and looks the
                                 # lower levels up in the same dictionary (core.py:2160-2185)
                                 for sk in centroid_sketches:
                                     wanted[sk] = None
-                            plan[q].append(("mean", (next_level, obj.get_full_taxonomy(), centroid_sketches)))
+                            plan[q].append(("mean", (next_level, taxonomy_label, centroid_sketches)))
                         first_iter = False
                 plan[q].insert(0, ("targets", list(wanted.keys())))
                 pairs.extend((sketch_filepath, target) for target in wanted)
@@ -649,7 +691,7 @@ class Database(object):
                         profiles[level][label] = round(dists[target], 5)
                     else:
                         level, label, centroid_sketches = payload
-                        profiles[level][label] = round(statistics.mean(dists[s] for s in centroid_sketches), 5)
+                        profiles[level][label] = mean_rounded([dists[s] for s in centroid_sketches], 5)
                 with open(result_paths[g], "w+") as table:
                     table.write("# level\tclosest\tani\n")
                     for level in LEVELS + ["genome"]:
