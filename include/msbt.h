@@ -152,6 +152,13 @@ int msbt_bf_and_popcount_pairs(msbt_ctx *ctx, const uint64_t *const *h_a, const 
 int msbt_bf_and_popcount_allpairs(msbt_ctx *ctx, const uint64_t *const *h_filters, uint32_t n,
                                   uint64_t words, uint64_t *d_intersect, void *stream);
 
+/* Every filter of list A against every filter of list B: d_intersect is a dense n_a x n_b row-major u64 matrix of
+ * popc(a_i & b_j).  The building block of an all-pairs matrix that does not fit one GPU: every rank holds a block of the
+ * filters and meets the other blocks one after the other (shard.all_pairs_ring). */
+int msbt_bf_and_popcount_rect(msbt_ctx *ctx, const uint64_t *const *h_a, uint32_t n_a,
+                              const uint64_t *const *h_b, uint32_t n_b, uint64_t words,
+                              uint64_t *d_intersect, void *stream);
+
 /* ---------------------------------------------------------------- K4: howdesbt query --distinctkmers
  * Replaces core.py:2039-2047 (Database.profile).
  * Step 1: the query's distinct positions are exactly the set bits of its own min=1 filter

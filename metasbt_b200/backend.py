@@ -295,14 +295,15 @@ class CudaBackend:
             return self.ctx.bf_allpairs([self.filter(p) for p in paths], self.num_bits)
         # more filters than may be resident at once: tile the matrix; only two half-chunks are alive at a time
         half = max(1, step // 2)
-        blocks = [list(range(lo, min(lo + half, n))) for lo in range(0, n, half)]
+        blocks = [(lo, min(lo + half, n)) for lo in range(0, n, half)]
         out = torch.zeros((n, n), dtype=torch.int64, device=self.ctx.device)
-        for bi, rows_i in enumerate(blocks):
-            for rows_j in blocks[bi:]:
-                idx = rows_i if rows_j is rows_i else rows_i + rows_j
-                sub = self.ctx.bf_allpairs([self.filter(paths[t]) for t in idx], self.num_bits)
-                sel = torch.tensor(idx, device=self.ctx.device)
-                out[sel.unsqueeze(1), sel.unsqueeze(0)] = sub
+        for bi, (i0, i1) in enumerate(blocks):
+            rows_i = [self.filter(paths[t]) for t in range(i0, i1)]
+            out[i0:i1, i0:i1] = self.ctx.bf_allpairs(rows_i, self.num_bits)
+            for j0, j1 in blocks[bi + 1:]:
+                rect = self.ctx.bf_rect(rows_i, [self.filter(paths[t]) for t in range(j0, j1)], self.num_bits)
+                out[i0:i1, j0:j1] = rect
+                out[j0:j1, i0:i1] = rect.t()
         return out
 
     def dist_all_pairs(self, paths: Sequence[str]) -> np.ndarray:

@@ -1887,7 +1887,10 @@ __device__ __forceinline__ void apc_step4(ApcPair (&st)[4], const uint32_t *a0, 
 
 __global__ void __launch_bounds__(APC_THREADS, 3)
 bf_allpairs_csa_kernel(const uint64_t *const *__restrict__ filters, uint32_t n, uint64_t words, uint32_t pair_base,
-                       unsigned long long *__restrict__ out) {
+                       unsigned long long *__restrict__ out, const uint64_t *const *__restrict__ filters_b = nullptr,
+                       uint32_t n_b = 0) {
+    // filters_b != nullptr: RECTANGULAR mode -- every filter of `filters` (n of them) against every filter of `filters_b`
+    // (n_b), out is n x n_b; block pairs are (I over A, J over B), none of them diagonal.
     extern __shared__ __align__(16) uint32_t apc_tile[];            // rows of tw + 4 words: I block, then J block
     __shared__ const uint64_t *sm_ptr[2 * APC_B];
     __shared__ uint32_t sm_dst[2 * APC_B];
@@ -1895,12 +1898,20 @@ bf_allpairs_csa_kernel(const uint64_t *const *__restrict__ filters, uint32_t n, 
     __shared__ unsigned long long sm_cnt[64 * 4];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // block pair (I <= J) from the linear index
+    const bool rect = filters_b != nullptr;
     const uint32_t nb = (n + APC_B - 1) / APC_B;
     uint32_t I = 0, t = pair_base + blockIdx.y;  // (more than 65,535 block pairs take several launches)
-    while (t >= nb - I) { t -= nb - I; I++; }
-    const uint32_t J = I + t;
-    const bool diag = I == J;
-    const uint32_t ni = min((uint32_t)APC_B, n - I * APC_B), nj = min((uint32_t)APC_B, n - J * APC_B);
+    uint32_t J;
+    if (rect) {
+        const uint32_t nbb = (n_b + APC_B - 1) / APC_B;
+        I = t / nbb;
+        J = t - I * nbb;
+    } else {
+        while (t >= nb - I) { t -= nb - I; I++; }
+        J = I + t;
+    }
+    const bool diag = !rect && I == J;
+    const uint32_t ni = min((uint32_t)APC_B, n - I * APC_B), nj = min((uint32_t)APC_B, (rect ? n_b : n) - J * APC_B);
     const uint32_t di_n = (ni + 1) / 2, dj_n = (nj + 1) / 2;
     const uint32_t LB = diag ? di_n * (di_n + 1) / 2 : di_n * dj_n;  // lane blocks: 1 .. 64
     // words of every filter per tile: the tile buffer holds 32 rows of 1 KiB; with fewer filters the rows get longer
@@ -1920,7 +1931,7 @@ bf_allpairs_csa_kernel(const uint64_t *const *__restrict__ filters, uint32_t n, 
         const uint32_t sl = threadIdx.x;
         const uint64_t *p = nullptr;
         if (sl < ni) p = filters[I * APC_B + sl];
-        else if (!diag && sl < ni + nj) p = filters[J * APC_B + sl - ni];
+        else if (!diag && sl < ni + nj) p = (rect ? filters_b : filters)[J * APC_B + sl - ni];
         sm_ptr[sl] = p;
         // byte offset of the slice's row: the I block's filters first (duo members interleaved by apc_row), then the J block's
         sm_dst[sl] = (sl < ni ? apc_row(sl, ni) : ni + apc_row(min(sl - ni, nj - 1), nj)) * stride * 4;
@@ -2022,7 +2033,9 @@ bf_allpairs_csa_kernel(const uint64_t *const *__restrict__ filters, uint32_t n, 
             const uint32_t cd = sm_lb[p];
             const uint32_t li = 2 * (cd >> 4) + (k >> 1), lj = 2 * (cd & 15) + (k & 1);
             const uint32_t fi = I * APC_B + li, fj = J * APC_B + lj;
-            if (li < ni && lj < nj && fi <= fj) {
+            if (rect) {
+                if (li < ni && lj < nj) atomicAdd(out + (uint64_t)fi * n_b + fj, c);
+            } else if (li < ni && lj < nj && fi <= fj) {
                 atomicAdd(out + (uint64_t)fi * n + fj, c);
                 if (fi != fj) atomicAdd(out + (uint64_t)fj * n + fi, c);
             }
@@ -2214,6 +2227,47 @@ extern "C" int msbt_bf_and_popcount_allpairs(msbt_ctx *ctx, const uint64_t *cons
         const unsigned cnt = (unsigned)std::min<uint64_t>(65535, block_pairs - base);
         bf_allpairs_csa_kernel<<<dim3((unsigned)gx, cnt), APC_THREADS, APC_SMEM_BYTES, stream>>>(
             d_f, n, words, (uint32_t)base, (unsigned long long *)d_intersect);
+        LAUNCH_CHECK(ctx);
+    }
+    return MSBT_OK;
+}
+
+// Every filter of list A against every filter of list B: d_intersect is a dense n_a x n_b row-major u64 matrix.  The same
+// carry-save kernel as the square case, block pairs (I over A) x (J over B).
+extern "C" int msbt_bf_and_popcount_rect(msbt_ctx *ctx, const uint64_t *const *h_a, uint32_t n_a, const uint64_t *const *h_b,
+                                         uint32_t n_b, uint64_t words, uint64_t *d_intersect, void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n_a == 0 || n_b == 0) return MSBT_OK;
+    if (words == 0 || !d_intersect) return fail(ctx, MSBT_EINVAL, "bf_and_popcount_rect: null/empty input");
+    int rc = check_ptrs(ctx, h_a, n_a);
+    if (rc) return rc;
+    rc = check_ptrs(ctx, h_b, n_b);
+    if (rc) return rc;
+    CTX_DEVICE(ctx);
+    const size_t tab_a = align_up((size_t)n_a * sizeof(void *), 256), tab_b = align_up((size_t)n_b * sizeof(void *), 256);
+    rc = ensure_scratch(ctx, tab_a + tab_b);
+    if (rc) return rc;
+    rc = stage_begin(ctx, tab_a + tab_b);
+    if (rc) return rc;
+    rc = stage_to_device(ctx, ctx->d_scratch, h_a, (size_t)n_a * sizeof(void *), 0, stream);
+    if (rc) return rc;
+    rc = stage_to_device(ctx, (char *)ctx->d_scratch + tab_a, h_b, (size_t)n_b * sizeof(void *), tab_a, stream);
+    if (rc) return rc;
+    rc = stage_end(ctx, stream);
+    if (rc) return rc;
+    const uint64_t *const *d_a = (const uint64_t *const *)ctx->d_scratch;
+    const uint64_t *const *d_b = (const uint64_t *const *)((char *)ctx->d_scratch + tab_a);
+    CU_TRY(ctx, cudaMemsetAsync(d_intersect, 0, (size_t)n_a * n_b * 8, stream));
+    const uint64_t nba = (n_a + APC_B - 1) / APC_B, nbb = (n_b + APC_B - 1) / APC_B, block_pairs = nba * nbb;
+    if (block_pairs > 0xFFFFFFFFull) return fail(ctx, MSBT_EINVAL, "bf_and_popcount_rect: too many block pairs");
+    const uint64_t n_tiles = (((words + 1) >> 1) + APC_TW / 4 - 1) / (APC_TW / 4);
+    const uint64_t gx = std::max<uint64_t>(1, std::min<uint64_t>(n_tiles, std::max<uint64_t>(1, (uint64_t)ctx->num_sms * 6 / block_pairs)));
+    CU_TRY(ctx, cudaFuncSetAttribute(bf_allpairs_csa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)APC_SMEM_BYTES));
+    for (uint64_t base = 0; base < block_pairs; base += 65535) {
+        const unsigned cnt = (unsigned)std::min<uint64_t>(65535, block_pairs - base);
+        bf_allpairs_csa_kernel<<<dim3((unsigned)gx, cnt), APC_THREADS, APC_SMEM_BYTES, stream>>>(
+            d_a, n_a, words, (uint32_t)base, (unsigned long long *)d_intersect, d_b, n_b);
         LAUNCH_CHECK(ctx);
     }
     return MSBT_OK;

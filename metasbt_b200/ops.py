@@ -391,6 +391,15 @@ class Context:
             self._check(rc, "msbt_bf_and_popcount_allpairs")
         return out
 
+    def bf_rect(self, a: Sequence[torch.Tensor], b: Sequence[torch.Tensor], num_bits: int) -> torch.Tensor:
+        """Dense len(a) x len(b) intersection matrix popc(a_i & b_j) (msbt_bf_and_popcount_rect)."""
+        out = torch.empty((len(a), len(b)), dtype=torch.int64, device=self.device)
+        if len(a) and len(b):
+            rc = self._L.msbt_bf_and_popcount_rect(self._h, _ptr_array(a), len(a), _ptr_array(b), len(b), filter_words(num_bits),
+                                                   out.data_ptr(), self._stream())
+            self._check(rc, "msbt_bf_and_popcount_rect")
+        return out
+
     # ------------------------------------------------------------------ K4
     def extract_positions(self, filt: torch.Tensor, num_bits: int, cap: Optional[int] = None) -> torch.Tensor:
         """Ascending positions of the set bits of one filter (uint32 bit patterns in an int32 tensor).

@@ -164,6 +164,96 @@ def query_exchange_sharded(ctx, sliced: torch.Tensor, n_leaves: int, num_bits: i
     return hits
 
 
+def ring_schedule(rank: int, world: int) -> List[Tuple[int, int, str]]:
+    """Which (peer to receive from, peer to send to, role) a rank meets in the half ring of all_pairs_ring.  Every unordered
+    pair of DIFFERENT blocks is computed exactly once: at step s = 1 .. floor(world / 2) rank r receives block (r + s) and
+    sends its own to (r - s); when world is even, the last step pairs r with r + world/2 in both directions, so the lower
+    rank takes the first half of its rows against the whole peer block ("low") and the upper one all of its rows against
+    the second half of the peer's ("high").  role is "full", "low" or "high"."""
+    out = []
+    for s in range(1, world // 2 + 1):
+        src, dst = (rank + s) % world, (rank - s) % world
+        role = "full"
+        if world % 2 == 0 and s == world // 2:
+            role = "low" if rank < src else "high"
+        out.append((src, dst, role))
+    return out
+
+
+def all_pairs_ring(ctx, mat: torch.Tensor, num_bits: int, group=None, chunk: int = 128) -> torch.Tensor:
+    """All-pairs intersections of a filter set that is spread over the ranks (each holds a block of rows `mat`
+    [n_local, stride] int64) and does not fit one GPU -- the `dist` loop of Entry.get_boundaries (core.py:4036-4081) over
+    e.g. 10,000 genomes.  Local block: one square all-pairs launch.  Other blocks: half ring (ring_schedule): the peer's
+    filters arrive `chunk` at a time over NCCL send/recv and meet the local rows in one rectangular launch each
+    (msbt_bf_and_popcount_rect).  Every pair is computed once.  Returns int64 [n_local, n_total] with -1 where the pair
+    belongs to the other side; all_pairs_assemble() gives the full symmetric matrix."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    n_local, stride = int(mat.shape[0]), int(mat.shape[1])
+    counts = [n_local]
+    if world > 1:
+        t = torch.tensor([n_local], dtype=torch.int64, device=mat.device)
+        allc = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allc, t, group=group)
+        counts = [int(c.item()) for c in allc]
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    out = torch.full((n_local, offs[-1]), -1, dtype=torch.int64, device=mat.device)
+    rows = [mat[i] for i in range(n_local)]
+    if n_local:
+        out[:, offs[rank]: offs[rank + 1]] = ctx.bf_allpairs(rows, num_bits)
+    for src, dst, role in ring_schedule(rank, world):
+        n_src, n_dst = counts[src], counts[dst]
+        # what travels: the whole block, except towards the "low" side of an opposite pair, which only needs ... the whole
+        # block too (it takes all of the peer's filters); the "high" side needs the second half of the lower rank's rows
+        send_lo, send_hi = (0, n_local)
+        recv_lo, recv_hi = (0, n_src)
+        if role == "low":      # I send my second half (the peer is "high"), I receive the peer's whole block
+            send_lo = n_local // 2
+        elif role == "high":   # I send my whole block (the peer is "low"), I receive the peer's second half
+            recv_lo = n_src // 2
+        my_rows = rows[: n_local // 2] if role == "low" else rows
+        row_hi = n_local // 2 if role == "low" else n_local
+        n_send, n_recv = send_hi - send_lo, recv_hi - recv_lo
+        steps = max((n_send + chunk - 1) // chunk, (n_recv + chunk - 1) // chunk)
+        for c in range(steps):
+            sb, se = min(send_lo + c * chunk, send_hi), min(send_lo + (c + 1) * chunk, send_hi)
+            rb, re_ = min(recv_lo + c * chunk, recv_hi), min(recv_lo + (c + 1) * chunk, recv_hi)
+            buf = torch.empty((re_ - rb, stride), dtype=mat.dtype, device=mat.device)
+            reqs = []
+            if se > sb:
+                reqs.append(dist.P2POp(dist.isend, mat[sb:se].contiguous(), dst if group is None else dist.get_global_rank(group, dst), group))
+            if re_ > rb:
+                reqs.append(dist.P2POp(dist.irecv, buf, src if group is None else dist.get_global_rank(group, src), group))
+            for q in (dist.batch_isend_irecv(reqs) if reqs else []):
+                q.wait()
+            if re_ > rb and my_rows:
+                block = ctx.bf_rect(my_rows, [buf[i] for i in range(re_ - rb)], num_bits)
+                out[:row_hi, offs[src] + rb: offs[src] + re_] = block
+    return out
+
+
+def all_pairs_assemble(local: torch.Tensor, group=None) -> torch.Tensor:
+    """Full symmetric [n_total, n_total] matrix on every rank from the per-rank row blocks of all_pairs_ring (small n:
+    tests, reports)."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    if world == 1:
+        return local
+    n_total = int(local.shape[1])
+    t = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+    allc = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allc, t, group=group)
+    counts = [int(c.item()) for c in allc]
+    pad = max(counts)
+    mine = torch.full((pad, n_total), -1, dtype=torch.int64, device=local.device)
+    mine[: local.shape[0]] = local
+    blocks = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(blocks, mine, group=group)
+    full = torch.cat([b[:c] for b, c in zip(blocks, counts)])
+    return torch.where(full >= 0, full, full.t())
+
+
 def or_merge(partial: torch.Tensor, num_bits: int, group=None, ctx=None) -> torch.Tensor:
     """Bitwise-OR merge of one partial filter per rank (int64 words, same length everywhere).
     all_to_all by bit range, local k-way OR of the received ranges (msbt_bf_or_reduce through `ctx` on the GPU; the

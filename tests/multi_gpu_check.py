@@ -85,6 +85,11 @@ def main():
     hits3 = shard.query_exchange_sharded(ctx, sliced, n, m, [qf[i] for i in range(qb, qe)], timings=timings)
     assert np.array_equal(hits3.cpu().numpy().astype(np.uint64), ref), "K4 query_exchange_sharded rank %d" % rank
     assert "ms_probe" in timings
+    # K3 all pairs over the filter set as it is spread over the ranks (half ring of rectangular launches over NCCL send/recv)
+    local = shard.all_pairs_ring(ctx, mine, m, chunk=3)
+    full = shard.all_pairs_assemble(local)
+    want_pairs = np.array([[O.bf_and_popcount(a, b) for b in want] for a in want], dtype=np.int64)
+    assert np.array_equal(full.cpu().numpy(), want_pairs), "K3 all_pairs_ring rank %d" % rank
     dist.barrier()
     if rank == 0:
         print("multi-GPU parity ok: world=%d, K1 blocks %s, K2 OR-merge, K3 and K4 bit-range shards all match the oracle" % (world, counts))

@@ -667,3 +667,16 @@ def test_context_with_a_repinned_hash_spec(oracle, key_bytes, digest_half, canon
     finally:
         oracle.set_spec()
         ctx2.close()
+
+
+@pytest.mark.parametrize("na,nb,num_bits", [(1, 1, 64), (3, 17, 100000), (16, 16, 1 << 16), (17, 40, (1 << 18) + 64), (70, 5, 8192 * 3 + 64)])
+def test_rectangular_all_pairs(ctx, oracle, na, nb, num_bits):
+    """msbt_bf_and_popcount_rect: list A against list B (the block of shard.all_pairs_ring and of the tiled all-pairs path)."""
+    rng = random.Random(na * 100 + nb)
+    fastas = [util.messy_fasta(rng, 2, 2500, "ACGTN") for _ in range(na + nb)]
+    mat, flt = build(ctx, fastas, 21, num_bits)
+    a, b = [mat[i] for i in range(na)], [mat[na + j] for j in range(nb)]
+    got = ctx.bf_rect(a, b, num_bits).cpu().numpy()
+    want = np.array([[oracle.bf_and_popcount(flt[i], flt[na + j]) for j in range(nb)] for i in range(na)], dtype=np.int64)
+    assert np.array_equal(got, want)
+    assert ctx.bf_rect([], b, num_bits).shape == (0, nb)

@@ -95,6 +95,27 @@ def _worker(rank, world, port, tmp):
         hits = torch.from_numpy(part)
         shard.all_reduce_counts(hits)
         assert np.array_equal(hits.numpy().astype(np.uint64), np.stack([O.query_hits(O.positions_distinct(q, k, bits), full) for q in queries]))
+        # K3 all pairs over a filter set spread across the ranks (half ring; every pair computed once)
+        class OracleOps:  # stands in for ops.Context in this CPU test: the two launches all_pairs_ring makes
+            def bf_allpairs(self, rows, num_bits):
+                return torch.tensor([[O.bf_and_popcount(a.numpy().view(np.uint64), b.numpy().view(np.uint64)) for b in rows] for a in rows],
+                                    dtype=torch.int64).reshape(len(rows), len(rows))
+
+            def bf_rect(self, a_rows, b_rows, num_bits):
+                return torch.tensor([[O.bf_and_popcount(a.numpy().view(np.uint64), b.numpy().view(np.uint64)) for b in b_rows] for a in a_rows],
+                                    dtype=torch.int64).reshape(len(a_rows), len(b_rows))
+        for total in (7, 2 * world + 1, world):  # ragged blocks, one filter per rank
+            lo, hi = total * rank // world, total * (rank + 1) // world
+            pool = [O.makebf(util.codes_to_fasta(util.mutate(util.synthetic_codes(9, 5000), 0.03 * g, 70 + g), "p%d" % g), k, bits) for g in range(total)]
+            mat = torch.from_numpy(np.stack(pool[lo:hi]).view(np.int64)) if hi > lo else torch.zeros((0, bits // 64), dtype=torch.int64)
+            local = shard.all_pairs_ring(OracleOps(), mat, bits, chunk=2)
+            full = shard.all_pairs_assemble(local)
+            want = np.array([[O.bf_and_popcount(a, b) for b in pool] for a in pool], dtype=np.int64)
+            assert np.array_equal(full.numpy(), want), (total, rank)
+            computed = torch.tensor([int((local >= 0).sum())], dtype=torch.int64)
+            dist.all_reduce(computed)
+            assert int(computed) == sum((total * (r + 1) // world - total * r // world) ** 2 for r in range(world)) + \
+                (total * total - sum((total * (r + 1) // world - total * r // world) ** 2 for r in range(world))) // 2  # each cross pair once
         open(os.path.join(tmp, "ok%d" % rank), "w").close()
     finally:
         dist.destroy_process_group()
