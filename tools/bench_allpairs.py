@@ -83,7 +83,6 @@ def main():
         n = a.genomes
         sec = float(ms.item()) / 1e3
         entries = int(done.item())
-        pairs = (entries - n) // 1 if world == 1 else entries - n  # square blocks hold both (i, j) and (j, i); see below
         # distinct unordered pairs actually computed: square local blocks compute each pair once but fill both entries
         blocks = [a.genomes * (r + 1) // world - a.genomes * r // world for r in range(world)]
         distinct = sum(b * (b - 1) // 2 for b in blocks) + (n * n - sum(b * b for b in blocks)) // 2

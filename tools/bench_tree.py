@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 import torch
 import torch.distributed as dist
 
+from bench import ClockSampler
 from metasbt_b200 import ops, shard, synth
 
 
@@ -98,6 +99,8 @@ def main():
         return out
 
     ctx.build_filters(batch, k, m, out=leaves)  # warm-up (scratch allocation)
+    clocks = ClockSampler(local)
+    clocks.__enter__()
     timed("K1_leaf_filters", lambda: ctx.build_filters(batch, k, m, out=leaves))
     rows = [leaves[i] for i in range(n_local)]
 
@@ -151,6 +154,7 @@ def main():
 
     similarities()
     pairs, n_clusters = timed("K3_similarities_and_densities", similarities)
+    clocks.__exit__(None, None, None)
 
     tot = torch.tensor([pairs, n_clusters, n_union, n_in, n_local], dtype=torch.int64, device=dev)
     if world > 1:
@@ -170,6 +174,7 @@ def main():
             "K2": {"algorithmic_GB": k2_bytes / 1e9, "frac_of_hbm_peak_per_gpu": k2_bytes / times["K2_unions_bottom_up"] / 1e9 / peak / world,
                    "note": "includes the cross-GPU bit-range OR-merge of the kingdom filter" if world > 1 else "single GPU: no merge"},
             "K3": {"pairs_per_s": pairs / times["K3_similarities_and_densities"]},
+            "clocks": clocks.summary(),
         }
         print(json.dumps(out))
     if world > 1:
