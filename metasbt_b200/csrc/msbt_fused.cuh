@@ -37,14 +37,24 @@ constexpr uint32_t FU_CHUNK_BASES = FU_P_THREADS * 32;  // k-mer starts per chun
 #ifndef MSBT_FU_NB
 #define MSBT_FU_NB 2048
 #endif
-constexpr uint32_t FU_MAX_BUCKETS = MSBT_FU_NB;         // 2048: at 2^30 bits a bucket is one 64 KiB tile (single-pass build)
-constexpr uint32_t FU_STAGE_WORDS = (32768 / FU_MAX_BUCKETS) * (FU_MAX_BUCKETS + 1);  // staging rows: (NB + 1) x cap
+// The bucket count is a template parameter of the kernel (NBM, the maximum number of buckets per filter): 2048 for filters
+// of 2^30 bits and more (a bucket is one 64 KiB tile: single-pass build), 512 below (fewer, larger buckets: a quarter of the
+// per-tile chains on the B side; 5 Mbp genomes, 2^22 .. 2^28 bits: 34.5 -> 27.4 us/genome, 2^29: 37.7 -> 30.8;
+// profiles/r02_k1_bucket_geometry.json).  Everything that depends on it is FuGeom<NBM>.
+constexpr uint32_t FU_NBM_LARGE = MSBT_FU_NB;
+constexpr uint32_t FU_NBM_SMALL = 512;
 constexpr uint32_t FU_TILE_LOG2 = 19;                   // <= 2^19 bits = 64 KiB per tile
 constexpr uint32_t FU_TILE_BYTES = 1u << (FU_TILE_LOG2 - 3);
-constexpr int FU_REG_QUADS = (768 * (2048 / (int)FU_MAX_BUCKETS) + FU_B_THREADS - 1) / FU_B_THREADS;  // 16-byte groups of bucket positions per B thread in registers
-constexpr int FU_REG_ENTRIES = 4 * FU_REG_QUADS;
-// dynamic shared memory: [tile 64 KiB][cnt NB][stage][claims]
-constexpr size_t FU_SMEM_BYTES = FU_TILE_BYTES + FU_MAX_BUCKETS * 4 + (size_t)FU_STAGE_WORDS * 4 + 64;
+template <uint32_t NBM>
+struct FuGeom {
+    static constexpr uint32_t MAX_BUCKETS = NBM;
+    static constexpr uint32_t STAGE_WORDS = (32768 / NBM) * (NBM + 1);  // staging rows: (NB + 1) x cap
+    // 16-byte groups of bucket positions per B thread in registers
+    static constexpr int REG_QUADS = (768 * (2048 / (int)NBM) + FU_B_THREADS - 1) / FU_B_THREADS;
+    static constexpr int REG_ENTRIES = 4 * REG_QUADS;
+    // dynamic shared memory: [tile 64 KiB][cnt NB][stage][claims]
+    static constexpr size_t SMEM_BYTES = FU_TILE_BYTES + NBM * 4 + (size_t)STAGE_WORDS * 4 + 64;
+};
 constexpr uint32_t FU_SKIP = 0xFFFFFFFFu;
 
 #ifdef MSBT_FU_TRACE
@@ -65,7 +75,7 @@ struct FusedParams {
     uint32_t n_genomes;
     uint32_t n_chunks_total;
     uint32_t bucket_shift;   // bucket = pos >> bucket_shift
-    uint32_t NB;             // buckets per filter (<= FU_MAX_BUCKETS)
+    uint32_t NB;             // buckets per filter (<= NBM)
     uint32_t cap;            // staging entries per bucket per chunk (multiple of 4)
     uint32_t quads;          // cap / 4
     uint32_t lanes_per_row;  // flush: power of two >= min(quads, 32)
@@ -172,9 +182,13 @@ __device__ __forceinline__ void fu_word(KmerBlock<KW> &kb, uint32_t vm, const Km
     }
 }
 
-template <int KW, int HV, bool POW2, bool FULL>
+template <int KW, int HV, bool POW2, bool FULL, uint32_t NBM>
 __global__ void __launch_bounds__(FU_THREADS, 1)
 kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
+    constexpr uint32_t FU_MAX_BUCKETS = FuGeom<NBM>::MAX_BUCKETS;
+    constexpr uint32_t FU_STAGE_WORDS = FuGeom<NBM>::STAGE_WORDS;
+    constexpr int FU_REG_QUADS = FuGeom<NBM>::REG_QUADS;
+    constexpr int FU_REG_ENTRIES = FuGeom<NBM>::REG_ENTRIES;
     extern __shared__ __align__(128) uint32_t fu_smem[];
     uint32_t *tile = fu_smem;                                        // B: one <= 64 KiB tile
     uint32_t *cnt = fu_smem + FU_TILE_BYTES / 4;                     // P: [NB + 1] staged per bucket (+ dummy)

@@ -345,14 +345,16 @@ template <int KW, int HV, bool POW2>
 __global__ void __launch_bounds__(TILE_THREADS, 4)
 kmer_bloom_direct_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ run_ends,
                          const DevGenome *__restrict__ genomes, uint32_t n_genomes, uint32_t n_tiles,
-                         KmerSpec spec, uint32_t *__restrict__ filters, const uint32_t *__restrict__ only_dirty) {
+                         KmerSpec spec, uint32_t *__restrict__ filters, const uint32_t *__restrict__ only_dirty,
+                         uint32_t tile_base = 0) {
     const uint32_t k = spec.k, len = (k + 3) >> 2;
     if (only_dirty) {  // redo pass: leave at once when no genome is marked (the normal case)
         int any = 0;
         for (uint32_t i = threadIdx.x; i < n_genomes; i += blockDim.x) any |= (only_dirty[i] != 0);
         if (!__syncthreads_or(any)) return;
     }
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // tile_base / n_tiles: the (absolute) tile range of this launch -- a group of genomes whose filters fit L2 together
+    for (uint32_t tile = tile_base + blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const uint32_t gi = find_genome(genomes, n_genomes, tile);
         const DevGenome g = genomes[gi];
         // redo pass after the fused kernel: only genomes whose ring buckets overflowed
@@ -1095,12 +1097,12 @@ static int build_tiled(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *
 
 static int launch_direct(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *d_run_ends, const DevGenome *d_genomes,
                          uint32_t n_genomes, uint64_t tiles, const KmerSpec &spec, uint64_t *d_filters,
-                         const uint32_t *only_dirty, cudaStream_t stream) {
-    if (tiles == 0) return MSBT_OK;
-    const int grid = (int)std::min<uint64_t>(tiles, (uint64_t)ctx->num_sms * 8);
+                         const uint32_t *only_dirty, cudaStream_t stream, uint64_t tile_base = 0) {
+    if (tiles <= tile_base) return MSBT_OK;
+    const int grid = (int)std::min<uint64_t>(tiles - tile_base, (uint64_t)ctx->num_sms * 8);
 #define MSBT_DIRECT_LAUNCH(KW, HV, P2)                                                                          \
     kmer_bloom_direct_kernel<KW, HV, P2><<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, d_genomes, n_genomes, \
-                                                                           (uint32_t)tiles, spec, (uint32_t *)d_filters, only_dirty)
+                                                                           (uint32_t)tiles, spec, (uint32_t *)d_filters, only_dirty, (uint32_t)tile_base)
     const int hv = msbt_hash_variant(spec.k);
     const bool p2 = spec.pos.pow2 != 0;
     if (hv == 0) { if (p2) MSBT_DIRECT_LAUNCH(1, 0, true); else MSBT_DIRECT_LAUNCH(1, 0, false); }
@@ -1125,7 +1127,12 @@ static int build_fused(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *
     const uint64_t num_bits = spec.pos.num_bits;
     const uint32_t k = spec.k;
     uint32_t shift = 7;  // a tile is at least 128 bits (one 16-byte bulk store)
-    while (((num_bits + (1ull << shift) - 1) >> shift) > FU_MAX_BUCKETS) shift++;
+    // at most 512 buckets below 2^30 bits, 2048 from there (msbt_fused.cuh: FuGeom); MSBT_FU_NBMAX=512|2048 forces one (tuning)
+    uint32_t nbm = num_bits < (1ull << 30) ? FU_NBM_SMALL : FU_NBM_LARGE;
+    if (const char *e = getenv("MSBT_FU_NBMAX")) { const int v = atoi(e); if (v == (int)FU_NBM_SMALL || v == (int)FU_NBM_LARGE) nbm = (uint32_t)v; }
+    const uint32_t stage_words = nbm == FU_NBM_SMALL ? FuGeom<FU_NBM_SMALL>::STAGE_WORDS : FuGeom<FU_NBM_LARGE>::STAGE_WORDS;
+    const size_t smem_bytes = nbm == FU_NBM_SMALL ? FuGeom<FU_NBM_SMALL>::SMEM_BYTES : FuGeom<FU_NBM_LARGE>::SMEM_BYTES;
+    while (((num_bits + (1ull << shift) - 1) >> shift) > nbm) shift++;
     const uint32_t NB = (uint32_t)((num_bits + (1ull << shift) - 1) >> shift);
     if (fchunks == 0 || (fchunks >> 31) || ((uint64_t)n_genomes * NB >> 28)) return 1;  // counters: 4 B per (genome, bucket)
 
@@ -1133,7 +1140,7 @@ static int build_fused(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *
     memset(&P, 0, sizeof(P));
     P.bucket_shift = shift;
     P.NB = NB;
-    P.cap = std::min<uint32_t>((FU_STAGE_WORDS / (NB + 1)) & ~3u, 252u);  // n is packed into 8 bits by the flush
+    P.cap = std::min<uint32_t>((stage_words / (NB + 1)) & ~3u, 252u);  // n is packed into 8 bits by the flush
     P.quads = P.cap / 4;
     P.lanes_per_row = 1;
     while (P.lanes_per_row < P.quads && P.lanes_per_row < 32) P.lanes_per_row <<= 1;
@@ -1198,29 +1205,33 @@ static int build_fused(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_t *
     CU_TRY(ctx, cudaMemsetAsync(S + sync_off, 0, zero_end - sync_off, stream));
 
     if (!ctx->fused_attr_set) {
-#define MSBT_FU_ATTR(KW, HV) \
-        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_fused_kernel<KW, HV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES)); \
-        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_fused_kernel<KW, HV, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES)); \
-        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_fused_kernel<KW, HV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES)); \
-        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_fused_kernel<KW, HV, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FU_SMEM_BYTES));
+#define MSBT_FU_ATTR1(KW, HV, NBM_)                                                                                                          \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_fused_kernel<KW, HV, true, true, NBM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuGeom<NBM_>::SMEM_BYTES)); \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_fused_kernel<KW, HV, true, false, NBM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuGeom<NBM_>::SMEM_BYTES)); \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_fused_kernel<KW, HV, false, true, NBM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuGeom<NBM_>::SMEM_BYTES)); \
+        CU_TRY(ctx, cudaFuncSetAttribute(kmer_bloom_fused_kernel<KW, HV, false, false, NBM_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FuGeom<NBM_>::SMEM_BYTES));
+#define MSBT_FU_ATTR(KW, HV) MSBT_FU_ATTR1(KW, HV, FU_NBM_SMALL) MSBT_FU_ATTR1(KW, HV, FU_NBM_LARGE)
         MSBT_FU_ATTR(1, 0) MSBT_FU_ATTR(2, 1) MSBT_FU_ATTR(2, 2)
 #undef MSBT_FU_ATTR
+#undef MSBT_FU_ATTR1
         ctx->fused_attr_set = true;
     }
     const int grid = ctx->num_sms;
-#define MSBT_FU_LAUNCH(KW, HV)                                                                                     \
-    {                                                                                                              \
-        if (p2 && full) kmer_bloom_fused_kernel<KW, HV, true, true><<<grid, FU_THREADS, FU_SMEM_BYTES, stream>>>(P, spec);   \
-        else if (p2) kmer_bloom_fused_kernel<KW, HV, true, false><<<grid, FU_THREADS, FU_SMEM_BYTES, stream>>>(P, spec);     \
-        else if (full) kmer_bloom_fused_kernel<KW, HV, false, true><<<grid, FU_THREADS, FU_SMEM_BYTES, stream>>>(P, spec);   \
-        else kmer_bloom_fused_kernel<KW, HV, false, false><<<grid, FU_THREADS, FU_SMEM_BYTES, stream>>>(P, spec);            \
+#define MSBT_FU_LAUNCH1(KW, HV, NBM_)                                                                                        \
+    {                                                                                                                        \
+        if (p2 && full) kmer_bloom_fused_kernel<KW, HV, true, true, NBM_><<<grid, FU_THREADS, smem_bytes, stream>>>(P, spec);    \
+        else if (p2) kmer_bloom_fused_kernel<KW, HV, true, false, NBM_><<<grid, FU_THREADS, smem_bytes, stream>>>(P, spec);      \
+        else if (full) kmer_bloom_fused_kernel<KW, HV, false, true, NBM_><<<grid, FU_THREADS, smem_bytes, stream>>>(P, spec);    \
+        else kmer_bloom_fused_kernel<KW, HV, false, false, NBM_><<<grid, FU_THREADS, smem_bytes, stream>>>(P, spec);             \
     }
+#define MSBT_FU_LAUNCH(KW, HV) { if (nbm == FU_NBM_SMALL) MSBT_FU_LAUNCH1(KW, HV, FU_NBM_SMALL) else MSBT_FU_LAUNCH1(KW, HV, FU_NBM_LARGE) }
     const int hv = msbt_hash_variant(k);
     const bool p2 = spec.pos.pow2 != 0, full = spec.pos.modulus <= spec.pos.num_bits;
     if (hv == 0) MSBT_FU_LAUNCH(1, 0)
     else if (hv == 1) MSBT_FU_LAUNCH(2, 1)
     else MSBT_FU_LAUNCH(2, 2)
 #undef MSBT_FU_LAUNCH
+#undef MSBT_FU_LAUNCH1
     LAUNCH_CHECK(ctx);
     // genomes whose ring buckets overflowed (skewed inputs) are completed by the direct kernel
     return launch_direct(ctx, d_packed, d_run_ends, P.genomes, n_genomes, tiles, spec, d_filters, P.dirty, stream);
@@ -1426,6 +1437,26 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
         const int rc = build_tiled(ctx, d_packed, d_run_ends, dg, tiles, spec, words, d_filters, stream);
         if (rc <= 0) return rc;
         if (variant == 2) return fail(ctx, MSBT_EINVAL, "variant 2: bucket scratch exceeds 2^32 entries per filter");
+    }
+
+    // Direct kernel in L2-sized groups: with every filter of a large batch zeroed up front, none of them is L2-resident by
+    // the time its genome is hashed, and each RED becomes a DRAM sector read-modify-write (146 us/genome at 2^28 bits).
+    // Zeroing a group of genomes whose filters fit L2 together right before hashing that group keeps the REDs in L2.
+    uint64_t group_mb = 0;
+    if (const char *e = getenv("MSBT_DIRECT_GROUP_MB")) group_mb = strtoull(e, nullptr, 10);
+    if (group_mb && min_abund <= 1 && distinct && tiles && words * 8 <= (group_mb << 20) && (uint64_t)n_genomes * words * 8 > (group_mb << 20)) {
+        size_t table_b = 0;
+        int rc = stage_genome_table(ctx, dg, &table_b, stream);
+        if (rc) return rc;
+        const uint32_t per_group = (uint32_t)std::max<uint64_t>(1, (group_mb << 20) / (words * 8));
+        for (uint32_t g0 = 0; g0 < n_genomes; g0 += per_group) {
+            const uint32_t g1 = std::min(n_genomes, g0 + per_group);
+            for (uint32_t i = g0; i < g1; i++) CU_TRY(ctx, cudaMemsetAsync(d_filters + dg[i].filter_word_off, 0, words * 8, stream));
+            const uint64_t t0 = dg[g0].tile_begin, t1 = g1 < n_genomes ? dg[g1].tile_begin : tiles;
+            rc = launch_direct(ctx, d_packed, d_run_ends, (const DevGenome *)ctx->d_scratch, n_genomes, t1, spec, d_filters, nullptr, stream, t0);
+            if (rc) return rc;
+        }
+        return MSBT_OK;
     }
 
     // zero-fill every output filter (the reference always writes a complete new file)

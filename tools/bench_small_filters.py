@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """K1 across small filter sizes (real MetaSBT databases use 2^22..2^26 bits) and variants: us/genome.
-    python tools/bench_small_filters.py [genomes] [genome_bp]"""
+    python tools/bench_small_filters.py [genomes] [genome_bp] [log2 sizes, comma separated] [variants, comma separated]"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -11,11 +11,13 @@ ctx = ops.Context(0)
 dev = ctx.device
 words = [synth.packed_genome(0x5EED0000 + g, bp, dev) for g in range(n)]
 batch = ops.GenomeBatch.from_device_words(words, [bp] * n, dev)
+sizes = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else list(range(20, 29))
+variants = [int(x) for x in sys.argv[4].split(",")] if len(sys.argv) > 4 else [0, 1, 2, 3]
 res = {}
-for lb in range(20, 29):
+for lb in sizes:
     out = ctx.alloc_filters(n, 1 << lb)
     row = {}
-    for variant in (0, 1, 2, 3):
+    for variant in variants:
         try:
             ctx.build_filters(batch, 31, 1 << lb, out=out, variant=variant)
             torch.cuda.synchronize()
@@ -29,4 +31,4 @@ for lb in range(20, 29):
             row["v%d" % variant] = "n/a"
     res["2^%d" % lb] = row
     del out
-print(json.dumps({"genomes": n, "genome_bp": bp, "us_per_genome": res}))
+print(json.dumps({"lib": os.environ.get("MSBT_LIB", "default"), "direct_group_mb": os.environ.get("MSBT_DIRECT_GROUP_MB"), "genomes": n, "genome_bp": bp, "us_per_genome": res}))
