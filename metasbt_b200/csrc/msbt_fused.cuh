@@ -291,7 +291,17 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
                         const uint32_t b = rb + lane + 32 * j;
                         if (b < r1) {
                             uint32_t n = nn[j];
-                            if (n && oo[j] + ((n + 3u) & ~3u) > P.gcap) { *dirty_g = 1u; n = 0; }  // ring bucket full: redone by the direct kernel
+                            if (n && oo[j] + ((n + 3u) & ~3u) > P.gcap) {
+                                // ring bucket full (skewed input): the direct kernel redoes this genome afterwards.  B reads
+                                // min(count, gcap) entries of the bucket, so the tail this reservation leaves unwritten is
+                                // padded with a position that does belong to the bucket (OR is idempotent) -- stale ring
+                                // content there would set bits the redo pass cannot take back.
+                                *dirty_g = 1u;
+                                const uint32_t first = stage[b * P.cap];
+                                for (uint32_t o = oo[j]; o + 4u <= P.gcap; o += 4u)
+                                    *(uint4 *)(gb + (uint64_t)b * P.gcap + o) = make_uint4(first, first, first, first);
+                                n = 0;
+                            }
                             cnt[b] = (oo[j] << 8) | n;
                         }
                     }

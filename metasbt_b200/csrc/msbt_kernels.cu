@@ -551,8 +551,18 @@ kmer_partition_kernel(const uint64_t *__restrict__ packed, const uint32_t *__res
             uint32_t o = 0;
             if (n) {
                 const uint32_t n4 = (n + 3u) & ~3u;
-                o = atomicAdd(gc + b, n4);
-                o = (o + n4 <= P.gcap) ? b * P.gcap + o : PT_SKIP;
+                const uint32_t o_raw = atomicAdd(gc + b, n4);
+                if (o_raw + n4 <= P.gcap) {
+                    o = b * P.gcap + o_raw;
+                } else {
+                    // scratch bucket full: the entries take the overflow path.  tile_build reads min(count, gcap) entries, so
+                    // the tail this reservation leaves unwritten is padded with a position of this very bucket (OR is
+                    // idempotent); stale scratch content there could set foreign bits.
+                    o = PT_SKIP;
+                    const uint32_t first = stage[b * PT_CAP];
+                    uint32_t *tail = gbuf + ((uint64_t)gl * NB + b) * P.gcap;
+                    for (uint32_t t = o_raw; t < P.gcap; t++) tail[t] = first;
+                }
             }
             base[b] = o;
         }

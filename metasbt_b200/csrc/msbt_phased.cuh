@@ -280,6 +280,10 @@ kmer_bloom_phased_kernel(PhasedParams P, KmerSpec spec) {
                             dst4[nq - 1] = v;
                         } else {
                             *dirty_g = 1u;  // ring bucket full (skewed input): the direct kernel redoes this genome
+                            // pad the tail this reservation leaves unwritten (the BUILD phase reads min(count, gcap) entries)
+                            const uint32_t first = stage4[b * P.quads].x;
+                            for (uint32_t o = orow[j]; o + 4u <= P.gcap; o += 4u)
+                                *(uint4 *)(gb + (uint64_t)b * P.gcap + o) = make_uint4(first, first, first, first);
                         }
                     }
                 }

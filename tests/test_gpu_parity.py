@@ -680,3 +680,23 @@ def test_rectangular_all_pairs(ctx, oracle, na, nb, num_bits):
     want = np.array([[oracle.bf_and_popcount(flt[i], flt[na + j]) for j in range(nb)] for i in range(na)], dtype=np.int64)
     assert np.array_equal(got, want)
     assert ctx.bf_rect([], b, num_bits).shape == (0, nb)
+
+
+@pytest.mark.parametrize("variant", [2, 3, 4])
+@pytest.mark.parametrize("num_bits", [1 << 17, 200003, 1 << 20, (1 << 22) + 64])
+def test_makebf_skewed_batch_after_a_random_one(ctx, oracle, variant, num_bits):
+    """A skewed genome overflows its ring / scratch bucket and is completed by the direct redo pass, which can only ADD
+    bits: whatever a rejected reservation leaves unwritten in the bucket must not be read as positions.  The scratch is
+    first filled with the positions of a random batch of the same geometry, then low-complexity genomes are built."""
+    rng = random.Random(num_bits + variant)
+    noise = [util.codes_to_fasta(util.synthetic_codes(900 + i, 40_000), "n%d" % i) for i in range(6)]
+    build(ctx, noise, 21, num_bits, variant=variant)
+    skewed = [b">polyA\n" + b"A" * 30_000 + b"\n",
+              b">two\n" + b"AC" * 20_000 + b"\n",
+              util.messy_fasta(rng, 4, 6000, "ACGTN"),
+              b">mix\n" + b"ACGT" * 3000 + b"N" + b"T" * 25_000 + b"\n"]
+    for k in (1, 2, 5, 21):
+        _, got = build(ctx, skewed, k, num_bits, variant=variant)
+        for f, g in zip(skewed, got):
+            assert np.array_equal(g, oracle.makebf(f, k, num_bits)), (k, f[:12])
+        build(ctx, noise, 21, num_bits, variant=variant)
