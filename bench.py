@@ -321,12 +321,37 @@ def run_e2e(args, ctx, rank, world, device, barrier, dist, check_filter0):
     if world > 1:
         dist.all_reduce(tc, op=dist.ReduceOp.MAX)
     d2h_gbs = 4 * (1 << 30) / float(tc.item()) / 1e9
+    # ... and the ceiling of the sparse transport: all ranks writing dense filter words into host memory at once (the
+    # zero-fill half of msbt_positions_expand on an empty position list, on the threads the pipeline uses), no GPU involved
+    from concurrent.futures import ThreadPoolExecutor
+    from metasbt_b200 import ops as _ops
+    rows = max(1, (1 << 30) // (m // 8))
+    host_rows = buf_h.numpy().view(np.uint64)[: rows * (m // 64)].reshape(rows, m // 64)
+    empty = np.zeros(0, dtype=np.uint32)
+    threads = max(1, min(args.e2e_chunk, os.cpu_count() or 1))
+    with ThreadPoolExecutor(max_workers=threads) as ex:
+        list(ex.map(lambda i: _ops.positions_expand(empty, m, host_rows[i % rows]), range(threads)))
+        barrier()
+        t0 = time.perf_counter()
+        reps = 4 * max(threads, rows)
+        list(ex.map(lambda i: _ops.positions_expand(empty, m, host_rows[i % rows]), range(reps)))
+        barrier()
+        dt = time.perf_counter() - t0
+    tw = torch.tensor([dt], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+    host_write_gbs = reps * (m // 8) / float(tw.item()) / 1e9
     best = max(out, key=lambda md: out[md]["value"])
     e2e = out[best]
     e2e["note"] = ("FASTA bytes pinned-host->device + device ingest + K1 + every filter back in pinned host memory each step; "
                    "%s transport" % best)
     e2e["d2h_ceiling_gbs_per_gpu_all_ranks_copying"] = d2h_gbs
     e2e["dense_ceiling_mbp_s"] = d2h_gbs * 1e9 / (m // 8) * G * world / 1e6
+    e2e["host_filter_write_gbs_per_rank_all_ranks_writing"] = host_write_gbs
+    e2e["sparse_ceiling_mbp_s"] = host_write_gbs * 1e9 / (m // 8) * G * world / 1e6
+    e2e["ceilings_note"] = ("every genome's result is a %d MiB filter in host memory: the dense transport cannot beat the box's device->host copy rate, "
+                            "the sparse one cannot beat the rate at which the host cores write filter words; both are measured here with all ranks "
+                            "active and nothing else running" % (m // 8 // 2 ** 20))
     alt = out["sparse" if best == "dense" else "dense"]
     return e2e, alt
 

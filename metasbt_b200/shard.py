@@ -96,17 +96,19 @@ def exchange_plan(counts_all: Sequence[Sequence[Sequence[int]]], rank: int) -> T
 
 
 def query_exchange_sharded(ctx, sliced: torch.Tensor, n_leaves: int, num_bits: int, local_filters: Sequence[torch.Tensor],
-                           group=None, timings: dict | None = None) -> torch.Tensor:
+                           group=None, timings: dict | None = None, cap: int | None = None,
+                           batch_size: int | None = None) -> torch.Tensor:
     """K4 across ranks with the HASHING sharded as well (second option).  Every rank has hashed only
     its block of the MAG batch (query_blocks): `local_filters` are those MAGs' own min=1 filters.  Per step:
-      1. K3' on word sub-views: how many positions of each local MAG fall into each rank's bit range (one launch, one
-         small device->host copy, one all_gather of the counts);
-      2. per destination rank one batched ordered extraction of that bit range straight into the send buffer
-         (positions relative to the range start);
+      1. ONE batched ordered extraction over the word sub-views (destination-major) of the local filters: the positions of
+         every local MAG inside every rank's bit range, relative to the range start, land in the send buffer in exactly the
+         order the exchange wants; the extraction's offsets give the split sizes (one small device->host copy);
+      2. all_gather of the per-(MAG, destination) counts (a fixed-size tensor when `batch_size` is given);
       3. all_to_all of the position lists (rank r receives, MAG by MAG, the positions inside ITS rows);
       4. one bit-sliced probe of the local shard with the positions of the WHOLE batch -> partial hits[B][L];
       5. all_reduce(SUM) of the partial hit matrices.
-    Returns int32[B, L] on every rank, B = the batch size over all ranks, in rank order."""
+    `cap`: upper bound on the number of positions of the local MAGs (e.g. their summed lengths); None sizes the send
+    buffer with a popcount pass.  Returns int32[B, L] on every rank, B = the batch size over all ranks, in rank order."""
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     dev = ctx.device
@@ -116,28 +118,45 @@ def query_exchange_sharded(ctx, sliced: torch.Tensor, n_leaves: int, num_bits: i
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timings is not None else None
     if ev:
         ev[0].record()
-    # 1. counts[q][d]
-    views = [f[w0:w1] for w0, w1 in words for f in local_filters]  # d-major
-    if n_local:
-        counts = ctx.bf_popcount(views, 64 * max(w1 - w0 for w0, w1 in words)) if len({w1 - w0 for w0, w1 in words}) == 1 else \
-            torch.cat([ctx.bf_popcount(views[d * n_local:(d + 1) * n_local], 64 * (words[d][1] - words[d][0])) for d in range(world)])
-        counts_h = counts.view(world, n_local).t().contiguous().cpu().tolist()  # [q][d]
+    # 1. positions, destination-major, straight into the send buffer
+    equal = len({w1 - w0 for w0, w1 in words}) == 1
+    if n_local == 0:
+        counts_h: List[List[int]] = []
+        send = torch.empty(1, dtype=torch.int32, device=dev)
     else:
-        counts_h = []
-    if world > 1:
-        gathered: List[object] = [None] * world
+        if cap is None:
+            cap = int(ctx.bf_popcount(list(local_filters), num_bits).sum().item())
+        send = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+        if equal:
+            views = [f[w0:w1] for w0, w1 in words for f in local_filters]
+            offs = ctx.extract_positions_into(views, 64 * (words[0][1] - words[0][0]), send).cpu().tolist()
+        else:  # ragged ranges: one extraction per destination
+            offs, cursor = [0], 0
+            for w0, w1 in words:
+                o = ctx.extract_positions_into([f[w0:w1] for f in local_filters], 64 * (w1 - w0), send[cursor:]).cpu().tolist()
+                offs.extend(cursor + x for x in o[1:])
+                cursor += o[-1]
+        if offs[-1] > send.numel():
+            raise ValueError("query_exchange_sharded: `cap` is smaller than the number of positions of the local queries")
+        counts_h = [[offs[d * n_local + q + 1] - offs[d * n_local + q] for d in range(world)] for q in range(n_local)]
+    # 2. everybody's counts
+    if world == 1:
+        gathered: List[List[List[int]]] = [counts_h]
+    elif batch_size is not None:
+        blocks = query_blocks(batch_size, world)
+        n_max = max(e - b for b, e in blocks)
+        mine = torch.zeros((n_max, world), dtype=torch.int64)
+        if n_local:
+            mine[:n_local] = torch.tensor(counts_h, dtype=torch.int64)
+        mine = mine.to(dev)
+        allc = torch.empty((world, n_max, world), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(allc, mine, group=group)
+        allc_h = allc.cpu().tolist()
+        gathered = [allc_h[r][: blocks[r][1] - blocks[r][0]] for r in range(world)]
+    else:
+        gathered = [None] * world  # type: ignore[list-item]
         dist.all_gather_object(gathered, counts_h, group=group)
-    else:
-        gathered = [counts_h]
     send_sizes, recv_sizes, q_ranges = exchange_plan(gathered, rank)
-    # 2. per destination, straight into the send buffer
-    send = torch.empty(max(sum(send_sizes), 1), dtype=torch.int32, device=dev)
-    cursor = 0
-    for d in range(world):
-        if send_sizes[d]:
-            w0, w1 = words[d]
-            ctx.extract_positions_into([f[w0:w1] for f in local_filters], 64 * (w1 - w0), send[cursor: cursor + send_sizes[d]])
-        cursor += send_sizes[d]
     if ev:
         ev[1].record()
     # 3. exchange
@@ -158,7 +177,7 @@ def query_exchange_sharded(ctx, sliced: torch.Tensor, n_leaves: int, num_bits: i
     if ev:
         ev[4].record()
         torch.cuda.synchronize(dev)
-        for name, i in (("ms_count_extract", 0), ("ms_all_to_all", 1), ("ms_probe", 2), ("ms_all_reduce", 3)):
+        for name, i in (("ms_extract_and_counts", 0), ("ms_all_to_all", 1), ("ms_probe", 2), ("ms_all_reduce", 3)):
             timings[name] = timings.get(name, 0.0) + ev[i].elapsed_time(ev[i + 1])
         timings["positions_in_shard"] = timings.get("positions_in_shard", 0) + sum(recv_sizes)
     return hits

@@ -85,6 +85,8 @@ def main():
     hits3 = shard.query_exchange_sharded(ctx, sliced, n, m, [qf[i] for i in range(qb, qe)], timings=timings)
     assert np.array_equal(hits3.cpu().numpy().astype(np.uint64), ref), "K4 query_exchange_sharded rank %d" % rank
     assert "ms_probe" in timings
+    hits4 = shard.query_exchange_sharded(ctx, sliced, n, m, [qf[i] for i in range(qb, qe)], cap=(qe - qb) * 40_000, batch_size=len(queries))
+    assert np.array_equal(hits4.cpu().numpy().astype(np.uint64), ref), "K4 query_exchange_sharded (cap, batch_size) rank %d" % rank
     # K3 all pairs over the filter set as it is spread over the ranks (half ring of rectangular launches over NCCL send/recv)
     local = shard.all_pairs_ring(ctx, mine, m, chunk=3)
     full = shard.all_pairs_assemble(local)

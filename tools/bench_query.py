@@ -75,7 +75,7 @@ def run(ctx, rank: int, world: int, leaves: int = 10000, filter_bits: int = 1 <<
             ctx.build_filters(qbatch, k, m, out=qf)  # K1 on this rank's block of the batch
         if replicated_hash:
             return shard.query_sharded(ctx, sliced, L, m, qrows, cap=mags * mag_bp)
-        return shard.query_exchange_sharded(ctx, sliced, L, m, qrows, timings=tm)
+        return shard.query_exchange_sharded(ctx, sliced, L, m, qrows, timings=tm, cap=(qe - qb) * mag_bp, batch_size=mags)
 
     def barrier():
         torch.cuda.synchronize()
