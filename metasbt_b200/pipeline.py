@@ -63,7 +63,9 @@ class SketchPipeline:
         self._text_cap = 0
         self._sparse = False
         import os
-        self._threads = expand_threads or max(1, min(self.chunk, (os.cpu_count() or 2)))
+        # host threads that rebuild dense words (sparse transport): the box's cores are shared by the ranks on it
+        ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1))
+        self._threads = expand_threads or max(2, min(self.chunk, (os.cpu_count() or 2) // ranks_here))
         self._pool = ThreadPoolExecutor(max_workers=self._threads)
         self._sinks = ThreadPoolExecutor(max_workers=self.n_slots)
         self.h2d_bytes = 0

@@ -95,29 +95,26 @@ def exchange_plan(counts_all: Sequence[Sequence[Sequence[int]]], rank: int) -> T
     return send, recv, ranges
 
 
-def query_exchange_sharded(ctx, sliced: torch.Tensor, n_leaves: int, num_bits: int, local_filters: Sequence[torch.Tensor],
-                           group=None, timings: dict | None = None, cap: int | None = None,
-                           batch_size: int | None = None) -> torch.Tensor:
-    """K4 across ranks with the HASHING sharded as well (SURVEY.md 8e, K4 row, second option).  Every rank has hashed only
-    its block of the MAG batch (query_blocks): `local_filters` are those MAGs' own min=1 filters.  Per step:
-      1. ONE batched ordered extraction over the word sub-views (destination-major) of the local filters: the positions of
-         every local MAG inside every rank's bit range, relative to the range start, land in the send buffer in exactly the
-         order the exchange wants; the extraction's offsets give the split sizes (one small device->host copy);
-      2. all_gather of the per-(MAG, destination) counts (a fixed-size tensor when `batch_size` is given);
-      3. all_to_all of the position lists (rank r receives, MAG by MAG, the positions inside ITS rows);
-      4. one bit-sliced probe of the local shard with the positions of the WHOLE batch -> partial hits[B][L];
-      5. all_reduce(SUM) of the partial hit matrices.
-    `cap`: upper bound on the number of positions of the local MAGs (e.g. their summed lengths); None sizes the send
-    buffer with a popcount pass.  Returns int32[B, L] on every rank, B = the batch size over all ranks, in rank order."""
+class QueryExchange:
+    """What query_exchange_prepare hands to query_exchange_finish: the positions of the WHOLE batch inside this rank's bit
+    range (device, relative to the range start) and each query's [begin, end) inside them."""
+
+    def __init__(self, recv: torch.Tensor, q_ranges: List[Tuple[int, int]], n_received: int):
+        self.recv, self.q_ranges, self.n_received = recv, q_ranges, n_received
+
+
+def query_exchange_prepare(ctx, num_bits: int, local_filters: Sequence[torch.Tensor], group=None, cap: int | None = None,
+                           batch_size: int | None = None, events: list | None = None) -> QueryExchange:
+    """Steps 1-3 of query_exchange_sharded (extraction, counts, all_to_all) on torch's CURRENT stream -- callers that
+    pipeline batches run it on a side stream while the previous batch is being probed."""
     world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
     rank = dist.get_rank(group) if world > 1 else 0
     dev = ctx.device
     n_local = len(local_filters)
     ranges_bits = bit_ranges(num_bits, world)
     words = [(b // 64, (e + 63) // 64) for b, e in ranges_bits]
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timings is not None else None
-    if ev:
-        ev[0].record()
+    if events:
+        events[0].record()
     # 1. positions, destination-major, straight into the send buffer
     equal = len({w1 - w0 for w0, w1 in words}) == 1
     if n_local == 0:
@@ -137,7 +134,7 @@ def query_exchange_sharded(ctx, sliced: torch.Tensor, n_leaves: int, num_bits: i
                 offs.extend(cursor + x for x in o[1:])
                 cursor += o[-1]
         if offs[-1] > send.numel():
-            raise ValueError("query_exchange_sharded: `cap` is smaller than the number of positions of the local queries")
+            raise ValueError("query_exchange: `cap` is smaller than the number of positions of the local queries")
         counts_h = [[offs[d * n_local + q + 1] - offs[d * n_local + q] for d in range(world)] for q in range(n_local)]
     # 2. everybody's counts
     if world == 1:
@@ -157,29 +154,60 @@ def query_exchange_sharded(ctx, sliced: torch.Tensor, n_leaves: int, num_bits: i
         gathered = [None] * world  # type: ignore[list-item]
         dist.all_gather_object(gathered, counts_h, group=group)
     send_sizes, recv_sizes, q_ranges = exchange_plan(gathered, rank)
-    if ev:
-        ev[1].record()
+    if events:
+        events[1].record()
     # 3. exchange
     if world > 1:
         recv = torch.empty(max(sum(recv_sizes), 1), dtype=torch.int32, device=dev)
         dist.all_to_all_single(recv[: sum(recv_sizes)], send[: sum(send_sizes)], recv_sizes, send_sizes, group=group)
     else:
         recv = send
+    if events:
+        events[2].record()
+    return QueryExchange(recv, q_ranges, sum(recv_sizes))
+
+
+def query_exchange_finish(ctx, sliced: torch.Tensor, n_leaves: int, num_bits: int, ex: QueryExchange, group=None,
+                          events: list | None = None, reduce: bool = True) -> torch.Tensor:
+    """Steps 4-5: probe this rank's shard with the exchanged positions, sum the partial hit matrices."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    rb, re_ = bit_ranges(num_bits, world)[rank]
+    ex.recv.record_stream(torch.cuda.current_stream(ctx.device)) if ex.recv.is_cuda else None
+    hits = ctx.query_sliced_ranges(sliced, n_leaves, 0, re_ - rb, ex.recv, ex.q_ranges)  # row indices relative to the range
+    if events:
+        events[3].record()
+    if reduce:
+        all_reduce_counts(hits, group)
+    if events:
+        events[4].record()
+    return hits
+
+
+def query_exchange_sharded(ctx, sliced: torch.Tensor, n_leaves: int, num_bits: int, local_filters: Sequence[torch.Tensor],
+                           group=None, timings: dict | None = None, cap: int | None = None,
+                           batch_size: int | None = None) -> torch.Tensor:
+    """K4 across ranks with the HASHING sharded as well (SURVEY.md 8e, K4 row, second option).  Every rank has hashed only
+    its block of the MAG batch (query_blocks): `local_filters` are those MAGs' own min=1 filters.  Per step:
+      1. ONE batched ordered extraction over the word sub-views (destination-major) of the local filters: the positions of
+         every local MAG inside every rank's bit range, relative to the range start, land in the send buffer in exactly the
+         order the exchange wants; the extraction's offsets give the split sizes (one small device->host copy);
+      2. all_gather of the per-(MAG, destination) counts (a fixed-size tensor when `batch_size` is given);
+      3. all_to_all of the position lists (rank r receives, MAG by MAG, the positions inside ITS rows);
+      4. one bit-sliced probe of the local shard with the positions of the WHOLE batch -> partial hits[B][L];
+      5. all_reduce(SUM) of the partial hit matrices.
+    `cap`: upper bound on the number of positions of the local MAGs (e.g. their summed lengths); None sizes the send
+    buffer with a popcount pass.  Returns int32[B, L] on every rank, B = the batch size over all ranks, in rank order.
+    query_exchange_prepare (1-3) and query_exchange_finish (4-5) are the two halves, for callers that overlap the
+    preparation of the next batch with the probe of the current one."""
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if timings is not None else None
+    ex = query_exchange_prepare(ctx, num_bits, local_filters, group, cap, batch_size, ev)
+    hits = query_exchange_finish(ctx, sliced, n_leaves, num_bits, ex, group, ev)
     if ev:
-        ev[2].record()
-    # 4. probe (row indices are relative to this rank's range)
-    rb, re_ = ranges_bits[rank]
-    hits = ctx.query_sliced_ranges(sliced, n_leaves, 0, re_ - rb, recv, q_ranges)
-    if ev:
-        ev[3].record()
-    # 5. sum the partial matrices
-    all_reduce_counts(hits, group)
-    if ev:
-        ev[4].record()
-        torch.cuda.synchronize(dev)
+        torch.cuda.synchronize(ctx.device)
         for name, i in (("ms_extract_and_counts", 0), ("ms_all_to_all", 1), ("ms_probe", 2), ("ms_all_reduce", 3)):
             timings[name] = timings.get(name, 0.0) + ev[i].elapsed_time(ev[i + 1])
-        timings["positions_in_shard"] = timings.get("positions_in_shard", 0) + sum(recv_sizes)
+        timings["positions_in_shard"] = timings.get("positions_in_shard", 0) + ex.n_received
     return hits
 
 

@@ -25,7 +25,7 @@ sys.path.insert(0, ROOT)
 
 def run(ctx, rank: int, world: int, leaves: int = 10000, filter_bits: int = 1 << 25, mags: int = 256,
         genome_bp: int = 5_000_000, mag_bp: int = 2_000_000, steps: int = 3, warmup: int = 1, replicated_hash: bool = False,
-        peak_gbs: float = 6537.6):
+        peak_gbs: float = 6537.6, pipelined: bool = True):
     """-> the result dict on rank 0, None elsewhere.  torch.distributed must be initialised when world > 1."""
     import torch
     import torch.distributed as dist
@@ -83,13 +83,41 @@ def run(ctx, rank: int, world: int, leaves: int = 10000, filter_bits: int = 1 <<
             dist.barrier()
         torch.cuda.synchronize()
 
+    # Batches are pipelined over two streams: while the shard is probed with batch i (main stream), batch i + 1 is hashed,
+    # its positions extracted and exchanged (side stream) -- what a stream of query batches looks like in production.
+    main, side = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
+
+    def prepare(first=False):
+        if first:
+            side.wait_stream(main)  # (later batches must NOT wait for the probe that was just queued on the main stream)
+        with torch.cuda.stream(side):
+            if qe > qb:
+                ctx.build_filters(qbatch, k, m, out=qf)
+            return shard.query_exchange_prepare(ctx, m, qrows, cap=(qe - qb) * mag_bp, batch_size=mags)
+
+    def run_steps(n):
+        out = None
+        ex = prepare(first=True)
+        for i in range(n):
+            main.wait_stream(side)
+            out = shard.query_exchange_finish(ctx, sliced, L, m, ex, reduce=False)   # probe, asynchronous
+            if i + 1 < n:
+                ex = prepare()                                                        # next batch under the probe
+            shard.all_reduce_counts(out)
+        return out
+
     for _ in range(max(warmup, 1)):
         step()
+    if not replicated_hash and pipelined:
+        run_steps(2)
     barrier()
     launches0 = ctx.launch_count
     e0.record()
-    for _ in range(steps):
-        hits = step()
+    if not replicated_hash and pipelined:
+        hits = run_steps(steps)
+    else:
+        for _ in range(steps):
+            hits = step()
     e1.record()
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -133,7 +161,8 @@ def run(ctx, rank: int, world: int, leaves: int = 10000, filter_bits: int = 1 <<
                    "sharding": ("rows [r*m/N, (r+1)*m/N) of the bit-sliced matrix per rank; " +
                                 ("hashing replicated on every rank, extraction and probe per bit range" if replicated_hash else
                                  "MAG hashing sharded across ranks, positions exchanged by bit range (all_to_all), probe per bit range") +
-                                "; hits all_reduce(SUM)"),
+                                "; hits all_reduce(SUM)" + ("; batches pipelined over two streams (hash + exchange of batch i+1 under the probe of batch i)"
+                                                            if pipelined and not replicated_hash else "")),
                    "l2": "the shard (%.1f GB) is far larger than L2" % (sliced.numel() * 4 / 1e9)},
         "gpu_launches": launches,
         "roofline": roof,
@@ -152,6 +181,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--replicated-hash", action="store_true")
+    ap.add_argument("--no-pipeline", action="store_true", help="one batch after the other on one stream")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -173,7 +203,7 @@ def main():
     except Exception:
         pass
     res = run(ops.Context(local), rank, world, a.leaves, a.filter_bits, a.mags, a.genome_bp, a.mag_bp, a.steps, a.warmup,
-              a.replicated_hash, peak)
+              a.replicated_hash, peak, not a.no_pipeline)
     if rank == 0:
         print(json.dumps(res))
     if world > 1:
