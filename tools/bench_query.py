@@ -85,15 +85,17 @@ def run(ctx, rank: int, world: int, leaves: int = 10000, filter_bits: int = 1 <<
 
     # Batches are pipelined over two streams: while the shard is probed with batch i (main stream), batch i + 1 is hashed,
     # its positions extracted and exchanged (side stream) -- what a stream of query batches looks like in production.
+    # A context is driven from one stream at a time (its scratch is shared by its calls): the side stream gets its own.
     main, side = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
+    ctx_side = ops.Context(dev.index) if pipelined and not replicated_hash else ctx
 
     def prepare(first=False):
         if first:
             side.wait_stream(main)  # (later batches must NOT wait for the probe that was just queued on the main stream)
         with torch.cuda.stream(side):
             if qe > qb:
-                ctx.build_filters(qbatch, k, m, out=qf)
-            return shard.query_exchange_prepare(ctx, m, qrows, cap=(qe - qb) * mag_bp, batch_size=mags)
+                ctx_side.build_filters(qbatch, k, m, out=qf)
+            return shard.query_exchange_prepare(ctx_side, m, qrows, cap=(qe - qb) * mag_bp, batch_size=mags)
 
     def run_steps(n):
         out = None
@@ -111,7 +113,7 @@ def run(ctx, rank: int, world: int, leaves: int = 10000, filter_bits: int = 1 <<
     if not replicated_hash and pipelined:
         run_steps(2)
     barrier()
-    launches0 = ctx.launch_count
+    launches0 = ctx.launch_count + (ctx_side.launch_count if ctx_side is not ctx else 0)
     e0.record()
     if not replicated_hash and pipelined:
         hits = run_steps(steps)
@@ -124,7 +126,7 @@ def run(ctx, rank: int, world: int, leaves: int = 10000, filter_bits: int = 1 <<
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     sec = float(ms.item()) / 1e3
-    launches = ctx.launch_count - launches0
+    launches = ctx.launch_count + (ctx_side.launch_count if ctx_side is not ctx else 0) - launches0
     # one more step with per-phase events (synchronises between phases, so it is not part of the timed region)
     if not replicated_hash:
         step(timings)
