@@ -86,7 +86,7 @@ def run(ctx, rank: int, world: int, leaves: int = 10000, filter_bits: int = 1 <<
     # Batches are pipelined over two streams: while the shard is probed with batch i (main stream), batch i + 1 is hashed,
     # its positions extracted and exchanged (side stream) -- what a stream of query batches looks like in production.
     # A context is driven from one stream at a time (its scratch is shared by its calls): the side stream gets its own.
-    main, side = torch.cuda.current_stream(dev), torch.cuda.Stream(dev)
+    main, side = torch.cuda.current_stream(dev), torch.cuda.Stream(dev, priority=-1 if os.environ.get("MSBT_QPIPE_PRIO", "1") != "0" else 0)
     ctx_side = ops.Context(dev.index) if pipelined and not replicated_hash else ctx
 
     def prepare(first=False):
