@@ -4,7 +4,7 @@ metasbt.py:1124-1143) on a synthetic 7-level database: wall-clock MAGs/s from FA
 disk, against the per-genome Database.profile on a sample of the same MAGs.  bench.py reports it as
 secondary.profile_many (N = 1); alone:
 
-    python tools/bench_profile.py [--species 128 --genomes-per-species 4 --genome-bp 200000 --filter-bits 16777216 --mags 512]
+    python tools/bench_profile.py [--species 64 --genomes-per-species 4 --genome-bp 50000 --filter-bits 33554432 --mags 512]
 """
 import argparse
 import json
@@ -24,8 +24,11 @@ def _taxonomy(s: int) -> str:
                      "g__G%d" % (s % 32), "s__S%d" % s])
 
 
-def run(ctx, species: int = 128, per_species: int = 4, genome_bp: int = 200_000, filter_bits: int = 1 << 24, mags: int = 512,
-        mag_bp: int = 100_000, single_sample: int = 32, workdir: str = None):
+def run(ctx, species: int = 64, per_species: int = 4, genome_bp: int = 50_000, filter_bits: int = 1 << 25, mags: int = 512,
+        mag_bp: int = 25_000, single_sample: int = 32, workdir: str = None):
+    """Defaults: 12.8 M k-mers in the database against 2^25-bit filters -- the root filter is about a third full, the regime
+    MetaSBT's own filter-size estimate (the number of distinct k-mers, core.py:470-529) puts a database in; with a filter
+    that saturates at the upper levels every cluster matches every query and the descent visits the whole tree."""
     import torch
     from metasbt_b200 import cli, core, synth
     from metasbt_b200 import ops
@@ -90,6 +93,7 @@ def run(ctx, species: int = 128, per_species: int = 4, genome_bp: int = 200_000,
             "per_genome_profile_mags_per_s": ns / t_single, "per_genome_launches_per_mag": launches_single / ns,
             "batch_speedup": (mags / t_many) / (ns / t_single),
             "index_s": t_index, "sketch_mags_s": t_sketch,
+            "trees_probed_per_mag": sum(len(t[level]) for t in tables for level in t) / max(len(tables), 1),
             "check": {"batch_equals_per_genome": single == tables[:ns], "closest_species_is_source": "%d/%d" % (right, mags)},
             "note": "wall clock through Database.profile_many: FASTA files on disk -> ingest + K1 + extraction for the whole batch, "
                     "8 level-synchronous tree probes (one device->host copy each), one pair-list distance launch, tables on disk"}
@@ -100,11 +104,11 @@ def run(ctx, species: int = 128, per_species: int = 4, genome_bp: int = 200_000,
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("--species", type=int, default=128)
+    ap.add_argument("--species", type=int, default=64)
     ap.add_argument("--genomes-per-species", type=int, default=4)
-    ap.add_argument("--genome-bp", type=int, default=200_000)
-    ap.add_argument("--filter-bits", type=int, default=1 << 24)
+    ap.add_argument("--genome-bp", type=int, default=50_000)
+    ap.add_argument("--filter-bits", type=int, default=1 << 25)
     ap.add_argument("--mags", type=int, default=512)
     a = ap.parse_args()
     from metasbt_b200 import ops
-    print(json.dumps(run(ops.default_context(0), a.species, a.genomes_per_species, a.genome_bp, a.filter_bits, a.mags)))
+    print(json.dumps(run(ops.default_context(0), a.species, a.genomes_per_species, a.genome_bp, a.filter_bits, a.mags, a.genome_bp // 2)))
