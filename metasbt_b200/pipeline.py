@@ -13,13 +13,16 @@ genomes move through the device in chunks, three stages overlapping on three CUD
 PCIe is full duplex, so the output copy of chunk c runs under the input copy, ingest and K1 of chunk c + 1; with
 `slots` >= 2 the consumer of chunk c runs under all of that.  In `sparse` mode a filter leaves the device as the ascending
 list of its set bits (a 5 Mbp genome in a 2^30-bit filter: 20 MB instead of 128 MiB) and the dense words are rebuilt in
-the host slot by msbt_positions_expand on the sink's threads; what the sink sees is identical in both modes.
+the host slot by msbt_positions_expand on the sink's threads; what the sink sees is identical in every mode.  The dense
+transport is bound by the copy engine and leaves the host cores idle, the sparse one is bound by the host cores and
+leaves the copy engine idle: `hybrid` sends part of every chunk either way.
 Pinned buffers and device slots are allocated once per pipeline and reused.
 """
 
 from __future__ import annotations
 
 import threading
+import time
 from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, List, Optional, Sequence
 
@@ -42,18 +45,21 @@ class _Slot:
         self.free = threading.Event()
         self.free.set()
         self.copied = torch.cuda.Event()
+        self.positions_copied = torch.cuda.Event()
         self.error: Optional[BaseException] = None
 
 
 class SketchPipeline:
     """makebf for a stream of genomes whose FASTA text sits in (pinned) host memory; filters are delivered to `sink` in
     host memory, chunk by chunk.  mode: "dense" (filters cross PCIe as they are), "sparse" (position lists cross, dense
-    words rebuilt on the host) or "auto" (sparse when the position lists are expected to be under half the dense bytes)."""
+    words rebuilt on the host), "hybrid" (both at once: part of every chunk dense on the copy engine, the rest sparse on
+    the host cores, the split following their measured costs) or "auto" (hybrid when the position lists are expected to
+    be under half the dense bytes, else dense)."""
 
     def __init__(self, ctx: ops.Context, kmer_size: int, num_bits: int, min_abund: int = 1, chunk_genomes: int = 32,
                  slots: int = 2, mode: str = "auto", variant: int = 0, expand_threads: Optional[int] = None):
-        if mode not in ("dense", "sparse", "auto"):
-            raise ValueError("mode must be dense, sparse or auto")
+        if mode not in ("dense", "sparse", "hybrid", "auto"):
+            raise ValueError("mode must be dense, sparse, hybrid or auto")
         self.ctx, self.k, self.num_bits, self.min_abund = ctx, int(kmer_size), int(num_bits), int(min_abund)
         self.chunk, self.n_slots, self.mode, self.variant = int(chunk_genomes), int(slots), mode, variant
         self.words = ops.filter_words(self.num_bits)
@@ -61,7 +67,9 @@ class SketchPipeline:
         self.stream_out = torch.cuda.Stream(ctx.device)
         self._slots: List[_Slot] = []
         self._text_cap = 0
-        self._sparse = False
+        self._sparse = False                     # any position-list transport (sparse or hybrid)
+        self._hybrid = mode in ("hybrid", "auto")
+        self._dense_fraction = 0.3               # hybrid: share of a chunk that travels dense; follows the measured costs
         import os
         # host threads that rebuild dense words (sparse transport): the box's cores are shared by the ranks on it
         ranks_here = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1))
@@ -81,8 +89,8 @@ class SketchPipeline:
         chunks = [range(lo, min(lo + self.chunk, n)) for lo in range(0, n, self.chunk)]
         text_cap = max((offsets[c[-1] + 1] - offsets[c[0]] for c in chunks), default=1)
         total_text = offsets[-1] - offsets[0]
-        sparse = self.mode == "sparse" or (self.mode == "auto" and self.min_abund <= 1
-                                           and total_text * 4 < n * (self.num_bits // 8) // 2)
+        sparse = self.mode in ("sparse", "hybrid") or (self.mode == "auto" and self.min_abund <= 1
+                                                       and total_text * 4 < n * (self.num_bits // 8) // 2)
         if sparse and self.num_bits > (1 << 32):
             sparse = False
         if not self._slots or text_cap > self._text_cap or sparse != self._sparse:
@@ -123,36 +131,56 @@ class SketchPipeline:
             ctx.build_filters(batch, self.k, self.num_bits, min_abund=self.min_abund, out=slot.d_filters, variant=self.variant)
             if on_device is not None:
                 on_device(members[0], slot.d_filters[:nc])
-            if self._sparse:
-                pos, offs = ctx.extract_positions_packed([slot.d_filters[i] for i in range(nc)], self.num_bits, cap=max(e - b, 1))
-                built = torch.cuda.Event()
-                built.record(main)
-                with torch.cuda.stream(self.stream_out):
-                    self.stream_out.wait_event(built)
+            # Output: the first n_dense filters of the chunk cross PCIe as they are (copy engine, no host work), the rest as
+            # position lists that host threads expand -- the two transports run side by side (hybrid), the split follows
+            # their measured per-genome costs.
+            n_dense = nc if not self._sparse else (min(nc, int(round(nc * self._dense_fraction))) if self._hybrid else 0)
+            offs = None
+            if n_dense < nc:
+                sparse_rows = [slot.d_filters[i] for i in range(n_dense, nc)]
+                cap = max(sum(sizes[n_dense:]), 1)
+                pos, offs = ctx.extract_positions_packed(sparse_rows, self.num_bits, cap=cap)
+            built = torch.cuda.Event()
+            built.record(main)
+            t_dense = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if 0 < n_dense < nc else None
+            with torch.cuda.stream(self.stream_out):
+                self.stream_out.wait_event(built)
+                if offs is not None:
                     slot.h_positions[: offs[-1]].copy_(pos[: offs[-1]], non_blocking=True)
-                    slot.copied.record(self.stream_out)
+                    slot.positions_copied.record(self.stream_out)
+                    self.d2h_bytes += offs[-1] * 4
+                if n_dense:
+                    if t_dense:
+                        t_dense[0].record(self.stream_out)
+                    slot.h_filters[:n_dense].copy_(slot.d_filters[:n_dense, : self.words], non_blocking=True)
+                    if t_dense:
+                        t_dense[1].record(self.stream_out)
+                    self.d2h_bytes += n_dense * self.words * 8
+                slot.copied.record(self.stream_out)
+            if offs is not None:
                 pos.record_stream(self.stream_out)
-                self.d2h_bytes += offs[-1] * 4
-            else:
-                offs = None
-                built = torch.cuda.Event()
-                built.record(main)
-                with torch.cuda.stream(self.stream_out):
-                    self.stream_out.wait_event(built)
-                    slot.h_filters[:nc].copy_(slot.d_filters[:nc, : self.words], non_blocking=True)
-                    slot.copied.record(self.stream_out)
-                self.d2h_bytes += nc * self.words * 8
-            jobs.append(self._sinks.submit(self._consume, slot, members[0], nc, offs, sink))
+            jobs.append(self._sinks.submit(self._consume, slot, members[0], nc, n_dense, offs, sink, t_dense))
         for j in jobs:
             j.result()
 
-    def _consume(self, slot: _Slot, first: int, nc: int, offs: Optional[List[int]], sink) -> None:
+    def _consume(self, slot: _Slot, first: int, nc: int, n_dense: int, offs: Optional[List[int]], sink, t_dense) -> None:
         try:
-            slot.copied.synchronize()
             host = slot.h_filters.numpy().view(np.uint64)
+            t_expand = 0.0
             if offs is not None:
+                slot.positions_copied.synchronize()   # the position lists are here: expand while the dense rows still travel
                 hp = slot.h_positions.numpy().view(np.uint32)
-                list(self._pool.map(lambda i: ops.positions_expand(hp[offs[i]: offs[i + 1]], self.num_bits, host[i]), range(nc)))
+                t0 = time.perf_counter()
+                list(self._pool.map(lambda i: ops.positions_expand(hp[offs[i]: offs[i + 1]], self.num_bits, host[n_dense + i]),
+                                    range(nc - n_dense)))
+                t_expand = time.perf_counter() - t0
+            slot.copied.synchronize()
+            if t_dense is not None and t_expand > 0:
+                # per-genome cost of either transport -> the split that would have made both finish together
+                c_dense = t_dense[0].elapsed_time(t_dense[1]) / 1e3 / n_dense
+                c_sparse = t_expand / (nc - n_dense)
+                target = c_sparse / (c_sparse + c_dense)
+                self._dense_fraction = min(0.9, max(0.05, 0.5 * self._dense_fraction + 0.5 * target))
             if sink is not None:
                 sink(first, host[:nc])
         except BaseException as exc:  # surfaced by run() at the slot's next use or at the end

@@ -700,3 +700,37 @@ def test_makebf_skewed_batch_after_a_random_one(ctx, oracle, variant, num_bits):
         for f, g in zip(skewed, got):
             assert np.array_equal(g, oracle.makebf(f, k, num_bits)), (k, f[:12])
         build(ctx, noise, 21, num_bits, variant=variant)
+
+
+@pytest.mark.parametrize("mode", ["dense", "sparse", "hybrid", "auto"])
+def test_sketch_pipeline_every_transport(ctx, oracle, mode):
+    """pipeline.SketchPipeline: host FASTA bytes -> filters in host memory, chunked over three streams; the sink sees the
+    oracle's filters whatever the transport (dense copy, position lists expanded on the host, both at once)."""
+    from metasbt_b200 import pipeline
+    rng = random.Random(len(mode))
+    k, num_bits = 21, (1 << 20) + 64
+    fastas = [util.messy_fasta(rng, 2, 6000, "ACGTN") for _ in range(23)] + [b">empty\n", util.codes_to_fasta(util.synthetic_codes(5, 30_000), "big")]
+    offsets = [0]
+    for f in fastas:
+        offsets.append(offsets[-1] + len(f))
+    text = torch.empty(offsets[-1], dtype=torch.uint8, pin_memory=True)
+    text.numpy()[:] = np.frombuffer(b"".join(fastas), dtype=np.uint8)
+    pipe = pipeline.SketchPipeline(ctx, k, num_bits, chunk_genomes=4, slots=2, mode=mode)
+    got = {}
+    seen_on_device = []
+
+    def sink(first, words):
+        for i in range(len(words)):
+            got[first + i] = np.array(words[i], copy=True)
+
+    for _ in range(2):  # the second pass reuses the slots (and, in hybrid mode, an adapted split)
+        got.clear()
+        pipe.run(text, offsets, sink=sink, on_device=lambda first, filt: seen_on_device.append((first, filt.shape[0])))
+        assert sorted(got) == list(range(len(fastas)))
+        for i, f in enumerate(fastas):
+            assert np.array_equal(got[i], oracle.makebf(f, k, num_bits)), (mode, i)
+    assert sum(n for _, n in seen_on_device) == 2 * len(fastas)
+    assert pipe.h2d_bytes == 2 * offsets[-1] and pipe.d2h_bytes > 0
+    if mode == "sparse":
+        assert pipe.d2h_bytes < 2 * len(fastas) * (num_bits // 8)
+    pipe.close()
