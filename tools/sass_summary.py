@@ -48,7 +48,8 @@ for line in sass.splitlines():
 print("SASS summary of %s (cuobjdump -sass, sm_100a)\n" % so)
 for k in sorted(counts, key=lambda x: demangle.get(x, x)):
     c = counts[k]
-    short = re.sub(r"\(.*", "", demangle.get(k, k))
+    full = demangle.get(k, k)
+    short = full[: full.rindex(">(") + 1] if ">(" in full else re.sub(r"\(.*", "", full)
     print("%s\n    %d instructions; %s" % (short, total[k], usage.get(k, "")))
     print("    " + "  ".join("%s %d" % (op, sum(v for o, v in c.items() if o == op or (op in ("UTMA",) and o.startswith(op))))
                             for op in KEYS if any(o == op or (op == "UTMA" and o.startswith(op)) for o in c)))
