@@ -43,6 +43,22 @@ def read_files(paths: Sequence[str], threads: Optional[int] = None) -> List[byte
         return list(ex.map(read_fasta_bytes, paths))
 
 
+def _retry_after_oom(method):
+    """An operator that runs out of device memory drops the backend's caches (row-major filters, bit-sliced matrices,
+    torch's cached blocks) and runs once more -- budgets come from cudaMemGetInfo at construction, other users of the
+    device may have grown since."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, *args, **kwargs):
+        try:
+            return method(self, *args, **kwargs)
+        except torch.cuda.OutOfMemoryError:
+            self.release_memory()
+            return method(self, *args, **kwargs)
+    return wrapper
+
+
 class QueryBatch:
     """Distinct hash positions of a batch of queries on the device: `positions` (int32 tensor holding uint32 bit
     patterns) carries every query's ascending positions back to back, query i owns [offsets[i], offsets[i + 1])."""
@@ -107,6 +123,15 @@ class CudaBackend:
             _, old = self._cache.popitem(last=False)
             self._bytes -= old.numel() * 8
 
+    def release_memory(self) -> None:
+        """Drop every cached filter and bit-sliced matrix and return torch's cached blocks to the driver."""
+        self._cache.clear()
+        self._bytes = 0
+        self._sliced.clear()
+        self._sliced_bytes = 0
+        self._pipes.clear()
+        torch.cuda.empty_cache()
+
     def forget(self, path: str) -> None:
         path = os.path.abspath(path)
         t = self._cache.pop(path, None)
@@ -159,6 +184,7 @@ class CudaBackend:
             self._pipes[min_abund] = pipe
         return pipe
 
+    @_retry_after_oom
     def sketch_many(self, fasta_paths: Sequence[str], out_paths: Sequence[str], min_abund: int) -> None:
         """howdesbt makebf --k --min --bits --hashes=1 --seed=0,0 <fasta> --out=<bf> for every pair.
         The files of a group are read into one pinned text buffer and go through pipeline.SketchPipeline: raw FASTA text
@@ -231,6 +257,7 @@ class CudaBackend:
         return int(self.ctx.bf_popcount([acc], num_bits)[0])
 
     # ------------------------------------------------------------------ bfoperate --or
+    @_retry_after_oom
     def union(self, src_paths: Sequence[str], out_path: str) -> None:
         out = None
         step = self._chunk()
@@ -248,6 +275,7 @@ class CudaBackend:
         self._put(out_path, t)
 
     # ------------------------------------------------------------------ dumpbf --show:density
+    @_retry_after_oom
     def popcounts(self, paths: Sequence[str]) -> List[int]:
         out: List[torch.Tensor] = []
         step = self._chunk()
@@ -257,6 +285,7 @@ class CudaBackend:
         return [int(x) for x in torch.cat(out).cpu()] if out else []
 
     # ------------------------------------------------------------------ bfdistance
+    @_retry_after_oom
     def dist_one_vs_many(self, focus_path: str, target_paths: Sequence[str]) -> List[Tuple[int, int]]:
         """[(intersection, union)] of the focus against every target, in target order."""
         if not target_paths:
@@ -271,6 +300,7 @@ class CudaBackend:
         both = torch.stack([torch.cat(inter), torch.cat(union)]).cpu()
         return list(zip(both[0].tolist(), both[1].tolist()))
 
+    @_retry_after_oom
     def dist_pairs(self, pairs: Sequence[Tuple[str, str]]) -> List[Tuple[int, int]]:
         """[(intersection, union)] of an arbitrary list of (path, path) pairs: ONE launch and one device->host copy per
         chunk of pairs (the batch form of Database.dist that profile_many ends with)."""
@@ -306,10 +336,12 @@ class CudaBackend:
                 out[j0:j1, i0:i1] = rect.t()
         return out
 
+    @_retry_after_oom
     def dist_all_pairs(self, paths: Sequence[str]) -> np.ndarray:
         """Dense intersection matrix; diagonal = popcounts (union_ij = I_ii + I_jj - I_ij)."""
         return self._all_pairs_device(paths).cpu().numpy()
 
+    @_retry_after_oom
     def dist_all_pairs_many(self, groups: Sequence[Sequence[str]]) -> List[np.ndarray]:
         """dist_all_pairs for many clusters: every all-pairs launch is queued first, the matrices come back in ONE
         device->host copy per cache-sized run of clusters (one synchronisation instead of one per cluster)."""
@@ -339,6 +371,7 @@ class CudaBackend:
         return out
 
     # ------------------------------------------------------------------ query --distinctkmers
+    @_retry_after_oom
     def query_positions_many(self, fasta_paths: Sequence[str]) -> QueryBatch:
         """Distinct hash positions of ALL k-mers of every file (no min filter), ascending, on the device.
         They are the set bits of the file's own min=1 filter (App. A6), so per chunk of files: one FASTA ingest, ONE K1
@@ -368,6 +401,7 @@ class CudaBackend:
     def query_totals(self, qb: QueryBatch) -> List[int]:
         return [qb.total(i) for i in range(len(qb))]
 
+    @_retry_after_oom
     def query_hits_many(self, qb: QueryBatch, idxs: Sequence[int], leaf_paths: Sequence[str]) -> torch.Tensor:
         """hits[i][l] of queries `idxs` of the batch against the leaves of one flat tree, LEFT ON THE DEVICE (int32
         [len(idxs), len(leaf_paths)]); nothing synchronises -- fetch_hits() brings many of them back in one copy."""

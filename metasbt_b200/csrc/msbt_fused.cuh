@@ -3,15 +3,16 @@
 //
 // One CTA per SM, 1024 threads, two roles that run concurrently on the same SM:
 //
-//   P  (24 warps)  partition: claim a chunk of FU_CHUNK_BASES k-mer starts, hash every canonical k-mer,
-//                  stage its position in shared memory by bucket (bucket = pos >> bucket_shift, <= 1024
-//                  buckets per filter), then flush each staged row with one global reservation and aligned
-//                  16-byte stores into an L2-resident scratch ring (one slot per genome in flight).
+//   P  (20 warps)  partition: claim a chunk of FU_CHUNK_BASES k-mer starts, hash every canonical k-mer,
+//                  stage its position in shared memory by bucket (bucket = pos >> bucket_shift; at most NBM
+//                  buckets per filter, NBM = 512 below 2^30 bits and 2048 from there, see FuGeom), then flush
+//                  each staged row with one global reservation and aligned 16-byte stores into an L2-resident
+//                  scratch ring (one slot per genome in flight).
 //                  This role is instruction-issue bound (64-bit MurmurHash3 on a 32-bit ALU).
-//   B  (8 warps)   build: claim a (genome, bucket) item once all chunks of that genome are flushed, pull
+//   B  (12 warps)  build: claim a (genome, bucket) item once all chunks of that genome are flushed, pull
 //                  the bucket's positions into registers, and for each <= 64 KiB tile of the bucket: zero
-//                  the tile in shared memory, atomicOr the positions into it, and write the finished tile
-//                  to HBM with one TMA bulk store (cp.async.bulk.global.shared::cta).  This role is
+//                  the tile in shared memory, OR the positions into it (red.shared.or), and write the finished
+//                  tile to HBM with one TMA bulk store (cp.async.bulk.global.shared::cta).  This role is
 //                  HBM-write bound and mostly waits; P fills the issue slots it leaves idle.
 //
 // The filter is written exactly once (zeros included): no memset, no read-modify-write in HBM.  HBM traffic
@@ -22,7 +23,9 @@
 //   done[g]      P warps that flushed a chunk of genome g (B waits for done[g] == n_chunks(g) * P warps)
 //   consumed[g]  buckets of genome g built       (P waits for consumed[g - ring] == NB before reusing a slot)
 //   dirty[g]     set when a bucket of the ring overflowed (skewed inputs): genome g is redone afterwards by
-//                the direct kernel, which ORs every bit into the already written filter.
+//                the direct kernel, which ORs every bit into the already written filter.  The reservation that
+//                did not fit pads the tail it leaves unwritten with a position of the same bucket, because B
+//                reads min(count, capacity) entries and the redo pass can only add bits.
 // Claims are handed out in genome order, so a waiting role only ever waits on strictly earlier work that
 // is already owned by a running CTA: there is no circular wait, and a CTA that starts late simply joins.
 #pragma once
