@@ -53,7 +53,7 @@ class SketchPipeline:
     """makebf for a stream of genomes whose FASTA text sits in (pinned) host memory; filters are delivered to `sink` in
     host memory, chunk by chunk.  mode: "dense" (filters cross PCIe as they are), "sparse" (position lists cross, dense
     words rebuilt on the host), "hybrid" (both at once: part of every chunk dense on the copy engine, the rest sparse on
-    the host cores, the split following their measured costs) or "auto" (hybrid when the position lists are expected to
+    the host cores, the split following their measured costs) or "auto" (sparse when the position lists are expected to
     be under half the dense bytes, else dense)."""
 
     def __init__(self, ctx: ops.Context, kmer_size: int, num_bits: int, min_abund: int = 1, chunk_genomes: int = 32,
@@ -68,7 +68,8 @@ class SketchPipeline:
         self._slots: List[_Slot] = []
         self._text_cap = 0
         self._sparse = False                     # any position-list transport (sparse or hybrid)
-        self._hybrid = mode in ("hybrid", "auto")
+        self._hybrid = mode == "hybrid"          # (auto picks plain sparse: on the boxes measured, the two transports share the
+                                                 # host's memory system and hybrid is within +-25 % of sparse, not reliably above)
         self._dense_fraction = 0.3               # hybrid: share of a chunk that travels dense; follows the measured costs
         import os
         # host threads that rebuild dense words (sparse transport): the box's cores are shared by the ranks on it
