@@ -406,7 +406,9 @@ class MultiGpuBackend:
             for r, (seg, cut) in zip(rows, pieces[s]):
                 for d in range(P):
                     part = seg[cut[d]: cut[d + 1]]
-                    recv[d][r] = (part - tree.ranges[d][0]).to(self.parts[d].ctx.device, non_blocking=True)
+                    # uint32 bit patterns in an int32 tensor: rebase in 64 bits (a range start can be 2^31 and more)
+                    rel = ((part.to(torch.int64) & 0xFFFFFFFF) - tree.ranges[d][0]).to(torch.int32)
+                    recv[d][r] = rel.to(self.parts[d].ctx.device, non_blocking=True)
 
         def probe(d: int) -> torch.Tensor:
             part = self.parts[d]
