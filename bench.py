@@ -10,8 +10,12 @@ k=31, 2^30-bit filters, --min 1.  One step = one pass over the whole per-GPU bat
 
 * value   : genome Mbp/s, inputs (2-bit packed genomes) already resident in HBM, outputs
             (one 128 MiB filter per genome) left resident in HBM; CUDA events, max over ranks.
-* e2e     : the same metric through the public API with HOST buffers: every step copies the
-            packed genomes pinned-host -> device, builds, and copies every filter device -> host.
+* e2e     : the same metric through the public API (pipeline.SketchPipeline, what `metasbt index` drives) with HOST
+            buffers, over the WHOLE workload every step: FASTA bytes pinned-host -> device, device ingest, K1, every filter
+            back in pinned host memory (dense copy or position lists expanded by host threads; the faster is `e2e`, the
+            other `e2e_alt`), with the box's measured device->host and host-write ceilings beside it.
+* check   : every rank's first filter, word for word, against the oracle's makebf (a mismatch fails the run).
+* mag_queries: BASELINE's second metric (configs[3], tools/bench_query.py) at this N.
 * roofline: algorithmic bytes (ceil(G/4) + m/8 per genome) / measured duration
             against MEASURED_PEAKS.json's HBM copy bandwidth.
 * cpu_baseline: the oracle's rolling CPU makebf (oracle/, a port -- howdesbt itself is not
@@ -52,6 +56,7 @@ def parse_args():
     ap.add_argument("--e2e-genomes", type=int, default=0, help="genomes per end-to-end step (0 = the whole workload)")
     ap.add_argument("--e2e-steps", type=int, default=2, help="timed end-to-end passes per transport")
     ap.add_argument("--e2e-chunk", type=int, default=16, help="genomes per pipeline chunk (pinned slot = chunk x filter bytes)")
+    ap.add_argument("--e2e-hybrid", action="store_true", help="also time the hybrid transport (measured: within +-25 % of sparse on these boxes)")
     ap.add_argument("--no-numa", action="store_true", help="do not bind the rank to its GPU's NUMA node")
     ap.add_argument("--no-check", action="store_true", help="skip the oracle check of the first filter")
     ap.add_argument("--no-query", action="store_true", help="skip the MAG queries/s section (configs[3])")
@@ -276,7 +281,7 @@ def run_e2e(args, ctx, rank, world, device, barrier, dist, check_filter0):
     steps = max(1, min(args.steps, args.e2e_steps))
     out = {}
     first_words = {}
-    for mode in ("dense", "sparse", "hybrid"):
+    for mode in (("dense", "sparse", "hybrid") if args.e2e_hybrid else ("dense", "sparse")):
         pipe = pipeline.SketchPipeline(ctx, k, m, min_abund=1, chunk_genomes=args.e2e_chunk, slots=2, mode=mode, variant=args.variant)
 
         def sink(first, words, mode=mode):
