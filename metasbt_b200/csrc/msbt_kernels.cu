@@ -2959,6 +2959,94 @@ query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint
     }
 }
 
+// Row-coherent variant of the sliced probe for rows of several 256-byte pieces (more than 2,048 leaves).  In the kernel above
+// the pieces (column groups) of a row are fetched by DIFFERENT CTAs (grid.y) at unrelated times; here the warps of one CTA walk the
+// SAME positions, warp w reading piece w of every row, so the 1,280 bytes of a 10,000-leaf row are requested together.  A
+// micro-benchmark of the bare access pattern (tools/microbench4.cu: random 1,280-byte rows of a 43 GB matrix read as five 256-byte
+// warp loads) gives 2.07 TB/s when the five pieces of a row are requested at the same time against 1.37 TB/s when every warp
+// reads a piece of its own random row: DRAM page locality.  Counters: as above, 7 -> 3 carry-save compression into 12 vertical
+// planes per lane word; a warp owns its column group, so the planes are unpacked straight into global atomics per sub-chunk.
+constexpr int QSR_MAX_WARPS = 8;
+__global__ void __launch_bounds__(QSR_MAX_WARPS * 32)
+query_sliced_rows_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint32_t lw, uint32_t ls, uint64_t row_begin, uint64_t row_end,
+                         const uint32_t *__restrict__ positions, const ulonglong2 *__restrict__ q_rng, uint32_t *__restrict__ hits,
+                         uint32_t n_groups) {
+    constexpr int W = 2;
+    __shared__ unsigned long long sm_range[2];
+    const uint32_t q = blockIdx.x, chunk = blockIdx.y;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t group = blockIdx.z * QSR_MAX_WARPS + warp;     // column group = 64 words = 2,048 leaves
+    if (threadIdx.x == 0) {
+        const unsigned long long b = q_rng[q].x, e = q_rng[q].y;
+        unsigned long long lo = b, hi = e;
+        while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1; if (positions[mid] < row_begin) lo = mid + 1; else hi = mid; }
+        sm_range[0] = lo;
+        hi = e;
+        while (lo < hi) { const unsigned long long mid = (lo + hi) >> 1; if (positions[mid] < row_end) lo = mid + 1; else hi = mid; }
+        sm_range[1] = lo;
+    }
+    __syncthreads();
+    const unsigned long long rb = sm_range[0], re = sm_range[1];
+    const unsigned long long sub_b = rb + (unsigned long long)chunk * QS_SUB;
+    if (sub_b >= re || group >= n_groups) return;
+    const unsigned long long sub_e = min(sub_b + (unsigned long long)QS_SUB, re);
+    const uint32_t col = (group * 32 + lane) * W;
+    const bool live = col < lw;
+    const uint32_t *__restrict__ colp = sliced + (live ? col : 0);
+    uint32_t P[W][12];
+#pragma unroll
+    for (int w = 0; w < W; w++)
+#pragma unroll
+        for (int i = 0; i < 12; i++) P[w][i] = 0;
+    uint32_t nextpos = (lane < 28 && sub_b + lane < sub_e) ? positions[sub_b + lane] : 0xFFFFFFFFu;
+    for (unsigned long long base = sub_b; base < sub_e; base += 28) {
+        const uint32_t mypos = nextpos;
+        const unsigned long long idx = base + 28 + lane;
+        nextpos = (lane < 28 && idx < sub_e) ? positions[idx] : 0xFFFFFFFFu;
+#pragma unroll
+        for (int g7 = 0; g7 < 4; g7++) {
+            QsVec<W> x[7];
+#pragma unroll
+            for (int j = 0; j < 7; j++) {
+                const uint32_t p = __shfl_sync(0xffffffffu, mypos, g7 * 7 + j);
+                if (p != 0xFFFFFFFFu && live) x[j].load(colp + ((uint64_t)p - row_begin) * ls);
+                else {
+#pragma unroll
+                    for (int w = 0; w < W; w++) x[j].v[w] = 0u;
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < W; w++) {
+                uint32_t sa, ca, sb, cb, ones, cc, twos, fours;
+                full_add(x[0].v[w], x[1].v[w], x[2].v[w], sa, ca);
+                full_add(x[3].v[w], x[4].v[w], x[5].v[w], sb, cb);
+                full_add(sa, sb, x[6].v[w], ones, cc);
+                full_add(ca, cb, cc, twos, fours);
+                uint32_t k;
+                k = P[w][0] & ones; P[w][0] ^= ones;
+                full_add(P[w][1], twos, k, P[w][1], k);
+                full_add(P[w][2], fours, k, P[w][2], k);
+#pragma unroll
+                for (int i = 3; i < 12; i++) { const uint32_t t = P[w][i] & k; P[w][i] ^= k; k = t; }
+            }
+        }
+    }
+    if (live) {
+        uint32_t *__restrict__ hq = hits + (uint64_t)q * n_leaves;
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            const uint32_t leaf0 = (col + w) * 32;
+#pragma unroll 4
+            for (int l = 0; l < 32; l++) {
+                uint32_t c = 0;
+#pragma unroll
+                for (int i = 0; i < 12; i++) c |= ((P[w][i] >> l) & 1u) << i;
+                if (c && leaf0 + l < n_leaves) atomicAdd(hq + leaf0 + l, c);
+            }
+        }
+    }
+}
+
 // Row stride of the bit-sliced matrix: ceil(n_leaves / 32) words rounded up to 8 words, so that every row starts on a
 // 32-byte sector boundary (10,000 leaves: 313 -> 320 words; an unaligned 128-byte row segment costs five sectors, not four).
 extern "C" uint32_t msbt_sliced_row_words(uint32_t n_leaves) { return (((n_leaves + 31) / 32) + 7u) & ~7u; }
@@ -3032,6 +3120,19 @@ extern "C" int msbt_query_batch_sliced_ranges(msbt_ctx *ctx, const uint32_t *d_s
     // same row range (positions are uniform hashes).  With the QUERY as the fastest grid dimension the CTAs that run
     // together probe the same rows, so a row that several queries hit (256 MAGs against 2^25-row filters: 15 per row)
     // comes from L2 instead of DRAM.  MSBT_QS_ORDER=0 restores chunk-fastest order (one query after the other).
+    // rows of several 256-byte pieces: the row-coherent kernel (MSBT_QS_ROWS=0 keeps the column-group kernel)
+    bool rows_kernel = W == 2 && gy >= 2;
+    if (const char *e = getenv("MSBT_QS_ROWS")) rows_kernel = rows_kernel && atoi(e) != 0;
+    if (rows_kernel) {
+        const uint64_t chunks = (max_pos + QS_SUB - 1) / QS_SUB;
+        if (chunks <= 65535) {
+            const uint32_t warps = std::min<uint32_t>(gy, QSR_MAX_WARPS);
+            const dim3 grid_r(n_queries, (unsigned)chunks, (gy + QSR_MAX_WARPS - 1) / QSR_MAX_WARPS);
+            query_sliced_rows_kernel<<<grid_r, warps * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_rng, d_hits, gy);
+            LAUNCH_CHECK(ctx);
+            return MSBT_OK;
+        }
+    }
     bool qfast = n_queries > 1 && gx <= 65535;
     if (const char *e = getenv("MSBT_QS_ORDER")) qfast = qfast && atoi(e) != 0;
     const dim3 grid = qfast ? dim3(n_queries, gy, gx) : dim3(gx, gy, n_queries);

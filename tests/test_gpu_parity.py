@@ -734,3 +734,30 @@ def test_sketch_pipeline_every_transport(ctx, oracle, mode):
     if mode == "sparse":
         assert pipe.d2h_bytes < 2 * len(fastas) * (num_bits // 8)
     pipe.close()
+
+
+@pytest.mark.parametrize("n_leaves", [2049, 5000, 17000])
+@pytest.mark.parametrize("rows_kernel", ["1", "0"])
+def test_query_sliced_rows_of_several_pieces(ctx, oracle, n_leaves, rows_kernel, monkeypatch):
+    """More than 2,048 leaves: a row is several 256-byte pieces and the row-coherent probe (the warps of a CTA read the pieces
+    of the same rows together) serves the query; MSBT_QS_ROWS=0 keeps the column-group kernel.  Same hits either way, equal
+    to the oracle's; 17,000 leaves need more than the eight warps of one CTA."""
+    from metasbt_b200 import ops
+    monkeypatch.setenv("MSBT_QS_ROWS", rows_kernel)
+    num_bits = 1 << 14
+    rng = np.random.default_rng(n_leaves)
+    w = ops.filter_words(num_bits)
+    host = rng.integers(0, 1 << 63, size=(n_leaves, w), dtype=np.int64) & rng.integers(0, 1 << 63, size=(n_leaves, w), dtype=np.int64)
+    dev = torch.from_numpy(host).to(ctx.device)
+    leaves = [dev[i] for i in range(n_leaves)]
+    leaf_np = [host[i].view(np.uint64) for i in range(n_leaves)]
+    queries = [np.sort(rng.choice(num_bits, size=n, replace=False)).astype(np.uint64) for n in (9000, 4089, 0, 29, 4088)]
+    positions = [torch.from_numpy(q.astype(np.uint32).view(np.int32)).to(ctx.device) for q in queries]
+    want = np.stack([oracle.query_hits(q, leaf_np) for q in queries])
+    sliced = ctx.bitslice(leaves, 0, num_bits)
+    got = ctx.query_batch_sliced(sliced, n_leaves, 0, num_bits, positions).cpu().numpy()
+    assert np.array_equal(got.astype(np.uint64), want)
+    half = num_bits // 2
+    part = ctx.query_batch_sliced(ctx.bitslice(leaves, 0, half), n_leaves, 0, half, positions) + \
+        ctx.query_batch_sliced(ctx.bitslice(leaves, half, num_bits), n_leaves, half, num_bits, positions)
+    assert np.array_equal(part.cpu().numpy().astype(np.uint64), want)
