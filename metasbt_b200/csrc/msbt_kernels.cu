@@ -2964,13 +2964,13 @@ query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint
 // SAME positions, warp w reading piece w of every row, so the 1,280 bytes of a 10,000-leaf row are requested together.  A
 // micro-benchmark of the bare access pattern (tools/microbench4.cu: random 1,280-byte rows of a 43 GB matrix read as five 256-byte
 // warp loads) gives 2.07 TB/s when the five pieces of a row are requested at the same time against 1.37 TB/s when every warp
-// reads a piece of its own random row: DRAM page locality.  Counters: as above, 7 -> 3 carry-save compression into 12 vertical
-// planes per lane word; a warp owns its column group, so the planes are unpacked straight into global atomics per sub-chunk.
+// reads a piece of its own random row: DRAM page locality.  Counters: 12 vertical planes per lane word fed by a carry-save chain
+// (see the loop); a warp owns its column group, so the planes are unpacked straight into global atomics per sub-chunk.
 constexpr int QSR_MAX_WARPS = 8;
 __global__ void __launch_bounds__(QSR_MAX_WARPS * 32)
 query_sliced_rows_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint32_t lw, uint32_t ls, uint64_t row_begin, uint64_t row_end,
                          const uint32_t *__restrict__ positions, const ulonglong2 *__restrict__ q_rng, uint32_t *__restrict__ hits,
-                         uint32_t n_groups) {
+                         uint32_t n_groups, uint32_t sub) {
     constexpr int W = 2;
     __shared__ unsigned long long sm_range[2];
     const uint32_t q = blockIdx.x, chunk = blockIdx.y;
@@ -2987,9 +2987,9 @@ query_sliced_rows_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves,
     }
     __syncthreads();
     const unsigned long long rb = sm_range[0], re = sm_range[1];
-    const unsigned long long sub_b = rb + (unsigned long long)chunk * QS_SUB;
+    const unsigned long long sub_b = rb + (unsigned long long)chunk * sub;   // sub <= QS_SUB positions: 12 counter planes
     if (sub_b >= re || group >= n_groups) return;
-    const unsigned long long sub_e = min(sub_b + (unsigned long long)QS_SUB, re);
+    const unsigned long long sub_e = min(sub_b + (unsigned long long)sub, re);
     const uint32_t col = (group * 32 + lane) * W;
     const bool live = col < lw;
     const uint32_t *__restrict__ colp = sliced + (live ? col : 0);
@@ -2998,17 +2998,22 @@ query_sliced_rows_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves,
     for (int w = 0; w < W; w++)
 #pragma unroll
         for (int i = 0; i < 12; i++) P[w][i] = 0;
-    uint32_t nextpos = (lane < 28 && sub_b + lane < sub_e) ? positions[sub_b + lane] : 0xFFFFFFFFu;
-    for (unsigned long long base = sub_b; base < sub_e; base += 28) {
+    // 32 positions per round (one per lane), four groups of 8 rows.  Counting is a carry-save chain whose accumulators ARE
+    // the low counter planes: 8 rows fold into planes 0-2 with 7 full adders and leave one carry of weight 8; two such
+    // carries meet in one more full adder on plane 3, and only its carry (weight 16) ripples through planes 4-11 -- 2.9 ALU
+    // operations per row and lane word instead of 4.6 for the 7 -> 3 compression + 12-plane ripple of the kernel above.
+    uint32_t nextpos = (sub_b + lane < sub_e) ? positions[sub_b + lane] : 0xFFFFFFFFu;
+    for (unsigned long long base = sub_b; base < sub_e; base += 32) {
         const uint32_t mypos = nextpos;
-        const unsigned long long idx = base + 28 + lane;
-        nextpos = (lane < 28 && idx < sub_e) ? positions[idx] : 0xFFFFFFFFu;
+        const unsigned long long idx = base + 32 + lane;
+        nextpos = (idx < sub_e) ? positions[idx] : 0xFFFFFFFFu;
+        uint32_t pend[W];
 #pragma unroll
-        for (int g7 = 0; g7 < 4; g7++) {
-            QsVec<W> x[7];
+        for (int g8 = 0; g8 < 4; g8++) {
+            QsVec<W> x[8];
 #pragma unroll
-            for (int j = 0; j < 7; j++) {
-                const uint32_t p = __shfl_sync(0xffffffffu, mypos, g7 * 7 + j);
+            for (int j = 0; j < 8; j++) {
+                const uint32_t p = __shfl_sync(0xffffffffu, mypos, g8 * 8 + j);
                 if (p != 0xFFFFFFFFu && live) x[j].load(colp + ((uint64_t)p - row_begin) * ls);
                 else {
 #pragma unroll
@@ -3017,17 +3022,22 @@ query_sliced_rows_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves,
             }
 #pragma unroll
             for (int w = 0; w < W; w++) {
-                uint32_t sa, ca, sb, cb, ones, cc, twos, fours;
-                full_add(x[0].v[w], x[1].v[w], x[2].v[w], sa, ca);
-                full_add(x[3].v[w], x[4].v[w], x[5].v[w], sb, cb);
-                full_add(sa, sb, x[6].v[w], ones, cc);
-                full_add(ca, cb, cc, twos, fours);
-                uint32_t k;
-                k = P[w][0] & ones; P[w][0] ^= ones;
-                full_add(P[w][1], twos, k, P[w][1], k);
-                full_add(P[w][2], fours, k, P[w][2], k);
+                uint32_t a, b, c, d, e, f, g;
+                full_add(P[w][0], x[0].v[w], x[1].v[w], P[w][0], a);
+                full_add(P[w][0], x[2].v[w], x[3].v[w], P[w][0], b);
+                full_add(P[w][1], a, b, P[w][1], c);
+                full_add(P[w][0], x[4].v[w], x[5].v[w], P[w][0], d);
+                full_add(P[w][0], x[6].v[w], x[7].v[w], P[w][0], e);
+                full_add(P[w][1], d, e, P[w][1], f);
+                full_add(P[w][2], c, f, P[w][2], g);      // g: carry of weight 8
+                if ((g8 & 1) == 0) {
+                    pend[w] = g;
+                } else {
+                    uint32_t k;
+                    full_add(P[w][3], pend[w], g, P[w][3], k);   // k: carry of weight 16
 #pragma unroll
-                for (int i = 3; i < 12; i++) { const uint32_t t = P[w][i] & k; P[w][i] ^= k; k = t; }
+                    for (int i = 4; i < 12; i++) { const uint32_t t = P[w][i] & k; P[w][i] ^= k; k = t; }
+                }
             }
         }
     }
@@ -3124,11 +3134,13 @@ extern "C" int msbt_query_batch_sliced_ranges(msbt_ctx *ctx, const uint32_t *d_s
     bool rows_kernel = W == 2 && gy >= 2;
     if (const char *e = getenv("MSBT_QS_ROWS")) rows_kernel = rows_kernel && atoi(e) != 0;
     if (rows_kernel) {
-        const uint64_t chunks = (max_pos + QS_SUB - 1) / QS_SUB;
+        uint32_t sub = 4064;  // positions per warp sub-chunk: a multiple of 32, at most 4,095 (12 counter planes)
+        if (const char *e = getenv("MSBT_QSR_SUB")) { const int v = atoi(e); if (v >= 32 && v <= 4064) sub = (uint32_t)v / 32 * 32; }  // tuning aid
+        const uint64_t chunks = (max_pos + sub - 1) / sub;
         if (chunks <= 65535) {
             const uint32_t warps = std::min<uint32_t>(gy, QSR_MAX_WARPS);
             const dim3 grid_r(n_queries, (unsigned)chunks, (gy + QSR_MAX_WARPS - 1) / QSR_MAX_WARPS);
-            query_sliced_rows_kernel<<<grid_r, warps * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_rng, d_hits, gy);
+            query_sliced_rows_kernel<<<grid_r, warps * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_rng, d_hits, gy, sub);
             LAUNCH_CHECK(ctx);
             return MSBT_OK;
         }
