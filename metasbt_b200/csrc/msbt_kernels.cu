@@ -2966,8 +2966,10 @@ query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint
 // warp loads) gives 2.07 TB/s when the five pieces of a row are requested at the same time against 1.37 TB/s when every warp
 // reads a piece of its own random row: DRAM page locality.  Counters: 12 vertical planes per lane word fed by a carry-save chain
 // (see the loop); a warp owns its column group, so the planes are unpacked straight into global atomics per sub-chunk.
-template <int MAXW, int MINB>   // warps per CTA (pieces of a row it covers) and resident CTAs per SM the register budget aims at
-__global__ void __launch_bounds__(MAXW * 32, MINB)
+constexpr int QSR_MAX_WARPS = 8;  // pieces of a row one CTA covers (10,000 leaves: 5); more leaves take grid.z
+// (register-capped instantiations for 7 / 8 resident CTAs per SM were measured: 56 registers 82.4 ms, 48 registers with
+// spills 92.0 ms, against 79.4 ms for the plain 63-register build with 6 CTAs per SM)
+__global__ void __launch_bounds__(QSR_MAX_WARPS * 32)
 query_sliced_rows_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint32_t lw, uint32_t ls, uint64_t row_begin, uint64_t row_end,
                          const uint32_t *__restrict__ positions, const ulonglong2 *__restrict__ q_rng, uint32_t *__restrict__ hits,
                          uint32_t n_groups, uint32_t sub) {
@@ -2975,7 +2977,7 @@ query_sliced_rows_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves,
     __shared__ unsigned long long sm_range[2];
     const uint32_t q = blockIdx.x, chunk = blockIdx.y;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t group = blockIdx.z * MAXW + warp;              // column group = 64 words = 2,048 leaves
+    const uint32_t group = blockIdx.z * QSR_MAX_WARPS + warp;     // column group = 64 words = 2,048 leaves
     if (threadIdx.x == 0) {
         const unsigned long long b = q_rng[q].x, e = q_rng[q].y;
         unsigned long long lo = b, hi = e;
@@ -3138,17 +3140,9 @@ extern "C" int msbt_query_batch_sliced_ranges(msbt_ctx *ctx, const uint32_t *d_s
         if (const char *e = getenv("MSBT_QSR_SUB")) { const int v = atoi(e); if (v >= 32 && v <= 4064) sub = (uint32_t)v / 32 * 32; }  // tuning aid
         const uint64_t chunks = (max_pos + sub - 1) / sub;
         if (chunks <= 65535) {
-            int minb = 6;
-            if (const char *e = getenv("MSBT_QSR_MINB")) minb = atoi(e);  // tuning aid
-#define MSBT_QSR_LAUNCH(MW, MB)                                                                                                        \
-    query_sliced_rows_kernel<MW, MB><<<dim3(n_queries, (unsigned)chunks, (gy + MW - 1) / MW), std::min<uint32_t>(gy, MW) * 32, 0, stream>>>( \
-        d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_rng, d_hits, gy, sub)
-            if (gy <= 5) {
-                if (minb >= 8) MSBT_QSR_LAUNCH(5, 8);
-                else if (minb == 7) MSBT_QSR_LAUNCH(5, 7);
-                else MSBT_QSR_LAUNCH(5, 6);
-            } else MSBT_QSR_LAUNCH(8, 4);
-#undef MSBT_QSR_LAUNCH
+            const uint32_t warps = std::min<uint32_t>(gy, QSR_MAX_WARPS);
+            const dim3 grid_r(n_queries, (unsigned)chunks, (gy + QSR_MAX_WARPS - 1) / QSR_MAX_WARPS);
+            query_sliced_rows_kernel<<<grid_r, warps * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_rng, d_hits, gy, sub);
             LAUNCH_CHECK(ctx);
             return MSBT_OK;
         }
