@@ -63,7 +63,7 @@ def parse_args():
     ap.add_argument("--query-leaves", type=int, default=10000)
     ap.add_argument("--query-bits", type=int, default=1 << 25, help="filter size of the query section at every N (fits one GPU)")
     ap.add_argument("--query-bits-full", type=int, default=1 << 28, help="configs[3]'s own filter size, run in addition at N >= 8")
-    ap.add_argument("--query-mags", type=int, default=256)
+    ap.add_argument("--query-mags", type=int, default=1024, help="MAGs per query step (SURVEY.md 8d, config 4: batches of 1,024)")
     ap.add_argument("--cpu-genomes", type=int, default=0, help="genomes in the CPU-baseline sample (0 = 2 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -3,7 +3,7 @@
 (2 Mbp) against a many-leaf flat SBT whose bit-sliced leaf matrix is sharded by contiguous bit range over the GPUs of one
 box.  bench.py runs it at every N (key "mag_queries" of its JSON line); alone:
 
-    python tools/bench_query.py [--leaves 10000 --filter-bits 33554432 --mags 256 --steps 3 --warmup 1]
+    python tools/bench_query.py [--leaves 10000 --filter-bits 33554432 --mags 1024 --steps 3 --warmup 1]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29513 tools/bench_query.py ...
 
 Setup (untimed), every rank: builds all leaves (K1; related genomes, 10 per species) and keeps only ITS rows of the
@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(ctx, rank: int, world: int, leaves: int = 10000, filter_bits: int = 1 << 25, mags: int = 256,
+def run(ctx, rank: int, world: int, leaves: int = 10000, filter_bits: int = 1 << 25, mags: int = 1024,
         genome_bp: int = 5_000_000, mag_bp: int = 2_000_000, steps: int = 3, warmup: int = 1, replicated_hash: bool = False,
         peak_gbs: float = 6537.6, pipelined: bool = True):
     """-> the result dict on rank 0, None elsewhere.  torch.distributed must be initialised when world > 1."""
@@ -177,7 +177,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--leaves", type=int, default=10000)
     ap.add_argument("--filter-bits", type=int, default=1 << 25)
-    ap.add_argument("--mags", type=int, default=256)
+    ap.add_argument("--mags", type=int, default=1024)
     ap.add_argument("--genome-bp", type=int, default=5_000_000)
     ap.add_argument("--mag-bp", type=int, default=2_000_000)
     ap.add_argument("--steps", type=int, default=3)
