@@ -2833,7 +2833,7 @@ bitslice_kernel(const uint64_t *const *__restrict__ leaves, uint32_t n_leaves, u
 // per sub-chunk into shared-memory leaf counters, and once per CTA into hits[] with global atomics.
 // HBM traffic = one row segment per (position, leaf group): the algorithmic nP * ceil(L/8) bytes of SURVEY 8d.
 constexpr int QS_WARPS = 8;
-constexpr uint32_t QS_SUB = 4088;  // positions per warp sub-chunk: 7 * 584 <= 4095 (12 planes)
+constexpr uint32_t QS_SUB = 4064;  // positions per warp sub-chunk: a multiple of 32, at most 4,095 (12 counter planes)
 
 __device__ __forceinline__ void full_add(uint32_t a, uint32_t b, uint32_t c, uint32_t &sum, uint32_t &carry) {
     uint32_t s_, c_;  // the outputs may alias the inputs
@@ -2898,22 +2898,26 @@ query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint
         for (int w = 0; w < W; w++)
 #pragma unroll
             for (int i = 0; i < 12; i++) P[w][i] = 0;
-        uint32_t nextpos = (lane < 28 && sub_b + lane < sub_e) ? positions[sub_b + lane] : 0xFFFFFFFFu;
-        for (unsigned long long base = sub_b; base < sub_e; base += 28) {
-            // 28 positions per round: one coalesced load of positions (issued one round ahead, so that its latency is not
-            // in front of every round's row reads), then 4 groups of 7 independent row reads
+        // 32 positions per round (one per lane; loaded one round ahead, so that their latency is not in front of every
+        // round's row reads), four groups of 8 independent row reads, G groups in flight.  Counting is a carry-save chain
+        // whose accumulators ARE the low counter planes: 8 rows fold into planes 0-2 with 7 full adders and leave one
+        // carry of weight 8; two such carries meet in one more full adder on plane 3, and only its carry (weight 16)
+        // ripples through planes 4-11: 2.9 ALU operations per row and lane word (the first version compressed 7 rows to 3
+        // planes and rippled all 12 planes: 4.6).
+        uint32_t nextpos = (sub_b + lane < sub_e) ? positions[sub_b + lane] : 0xFFFFFFFFu;
+        for (unsigned long long base = sub_b; base < sub_e; base += 32) {
             const uint32_t mypos = nextpos;
-            const unsigned long long idx = base + 28 + lane;
-            nextpos = (lane < 28 && idx < sub_e) ? positions[idx] : 0xFFFFFFFFu;
-            // (issuing all 28 row reads before the first use was measured: 76 registers, lower occupancy, 1.5x slower)
+            const unsigned long long idx = base + 32 + lane;
+            nextpos = (idx < sub_e) ? positions[idx] : 0xFFFFFFFFu;
+            uint32_t pend[W];
 #pragma unroll
-            for (int g7 = 0; g7 < 4; g7 += G) {
-                QsVec<W> x[G][7];  // G groups of 7 rows in flight per lane
+            for (int g8 = 0; g8 < 4; g8 += G) {
+                QsVec<W> x[G][8];
 #pragma unroll
                 for (int g = 0; g < G; g++)
 #pragma unroll
-                    for (int j = 0; j < 7; j++) {
-                        const uint32_t p = __shfl_sync(0xffffffffu, mypos, (g7 + g) * 7 + j);
+                    for (int j = 0; j < 8; j++) {
+                        const uint32_t p = __shfl_sync(0xffffffffu, mypos, (g8 + g) * 8 + j);
                         if (p != 0xFFFFFFFFu && live) x[g][j].load(colp + ((uint64_t)p - row_begin) * ls);
                         else {
 #pragma unroll
@@ -2924,17 +2928,22 @@ query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint
                 for (int g = 0; g < G; g++)
 #pragma unroll
                     for (int w = 0; w < W; w++) {
-                        uint32_t sa, ca, sb, cb, ones, cc, twos, fours;
-                        full_add(x[g][0].v[w], x[g][1].v[w], x[g][2].v[w], sa, ca);
-                        full_add(x[g][3].v[w], x[g][4].v[w], x[g][5].v[w], sb, cb);
-                        full_add(sa, sb, x[g][6].v[w], ones, cc);
-                        full_add(ca, cb, cc, twos, fours);
-                        uint32_t k;
-                        k = P[w][0] & ones; P[w][0] ^= ones;
-                        full_add(P[w][1], twos, k, P[w][1], k);
-                        full_add(P[w][2], fours, k, P[w][2], k);
+                        uint32_t a, b, c, d, e, f, c8;
+                        full_add(P[w][0], x[g][0].v[w], x[g][1].v[w], P[w][0], a);
+                        full_add(P[w][0], x[g][2].v[w], x[g][3].v[w], P[w][0], b);
+                        full_add(P[w][1], a, b, P[w][1], c);
+                        full_add(P[w][0], x[g][4].v[w], x[g][5].v[w], P[w][0], d);
+                        full_add(P[w][0], x[g][6].v[w], x[g][7].v[w], P[w][0], e);
+                        full_add(P[w][1], d, e, P[w][1], f);
+                        full_add(P[w][2], c, f, P[w][2], c8);  // carry of weight 8
+                        if (((g8 + g) & 1) == 0) {
+                            pend[w] = c8;
+                        } else {
+                            uint32_t k;
+                            full_add(P[w][3], pend[w], c8, P[w][3], k);  // carry of weight 16
 #pragma unroll
-                        for (int i = 3; i < 12; i++) { const uint32_t t = P[w][i] & k; P[w][i] ^= k; k = t; }
+                            for (int i = 4; i < 12; i++) { const uint32_t t = P[w][i] & k; P[w][i] ^= k; k = t; }
+                        }
                     }
             }
         }
@@ -2969,6 +2978,7 @@ query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint
 constexpr int QSR_MAX_WARPS = 8;  // pieces of a row one CTA covers (10,000 leaves: 5); more leaves take grid.z
 // (register-capped instantiations for 7 / 8 resident CTAs per SM were measured: 56 registers 82.4 ms, 48 registers with
 // spills 92.0 ms, against 79.4 ms for the plain 63-register build with 6 CTAs per SM)
+template <int G>   // groups of 8 row loads in flight per lane (1 or 2)
 __global__ void __launch_bounds__(QSR_MAX_WARPS * 32)
 query_sliced_rows_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint32_t lw, uint32_t ls, uint64_t row_begin, uint64_t row_end,
                          const uint32_t *__restrict__ positions, const ulonglong2 *__restrict__ q_rng, uint32_t *__restrict__ hits,
@@ -3011,36 +3021,40 @@ query_sliced_rows_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves,
         nextpos = (idx < sub_e) ? positions[idx] : 0xFFFFFFFFu;
         uint32_t pend[W];
 #pragma unroll
-        for (int g8 = 0; g8 < 4; g8++) {
-            QsVec<W> x[8];
+        for (int g8 = 0; g8 < 4; g8 += G) {
+            QsVec<W> x[G][8];
 #pragma unroll
-            for (int j = 0; j < 8; j++) {
-                const uint32_t p = __shfl_sync(0xffffffffu, mypos, g8 * 8 + j);
-                if (p != 0xFFFFFFFFu && live) x[j].load(colp + ((uint64_t)p - row_begin) * ls);
-                else {
+            for (int g = 0; g < G; g++)
 #pragma unroll
-                    for (int w = 0; w < W; w++) x[j].v[w] = 0u;
+                for (int j = 0; j < 8; j++) {
+                    const uint32_t p = __shfl_sync(0xffffffffu, mypos, (g8 + g) * 8 + j);
+                    if (p != 0xFFFFFFFFu && live) x[g][j].load(colp + ((uint64_t)p - row_begin) * ls);
+                    else {
+#pragma unroll
+                        for (int w = 0; w < W; w++) x[g][j].v[w] = 0u;
+                    }
                 }
-            }
 #pragma unroll
-            for (int w = 0; w < W; w++) {
-                uint32_t a, b, c, d, e, f, g;
-                full_add(P[w][0], x[0].v[w], x[1].v[w], P[w][0], a);
-                full_add(P[w][0], x[2].v[w], x[3].v[w], P[w][0], b);
-                full_add(P[w][1], a, b, P[w][1], c);
-                full_add(P[w][0], x[4].v[w], x[5].v[w], P[w][0], d);
-                full_add(P[w][0], x[6].v[w], x[7].v[w], P[w][0], e);
-                full_add(P[w][1], d, e, P[w][1], f);
-                full_add(P[w][2], c, f, P[w][2], g);      // g: carry of weight 8
-                if ((g8 & 1) == 0) {
-                    pend[w] = g;
-                } else {
-                    uint32_t k;
-                    full_add(P[w][3], pend[w], g, P[w][3], k);   // k: carry of weight 16
+            for (int g = 0; g < G; g++)
 #pragma unroll
-                    for (int i = 4; i < 12; i++) { const uint32_t t = P[w][i] & k; P[w][i] ^= k; k = t; }
+                for (int w = 0; w < W; w++) {
+                    uint32_t a, b, c, d, e, f, c8;
+                    full_add(P[w][0], x[g][0].v[w], x[g][1].v[w], P[w][0], a);
+                    full_add(P[w][0], x[g][2].v[w], x[g][3].v[w], P[w][0], b);
+                    full_add(P[w][1], a, b, P[w][1], c);
+                    full_add(P[w][0], x[g][4].v[w], x[g][5].v[w], P[w][0], d);
+                    full_add(P[w][0], x[g][6].v[w], x[g][7].v[w], P[w][0], e);
+                    full_add(P[w][1], d, e, P[w][1], f);
+                    full_add(P[w][2], c, f, P[w][2], c8);      // carry of weight 8
+                    if (((g8 + g) & 1) == 0) {
+                        pend[w] = c8;
+                    } else {
+                        uint32_t k;
+                        full_add(P[w][3], pend[w], c8, P[w][3], k);   // k: carry of weight 16
+#pragma unroll
+                        for (int i = 4; i < 12; i++) { const uint32_t t = P[w][i] & k; P[w][i] ^= k; k = t; }
+                    }
                 }
-            }
         }
     }
     if (live) {
@@ -3136,13 +3150,18 @@ extern "C" int msbt_query_batch_sliced_ranges(msbt_ctx *ctx, const uint32_t *d_s
     bool rows_kernel = W == 2 && gy >= 2;
     if (const char *e = getenv("MSBT_QS_ROWS")) rows_kernel = rows_kernel && atoi(e) != 0;
     if (rows_kernel) {
-        uint32_t sub = 4064;  // positions per warp sub-chunk: a multiple of 32, at most 4,095 (12 counter planes)
+        uint32_t sub = QS_SUB;
         if (const char *e = getenv("MSBT_QSR_SUB")) { const int v = atoi(e); if (v >= 32 && v <= 4064) sub = (uint32_t)v / 32 * 32; }  // tuning aid
         const uint64_t chunks = (max_pos + sub - 1) / sub;
         if (chunks <= 65535) {
             const uint32_t warps = std::min<uint32_t>(gy, QSR_MAX_WARPS);
             const dim3 grid_r(n_queries, (unsigned)chunks, (gy + QSR_MAX_WARPS - 1) / QSR_MAX_WARPS);
-            query_sliced_rows_kernel<<<grid_r, warps * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_rng, d_hits, gy, sub);
+            int g_rows = 1;
+            if (const char *e = getenv("MSBT_QSR_G")) g_rows = atoi(e);  // tuning aid
+            if (g_rows == 2)
+                query_sliced_rows_kernel<2><<<grid_r, warps * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_rng, d_hits, gy, sub);
+            else
+                query_sliced_rows_kernel<1><<<grid_r, warps * 32, 0, stream>>>(d_sliced, n_leaves, lw, ls, row_begin, row_end, d_positions, d_rng, d_hits, gy, sub);
             LAUNCH_CHECK(ctx);
             return MSBT_OK;
         }
