@@ -463,9 +463,13 @@ def run_ours(args):
     # ---- end to end through the public API with host buffers
     e2e = e2e_alt = None
     if not args.no_e2e:
-        e2e, e2e_alt = run_e2e(args, ctx, rank, world, device, barrier, dist, check_filter0)
-        if numa_info:
-            e2e["numa"] = numa_info
+        try:
+            e2e, e2e_alt = run_e2e(args, ctx, rank, world, device, barrier, dist, check_filter0)
+            if numa_info:
+                e2e["numa"] = numa_info
+        except Exception as exc:  # (a result MISMATCH raises SystemExit and fails the run; anything else must not cost the headline)
+            e2e = {"error": repr(exc)}
+            torch.cuda.empty_cache()
 
     peak, peak_src = measured_peak_gbs()
     # ---- BASELINE's second metric, MAG queries/s, at this N (configs[3])
@@ -474,13 +478,16 @@ def run_ours(args):
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import bench_query
         with contextlib.redirect_stdout(sys.stderr):
-            mag_queries = bench_query.run(ctx, rank, world, leaves=args.query_leaves, filter_bits=args.query_bits, mags=args.query_mags,
-                                          steps=max(2, min(args.steps, 5)), warmup=1, peak_gbs=peak)
-            if world >= 8 and args.query_bits_full and args.query_bits_full != args.query_bits:
-                full = bench_query.run(ctx, rank, world, leaves=args.query_leaves, filter_bits=args.query_bits_full, mags=args.query_mags,
-                                       steps=2, warmup=1, peak_gbs=peak)
-                if rank == 0:
-                    mag_queries["at_config_filter_size"] = full
+            try:
+                mag_queries = bench_query.run(ctx, rank, world, leaves=args.query_leaves, filter_bits=args.query_bits, mags=args.query_mags,
+                                              steps=max(2, min(args.steps, 5)), warmup=1, peak_gbs=peak)
+                if world >= 8 and args.query_bits_full and args.query_bits_full != args.query_bits:
+                    full = bench_query.run(ctx, rank, world, leaves=args.query_leaves, filter_bits=args.query_bits_full, mags=args.query_mags,
+                                           steps=2, warmup=1, peak_gbs=peak)
+                    if rank == 0:
+                        mag_queries["at_config_filter_size"] = full
+            except Exception as exc:  # the headline line must survive a failure here
+                mag_queries = {"error": repr(exc)}
         torch.cuda.empty_cache()
 
     if rank != 0:
