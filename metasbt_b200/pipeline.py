@@ -110,59 +110,68 @@ class SketchPipeline:
         if len(offsets) < 2:
             return
         chunks = self._prepare(offsets)
-        ctx, main = self.ctx, torch.cuda.current_stream(self.ctx.device)
+        main = torch.cuda.current_stream(self.ctx.device)
         jobs = []
         for c, members in enumerate(chunks):
             slot = self._slots[c % self.n_slots]
             slot.free.wait()
             if slot.error is not None:
-                raise slot.error
+                err, slot.error = slot.error, None
+                raise err
             slot.free.clear()
-            b, e = offsets[members[0]], offsets[members[-1] + 1]
-            sizes = [offsets[g + 1] - offsets[g] for g in members]
-            nc = len(members)
-            with torch.cuda.stream(self.stream_in):
-                slot.d_text[: e - b].copy_(text[b:e], non_blocking=True)
-                arrived = torch.cuda.Event()
-                arrived.record(self.stream_in)
-            self.h2d_bytes += e - b
-            main.wait_event(arrived)
-            main.wait_event(slot.copied)  # the slot's previous output copy has read d_filters
-            batch = ctx.pack_device_text(slot.d_text, sizes, self.k)
-            ctx.build_filters(batch, self.k, self.num_bits, min_abund=self.min_abund, out=slot.d_filters, variant=self.variant)
-            if on_device is not None:
-                on_device(members[0], slot.d_filters[:nc])
-            # Output: the first n_dense filters of the chunk cross PCIe as they are (copy engine, no host work), the rest as
-            # position lists that host threads expand -- the two transports run side by side (hybrid), the split follows
-            # their measured per-genome costs.
-            n_dense = nc if not self._sparse else (min(nc, int(round(nc * self._dense_fraction))) if self._hybrid else 0)
-            offs = None
-            if n_dense < nc:
-                sparse_rows = [slot.d_filters[i] for i in range(n_dense, nc)]
-                cap = max(sum(sizes[n_dense:]), 1)
-                pos, offs = ctx.extract_positions_packed(sparse_rows, self.num_bits, cap=cap)
-            built = torch.cuda.Event()
-            built.record(main)
-            t_dense = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if 0 < n_dense < nc else None
-            with torch.cuda.stream(self.stream_out):
-                self.stream_out.wait_event(built)
-                if offs is not None:
-                    slot.h_positions[: offs[-1]].copy_(pos[: offs[-1]], non_blocking=True)
-                    slot.positions_copied.record(self.stream_out)
-                    self.d2h_bytes += offs[-1] * 4
-                if n_dense:
-                    if t_dense:
-                        t_dense[0].record(self.stream_out)
-                    slot.h_filters[:n_dense].copy_(slot.d_filters[:n_dense, : self.words], non_blocking=True)
-                    if t_dense:
-                        t_dense[1].record(self.stream_out)
-                    self.d2h_bytes += n_dense * self.words * 8
-                slot.copied.record(self.stream_out)
-            if offs is not None:
-                pos.record_stream(self.stream_out)
-            jobs.append(self._sinks.submit(self._consume, slot, members[0], nc, n_dense, offs, sink, t_dense))
+            try:
+                jobs.append(self._submit_chunk(slot, members, text, offsets, sink, on_device, main))
+            except BaseException:
+                slot.free.set()  # a failed launch must not leave the slot taken: the pipeline stays usable
+                raise
         for j in jobs:
             j.result()
+
+    def _submit_chunk(self, slot: "_Slot", members: range, text: torch.Tensor, offsets: List[int], sink, on_device, main):
+        ctx = self.ctx
+        b, e = offsets[members[0]], offsets[members[-1] + 1]
+        sizes = [offsets[g + 1] - offsets[g] for g in members]
+        nc = len(members)
+        with torch.cuda.stream(self.stream_in):
+            slot.d_text[: e - b].copy_(text[b:e], non_blocking=True)
+            arrived = torch.cuda.Event()
+            arrived.record(self.stream_in)
+        self.h2d_bytes += e - b
+        main.wait_event(arrived)
+        main.wait_event(slot.copied)  # the slot's previous output copy has read d_filters
+        batch = ctx.pack_device_text(slot.d_text, sizes, self.k)
+        ctx.build_filters(batch, self.k, self.num_bits, min_abund=self.min_abund, out=slot.d_filters, variant=self.variant)
+        if on_device is not None:
+            on_device(members[0], slot.d_filters[:nc])
+        # Output: the first n_dense filters of the chunk cross PCIe as they are (copy engine, no host work), the rest as
+        # position lists that host threads expand -- the two transports run side by side (hybrid), the split follows
+        # their measured per-genome costs.
+        n_dense = nc if not self._sparse else (min(nc, int(round(nc * self._dense_fraction))) if self._hybrid else 0)
+        offs = None
+        if n_dense < nc:
+            sparse_rows = [slot.d_filters[i] for i in range(n_dense, nc)]
+            cap = max(sum(sizes[n_dense:]), 1)
+            pos, offs = ctx.extract_positions_packed(sparse_rows, self.num_bits, cap=cap)
+        built = torch.cuda.Event()
+        built.record(main)
+        t_dense = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) if 0 < n_dense < nc else None
+        with torch.cuda.stream(self.stream_out):
+            self.stream_out.wait_event(built)
+            if offs is not None:
+                slot.h_positions[: offs[-1]].copy_(pos[: offs[-1]], non_blocking=True)
+                slot.positions_copied.record(self.stream_out)
+                self.d2h_bytes += offs[-1] * 4
+            if n_dense:
+                if t_dense:
+                    t_dense[0].record(self.stream_out)
+                slot.h_filters[:n_dense].copy_(slot.d_filters[:n_dense, : self.words], non_blocking=True)
+                if t_dense:
+                    t_dense[1].record(self.stream_out)
+                self.d2h_bytes += n_dense * self.words * 8
+            slot.copied.record(self.stream_out)
+        if offs is not None:
+            pos.record_stream(self.stream_out)
+        return self._sinks.submit(self._consume, slot, members[0], nc, n_dense, offs, sink, t_dense)
 
     def _consume(self, slot: _Slot, first: int, nc: int, n_dense: int, offs: Optional[List[int]], sink, t_dense) -> None:
         try:
