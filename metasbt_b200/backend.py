@@ -269,6 +269,59 @@ class CudaBackend:
         self._write(out_path, out)
         self._put(out_path, out)
 
+    def union_many(self, jobs: Sequence[Tuple[Sequence[str], str]]) -> None:
+        """Many independent `bfoperate --or` calls (all clusters of one taxonomic level, core.py:1408-1427 runs them one
+        spawn after the other): the OR kernels are queued back to back, the results leave through a small ring of pinned
+        buffers on a side stream and a thread pool writes the `.bf` files while the next unions run.  A job with a single
+        source is the byte copy of core.py:3781-3789."""
+        if not jobs:
+            return
+        header = bffile.BloomHeader(kmer_size=self.k, num_bits=self.num_bits)
+        ring = [torch.empty(self.words, dtype=torch.int64, pin_memory=True) for _ in range(min(4, len(jobs)))]
+        free: "list[torch.Tensor]" = list(ring)
+        import threading
+        cond = threading.Condition()
+        main = torch.cuda.current_stream(self.ctx.device)
+        side = torch.cuda.Stream(self.ctx.device)
+        step = self._chunk()
+        with ThreadPoolExecutor(max_workers=min(4, os.cpu_count() or 1)) as writers:
+            pending = []
+            for srcs, out_path in jobs:
+                out = None
+                if len(srcs) == 1:
+                    out = self.filter(srcs[0]).clone()
+                else:
+                    for lo in range(0, len(srcs), step):
+                        rows = [self.filter(p) for p in srcs[lo: lo + step]]
+                        out = self.ctx.bf_or(rows if out is None else [out] + rows, self.num_bits)
+                    if self.stride > self.words:
+                        out[self.words:] = 0
+                with cond:
+                    while not free:
+                        cond.wait()
+                    host = free.pop()
+                built = torch.cuda.Event()
+                built.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(built)
+                    host.copy_(out[: self.words], non_blocking=True)
+                    done = torch.cuda.Event()
+                    done.record(side)
+                out.record_stream(side)
+
+                def write(out_path=out_path, host=host, done=done):
+                    try:
+                        done.synchronize()
+                        bffile.write_bf(out_path, header, host.numpy().view(np.uint64))
+                    finally:
+                        with cond:
+                            free.append(host)
+                            cond.notify()
+                pending.append(writers.submit(write))
+                self._put(out_path, out)
+            for job in pending:
+                job.result()
+
     def copy(self, src_path: str, out_path: str) -> None:
         t = self.filter(src_path).clone()
         self._write(out_path, t)

@@ -352,12 +352,16 @@ class Database(object):
         processed = set()
         for level in reversed(LEVELS):
             pos = LEVELS.index(level)
+            # the clusters of one level are independent: their unions go to the device as ONE batch (Entry.index_many); the
+            # reference indexes them one after the other, one `bfoperate` spawn each (core.py:1408-1427)
+            batch = []
             for taxonomy in self._touched:
                 partial = "|".join(taxonomy.split("|")[: pos + 1])
                 if partial not in processed:
                     print(f"Update: {partial}")
-                    self.clusters[level][partial.split("|")[-1]].index()
+                    batch.append(self.clusters[level][partial.split("|")[-1]])
                     processed.add(partial)
+            Entry.index_many(batch)
         db_id = "MSBT0"
         db_folder = os.path.join(self.root, "clusters", self._get_cluster_batch(db_id), db_id)
         db_obj = Entry(self, db_id, "db", None, folder=db_folder, parent=None, children=set(self.clusters["kingdom"].keys()))
@@ -1085,6 +1089,59 @@ class Entry(object):
         return [e.sketch_filepath for e in entries]
 
     # ------------------------------------------------------------------ K2: index (core.py:3714-3878)
+    @staticmethod
+    def index_many(entries: Sequence["Entry"]) -> None:
+        """index() for many independent clusters (one taxonomic level): file lists and flat trees are written per entry, the
+        unions run as one batch (backend.union_many).  Clustered (flat=False) databases index entry by entry."""
+        if not entries:
+            return
+        db = entries[0].database
+        if not db.flat or not hasattr(db.backend, "union_many"):
+            for entry in entries:
+                entry.index()
+            return
+        jobs = []
+        for entry in entries:
+            ordered, target = entry._prepare_index()
+            jobs.append((ordered, target))
+        db.backend.union_many(jobs)
+        for entry, (ordered, target) in zip(entries, jobs):
+            entry._finish_index(ordered, target)
+
+    def _prepare_index(self) -> Tuple[List[str], str]:
+        """Checks, `<name>.txt` and the ordered child list of index() (core.py:3729-3776); -> (children, target filter)."""
+        db = self.database
+        if not Database._validate_metadata(db.metadata):
+            raise Exception("No database metadata found!")
+        if self.level == "genome":
+            raise Exception("Genome entries cannot be indexed!")
+        if not self.children:
+            raise Exception("This entry is empty!")
+        if os.path.isdir(self.folder):
+            shutil.rmtree(os.path.join(self.folder, "tree"), ignore_errors=True)
+            os.makedirs(os.path.join(self.folder, "tree"), exist_ok=True)
+        if self.level == "species":
+            sketches = {db.genomes[child].sketch_filepath for child in self.children}
+        else:
+            lower = "kingdom" if not self.level else LEVELS[LEVELS.index(self.level) + 1]
+            sketches = set()
+            for child in self.children:
+                obj = db.clusters[lower][child]
+                sketches.add(os.path.join(obj.folder, f"{obj.name}.bf"))
+        ordered = sorted(sketches)  # the reference iterates the set (hash order)
+        with open(os.path.join(self.folder, f"{self.name}.txt"), "w+") as handle:
+            for path in ordered:
+                handle.write(f"{path}\n")
+        return ordered, os.path.join(self.folder, f"{self.name}.bf")
+
+    def _finish_index(self, ordered: Sequence[str], target: str) -> None:
+        """The flat `index.detbrief.sbt` of index() (core.py:3870-3875)."""
+        with open(os.path.join(self.folder, "tree", "index.detbrief.sbt"), "w+") as flat_tree:
+            flat_tree.write(f"{target}\n")
+            for path in ordered:
+                flat_tree.write(f"*{path}\n")
+        self.sketch_filepath = target
+
     def index(self) -> None:
         db = self.database
         if not Database._validate_metadata(db.metadata):

@@ -181,6 +181,24 @@ class MultiGpuBackend:
         tpart._put(out_path, out)
         self._set_home(out_path, target)
 
+    def union_many(self, jobs: Sequence[Tuple[Sequence[str], str]]) -> None:
+        """All clusters of one level: a job whose sources live on one device runs there (jobs of different devices in
+        parallel, each through CudaBackend.union_many); a job that spans devices goes through union()."""
+        local: Dict[int, List[Tuple[Sequence[str], str]]] = dict()
+        spanning = []
+        for srcs, out in jobs:
+            homes = {self._home_of(p) for p in srcs}
+            if len(homes) == 1:
+                local.setdefault(homes.pop(), []).append((srcs, out))
+            else:
+                spanning.append((srcs, out))
+        self._each({d: (lambda d=d: self.parts[d].union_many(local[d])) for d in local})
+        for d, js in local.items():
+            for _srcs, out in js:
+                self._set_home(out, d)
+        for srcs, out in spanning:
+            self.union(srcs, out)
+
     def copy(self, src_path: str, out_path: str) -> None:
         d = self._home_of(src_path)
         self.parts[d].copy(src_path, out_path)

@@ -42,6 +42,10 @@ class OracleBackend:
     def union(self, src_paths: Sequence[str], out_path: str) -> None:
         self._store(out_path, O.bf_or([self._load(p) for p in src_paths]))
 
+    def union_many(self, jobs) -> None:
+        for srcs, out in jobs:
+            self.copy(srcs[0], out) if len(srcs) == 1 else self.union(srcs, out)
+
     def copy(self, src_path: str, out_path: str) -> None:
         self._store(out_path, self._load(src_path).copy())
 

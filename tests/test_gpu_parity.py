@@ -625,6 +625,13 @@ def test_backend_streams_operands_in_chunks(ctx, oracle, tmp_path):
     assert be.popcounts(bfs) == [oracle.bf_popcount(f) for f in flt]
     be.union(bfs, str(tmp_path / "u.bf"))
     assert np.array_equal(bffile.read_bf(str(tmp_path / "u.bf"))[1], oracle.bf_or(flt))
+    jobs = [(bfs[:9], str(tmp_path / "u0.bf")), ([bfs[4]], str(tmp_path / "u1.bf")), (bfs[7:], str(tmp_path / "u2.bf")),
+            (bfs[2:4], str(tmp_path / "u3.bf")), (bfs, str(tmp_path / "u4.bf")), (bfs[10:13], str(tmp_path / "u5.bf"))]
+    be.union_many(jobs)  # more jobs than pinned ring slots, one of them a single-source copy, all longer than a chunk or not
+    for srcs, out in jobs:
+        assert np.array_equal(bffile.read_bf(out)[1], oracle.bf_or([flt[bfs.index(p)] for p in srcs])), out
+        assert np.array_equal(be.filter(out)[: be.words].cpu().numpy().view(np.uint64), bffile.read_bf(out)[1])
+    assert open(jobs[1][1], "rb").read() == open(bfs[4], "rb").read()
     assert be.dist_one_vs_many(bfs[3], bfs) == [(oracle.bf_and_popcount(flt[3], f), oracle.bf_or_popcount(flt[3], f)) for f in flt]
     pairs = [(bfs[rng.randrange(n)], bfs[rng.randrange(n)]) for _ in range(17)]
     idx = {p: i for i, p in enumerate(bfs)}
