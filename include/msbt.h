@@ -126,6 +126,13 @@ int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, const uint32_
 int msbt_bf_or_reduce(msbt_ctx *ctx, const uint64_t *const *h_srcs, uint32_t n, uint64_t words,
                       uint64_t *d_dst, void *stream);
 
+/* ---------------------------------------------------------------- occurrence classes of a set of filters
+ * One streaming pass over n filters: d_out[0] = bits set in at least one filter, d_out[1] = bits set in at least two.
+ * Serves the k-mer size search that stands in for `kitsune kopt` (core.py:439-468): the number of distinct k-mers
+ * shared by two or more genomes.  d_out: 2 u64 in device memory, zeroed by the call. */
+int msbt_bf_occurrence(msbt_ctx *ctx, const uint64_t *const *h_filters, uint32_t n, uint64_t words,
+                       uint64_t *d_out, void *stream);
+
 /* ---------------------------------------------------------------- K3': howdesbt dumpbf --show:density
  * Replaces core.py:3588-3593 (Entry.get_density).  d_out[i] = popcount(filter i). */
 int msbt_bf_popcount(msbt_ctx *ctx, const uint64_t *const *h_filters, uint32_t n, uint64_t words,

@@ -28,7 +28,7 @@ NVCC_FLAGS = [
 SYMBOLS = [
     "msbt_abi_version", "msbt_hash_spec_default", "msbt_ctx_create", "msbt_ctx_get_spec", "msbt_ctx_destroy", "msbt_last_error", "msbt_sync",
     "msbt_launch_count", "msbt_fasta_pack", "msbt_fasta_pack_device", "msbt_kmer_bloom_build", "msbt_bf_or_reduce",
-    "msbt_bf_popcount", "msbt_bf_and_popcount_1vN", "msbt_bf_and_popcount_pairs", "msbt_bf_and_popcount_allpairs", "msbt_bf_and_popcount_rect",
+    "msbt_bf_popcount", "msbt_bf_occurrence", "msbt_bf_and_popcount_1vN", "msbt_bf_and_popcount_pairs", "msbt_bf_and_popcount_allpairs", "msbt_bf_and_popcount_rect",
     "msbt_query_batch_ranges", "msbt_query_batch_sliced_ranges", "msbt_positions_expand",
     "msbt_bf_extract_positions", "msbt_bf_extract_positions_batch", "msbt_query_batch", "msbt_bitslice_build", "msbt_query_batch_sliced", "msbt_sliced_row_words",
 ]
@@ -119,6 +119,8 @@ def lib() -> ctypes.CDLL:
     L.msbt_bf_or_reduce.restype = i32
     L.msbt_bf_popcount.argtypes = [vp, P(vp), u32, u64, vp, vp]
     L.msbt_bf_popcount.restype = i32
+    L.msbt_bf_occurrence.argtypes = [vp, P(vp), u32, u64, vp, vp]
+    L.msbt_bf_occurrence.restype = i32
     L.msbt_bf_and_popcount_1vN.argtypes = [vp, vp, P(vp), u32, u64, vp, vp, vp]
     L.msbt_bf_and_popcount_1vN.restype = i32
     L.msbt_bf_and_popcount_pairs.argtypes = [vp, P(vp), P(vp), u32, u64, vp, vp, vp]

@@ -130,6 +130,7 @@ class CudaBackend:
         self._sliced.clear()
         self._sliced_bytes = 0
         self._pipes.clear()
+        self._set_text_key = self._set_text = None
         torch.cuda.empty_cache()
 
     def forget(self, path: str) -> None:
@@ -255,6 +256,43 @@ class CudaBackend:
         if acc is None:
             return 0
         return int(self.ctx.bf_popcount([acc], num_bits)[0])
+
+    # ------------------------------------------------------------------ k-mer size search (kopt.py)
+    @property
+    def device(self) -> torch.device:
+        return self.ctx.device
+
+    def read_fasta(self, path: str) -> bytes:
+        return read_fasta_bytes(path)
+
+    @_retry_after_oom
+    def kmer_set_profile(self, fasta_paths: Sequence[str], kmer_size: int, num_bits: int, modulus: int):
+        """Per genome ONE filter of `num_bits` bits over the k-mers whose hash modulo `modulus` is below `num_bits`
+        (K1), then their popcounts and pairwise intersections (K3 all pairs) and the number of bits set in at least one /
+        at least two of them (msbt_bf_occurrence): (pop[n], inter[n][n], ge1, ge2) as Python integers.  The FASTA text
+        stays on the device between calls with the same path list (kopt.py walks k over a range)."""
+        key = tuple(fasta_paths)
+        if getattr(self, "_set_text_key", None) != key:
+            texts = read_files(fasta_paths)
+            sizes = [len(t) for t in texts]
+            h_text = torch.empty(max(sum(sizes), 1), dtype=torch.uint8, pin_memory=True)
+            hv, off = h_text.numpy(), 0
+            for t in texts:
+                hv[off: off + len(t)] = np.frombuffer(t, dtype=np.uint8)
+                off += len(t)
+            self._set_text = (h_text.to(self.ctx.device, non_blocking=True), sizes)
+            self._set_text_key = key
+        d_text, sizes = self._set_text
+        batch = self.ctx.pack_device_text(d_text, sizes, kmer_size)
+        filters = self.ctx.build_filters(batch, kmer_size, num_bits, min_abund=1, modulus=modulus)
+        rows = [filters[i] for i in range(len(sizes))]
+        inter = self.ctx.bf_allpairs(rows, num_bits)
+        occ = self.ctx.bf_occurrence(rows, num_bits)
+        inter_h, occ_h = inter.cpu().tolist(), occ.cpu().tolist()
+        return [inter_h[i][i] for i in range(len(sizes))], inter_h, occ_h[0], occ_h[1]
+
+    def kmer_set_profile_done(self) -> None:
+        self._set_text_key = self._set_text = None
 
     # ------------------------------------------------------------------ bfoperate --or
     @_retry_after_oom

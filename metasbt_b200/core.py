@@ -8,7 +8,7 @@ and result files (`clusters.tsv`, `genomes.tsv`, `metadata.json`, `<name>.txt`,
 `tree/index.detbrief.sbt`, `tmp/profiles/<genome>.txt`) as /root/reference/metasbt/core.py.
 flat=False databases get their tree topology from cluster.py (`howdesbt cluster`: greedy Hamming agglomeration over
 K3 / K2) with plain union nodes; the determined/brief RRR node files of `howdesbt build --howde` are out of scope.
-Out of scope and raising NotImplementedError: kitsune k-mer size estimation (pass --kmer-size), qc/merge/remove.
+Out of scope and raising NotImplementedError: qc/merge/remove.  The k-mer size search (kitsune, core.py:439-468) is restated in kopt.py.
 The `update` consumers of the same kernels (is_known, characterize, _estimate_boundaries) are included.
 
 Differences that are deliberate (documented in DESIGN.md):
@@ -266,7 +266,10 @@ class Database(object):
         if not kmer_size:
             if not kmer_max:
                 raise ValueError("Max kmer size must be provided!")
-            raise NotImplementedError("k-mer size estimation (kitsune) is outside the B200 hot path: pass kmer_size")
+            # core.py:439-468 runs `kitsune kopt --k-max kmer_max --canonical` here; kopt.py restates its method
+            from . import kopt
+            searcher = self._backend if self._backend is not None else get_backend(kmer_max, kopt.SET_BITS)
+            kmer_size = kopt.optimal_kmer_size(sorted(filepaths), kmer_max, searcher)
         self.metadata["kmer_size"] = kmer_size
         if not filter_size:
             # core.py:470-529 runs ntCard here; the distinct k-mer count comes from K1 + K3' instead (estimate.py)

@@ -199,12 +199,20 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
     volatile uint32_t *claim = stage + FU_STAGE_WORDS;               // [0..1] P: chunk, genome; [4..5] B: item
     const uint32_t NB = P.NB;
 
-    if (threadIdx.x < FU_P_THREADS) {
+    // MSBT_FU_B_FIRST puts the tile-build role on the low warp ids (a scheduler that breaks ties oldest-first would favour them)
+#ifdef MSBT_FU_B_FIRST
+    const bool role_p = threadIdx.x >= FU_B_THREADS;
+    const uint32_t role_tid = role_p ? threadIdx.x - FU_B_THREADS : threadIdx.x;
+#else
+    const bool role_p = threadIdx.x < FU_P_THREADS;
+    const uint32_t role_tid = role_p ? threadIdx.x : threadIdx.x - FU_P_THREADS;
+#endif
+    if (role_p) {
         // ------------------------------------------------------------------ P: partition
 #ifdef MSBT_FU_SETMAXNREG
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(MSBT_FU_P_REGS));  // registers handed over by the B warps
 #endif
-        const uint32_t tid = threadIdx.x;
+        const uint32_t tid = role_tid;
         const uint32_t cnt_s = (uint32_t)__cvta_generic_to_shared(cnt);
         const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
         const uint32_t k = spec.k, len = (k + 3) >> 2;
@@ -369,7 +377,7 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
         // Software-pipelined by one item: the claim of item i+1 and the L2 loads of its positions are issued
         // while item i's last tile drains, so that the only exposed latency per tile is the smem read-out of
         // the previous bulk store.
-        const uint32_t tid = threadIdx.x - FU_P_THREADS;
+        const uint32_t tid = role_tid;
         const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(tile);
         const uint32_t n_items = P.n_genomes * NB;
         const uint32_t tile_words32 = 1u << (P.tile_log2 - 5);

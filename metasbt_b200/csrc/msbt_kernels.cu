@@ -1729,6 +1729,50 @@ bf_or_reduce_kernel(const uint4 *const *__restrict__ srcs, uint32_t n, uint64_t 
     }
 }
 
+// out[0] += bits set in at least one of the n filters, out[1] += bits set in at least two: one streaming pass, nothing
+// filter-sized is written (kopt.py: the number of distinct k-mers seen in >= 2 genomes).  `vec` = uint4 per filter.
+__global__ void __launch_bounds__(256)
+bf_occurrence_kernel(const uint4 *const *__restrict__ srcs, uint32_t n, uint64_t vec, uint64_t words,
+                     unsigned long long *__restrict__ out) {
+    uint64_t c1 = 0, c2 = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < vec; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 once = make_uint4(0, 0, 0, 0), twice = make_uint4(0, 0, 0, 0);
+        uint32_t s = 0;
+        for (; s + 2 <= n; s += 2) {
+            const uint4 a = ld_stream(srcs[s] + i), b = ld_stream(srcs[s + 1] + i);
+            twice.x |= (once.x & (a.x | b.x)) | (a.x & b.x); once.x |= a.x | b.x;
+            twice.y |= (once.y & (a.y | b.y)) | (a.y & b.y); once.y |= a.y | b.y;
+            twice.z |= (once.z & (a.z | b.z)) | (a.z & b.z); once.z |= a.z | b.z;
+            twice.w |= (once.w & (a.w | b.w)) | (a.w & b.w); once.w |= a.w | b.w;
+        }
+        if (s < n) {
+            const uint4 a = ld_stream(srcs[s] + i);
+            twice.x |= once.x & a.x; once.x |= a.x;
+            twice.y |= once.y & a.y; once.y |= a.y;
+            twice.z |= once.z & a.z; once.z |= a.z;
+            twice.w |= once.w & a.w; once.w |= a.w;
+        }
+        c1 += popc4(once);
+        c2 += popc4(twice);
+    }
+    if ((words & 1) && blockIdx.x == 0 && threadIdx.x == 0) {  // odd number of u64 words
+        uint64_t once = 0, twice = 0;
+        for (uint32_t s = 0; s < n; s++) {
+            const uint64_t a = ((const uint64_t *)srcs[s])[words - 1];
+            twice |= once & a;
+            once |= a;
+        }
+        c1 += __popcll(once);
+        c2 += __popcll(twice);
+    }
+    c1 = block_sum_u64(c1);
+    c2 = block_sum_u64(c2);
+    if (threadIdx.x == 0) {
+        if (c1) atomicAdd(out + 0, (unsigned long long)c1);
+        if (c2) atomicAdd(out + 1, (unsigned long long)c2);
+    }
+}
+
 // scalar tail for an odd number of u64 words
 __global__ void bf_or_tail_kernel(const uint64_t *const *__restrict__ srcs, uint32_t n, uint64_t w, uint64_t *__restrict__ dst) {
     uint64_t acc = 0;
@@ -2135,6 +2179,26 @@ extern "C" int msbt_bf_or_reduce(msbt_ctx *ctx, const uint64_t *const *h_srcs, u
         bf_or_tail_kernel<<<1, 1, 0, stream>>>(d_srcs, n, words - 1, d_dst);
         LAUNCH_CHECK(ctx);
     }
+    return MSBT_OK;
+}
+
+extern "C" int msbt_bf_occurrence(msbt_ctx *ctx, const uint64_t *const *h_filters, uint32_t n, uint64_t words,
+                                  uint64_t *d_out, void *stream_) {
+    if (!ctx) return MSBT_EINVAL;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (words == 0 || !d_out) return fail(ctx, MSBT_EINVAL, "bf_occurrence: empty input");
+    CTX_DEVICE(ctx);
+    CU_TRY(ctx, cudaMemsetAsync(d_out, 0, 16, stream));
+    if (n == 0) return MSBT_OK;
+    int rc = check_ptrs(ctx, h_filters, n);
+    if (rc) return rc;
+    const uint64_t *const *d_f;
+    rc = upload_ptrs(ctx, h_filters, n, stream, &d_f);
+    if (rc) return rc;
+    const uint64_t vec = words >> 1;
+    bf_occurrence_kernel<<<stream_grid(ctx, std::max<uint64_t>(vec, 1), 8), 256, 0, stream>>>((const uint4 *const *)d_f, n, vec, words,
+                                                                                             (unsigned long long *)d_out);
+    LAUNCH_CHECK(ctx);
     return MSBT_OK;
 }
 

@@ -155,6 +155,20 @@ class MultiGpuBackend:
         # one shared counting filter: a single pass on one device (estimate.py; not worth an exchange)
         return self.parts[0].count_union_bits(fasta_paths, kmer_size, num_bits, modulus)
 
+    # k-mer size search (kopt.py): at most kopt.MAX_GENOMES small filters per k -- one device
+    @property
+    def device(self):
+        return self.parts[0].device
+
+    def read_fasta(self, path: str) -> bytes:
+        return self.parts[0].read_fasta(path)
+
+    def kmer_set_profile(self, fasta_paths: Sequence[str], kmer_size: int, num_bits: int, modulus: int):
+        return self.parts[0].kmer_set_profile(fasta_paths, kmer_size, num_bits, modulus)
+
+    def kmer_set_profile_done(self) -> None:
+        self.parts[0].kmer_set_profile_done()
+
     # ------------------------------------------------------------------ bfoperate --or
     def union(self, src_paths: Sequence[str], out_path: str) -> None:
         by_dev: Dict[int, List[str]] = dict()

@@ -356,6 +356,14 @@ class Context:
             self._check(rc, "msbt_bf_popcount")
         return out
 
+    def bf_occurrence(self, filters: Sequence[torch.Tensor], num_bits: int) -> torch.Tensor:
+        """int64[2]: bits set in at least one / in at least two of the filters (one streaming pass; kopt.py)."""
+        out = torch.empty(2, dtype=torch.int64, device=self.device)
+        rc = self._L.msbt_bf_occurrence(self._h, _ptr_array(filters) if len(filters) else None, len(filters),
+                                        filter_words(num_bits), out.data_ptr(), self._stream())
+        self._check(rc, "msbt_bf_occurrence")
+        return out
+
     # ------------------------------------------------------------------ K3
     def bf_dist(self, focus: torch.Tensor, targets: Sequence[torch.Tensor], num_bits: int) -> Tuple[torch.Tensor, torch.Tensor]:
         """howdesbt bfdistance --show:intersect and --show:union in one pass -> (I[n], U[n]) int64."""

@@ -333,3 +333,82 @@ def py_positions_distinct(fasta: bytes, k: int, num_bits: int, seed: int = 0,
         if pos < num_bits:
             s.add(pos)
     return np.array(sorted(s), dtype=np.uint64)
+
+
+# ---- k-mer size search (metasbt_b200/kopt.py): the three-step method of Zhang et al. 2017 that `kitsune kopt` implements
+# (reference call site: core.py:439-468; kitsune itself is absent and unpinned).  Exact, dictionary- and set-based.
+
+def py_canonical_str(w: str) -> str:
+    r = w[::-1].translate(str.maketrans("ACGT", "TGCA"))
+    return min(w, r)
+
+
+def py_word_counts(fasta: bytes, l: int) -> dict:
+    counts: dict = {}
+    for w in py_kmers(fasta, l):
+        c = py_canonical_str(w)
+        counts[c] = counts.get(c, 0) + 1
+    return counts
+
+
+def py_relative_entropy(fasta: bytes, l: int) -> float:
+    """RE(l) = sum_w f_l(w) log2( f_l(w) f_{l-2}(w[1:-1]) / (f_{l-1}(w[:-1]) f_{l-1}(w[1:])) ) over canonical words."""
+    import math
+    cl, c1, c2 = py_word_counts(fasta, l), py_word_counts(fasta, l - 1), py_word_counts(fasta, l - 2)
+    nl, n1, n2 = sum(cl.values()), sum(c1.values()), sum(c2.values())
+    if nl == 0:
+        return 0.0
+    total = 0.0
+    for w, c in cl.items():
+        f = c / nl
+        fp = c1[py_canonical_str(w[:-1])] / n1
+        fs = c1[py_canonical_str(w[1:])] / n1
+        fm = c2[py_canonical_str(w[1:-1])] / n2
+        total += f * math.log2(f * fm / (fp * fs))
+    return total
+
+
+def py_kopt(fastas: Sequence[bytes], k_max: int, k_min: int = 4, cre_cutoff: float = 0.1, acf_cutoff: float = 0.1) -> dict:
+    """{'k', 'k_lo', 'k_hi', 'acf', 'ofc', 'cre_limits'} with exact set sizes."""
+    k_min = max(3, min(k_min, k_max))
+    limits = []
+    for fa in fastas:
+        re = {l: py_relative_entropy(fa, l) for l in range(k_min, k_max + 1)}
+        cre, acc = {}, 0.0
+        for k in range(k_max, k_min - 1, -1):
+            acc += re[k]
+            cre[k] = acc
+        top = max(cre.values())
+        lim = k_max
+        if top <= 0.0:
+            lim = k_min
+        else:
+            for k in range(k_min, k_max + 1):
+                if cre[k] <= cre_cutoff * top:
+                    lim = k
+                    break
+        limits.append(lim)
+    k_lo = max(limits)
+    out = {"cre_limits": limits, "k_lo": k_lo}
+    n = len(fastas)
+    if n < 2:
+        out["k"] = k_lo
+        return out
+    acf, ofc = {}, {}
+    for k in range(k_min, k_max + 1):
+        sets = [set(py_word_counts(fa, k)) for fa in fastas]
+        acf[k] = sum(len(sets[i] & sets[j]) for i in range(n) for j in range(i + 1, n)) / (n * (n - 1) / 2)
+        seen, twice = set(), set()
+        for s in sets:
+            twice |= seen & s
+            seen |= s
+        ofc[k] = float(len(twice))
+    top = max(acf.values())
+    k_hi = k_min if top <= 0 else max(k for k in acf if acf[k] >= acf_cutoff * top)
+    best = k_lo
+    if k_lo <= k_hi:
+        for k in range(k_lo, k_hi + 1):
+            if ofc[k] > ofc[best]:
+                best = k
+    out.update({"acf": acf, "ofc": ofc, "k_hi": k_hi, "k": best})
+    return out

@@ -39,6 +39,21 @@ class OracleBackend:
             acc = w if acc is None else O.bf_or([acc, w])
         return 0 if acc is None else O.bf_popcount(acc)
 
+    device = "cpu"
+
+    def read_fasta(self, path: str) -> bytes:
+        return open(path, "rb").read()
+
+    def kmer_set_profile(self, fasta_paths: Sequence[str], kmer_size: int, num_bits: int, modulus: int):
+        f = [O.makebf(open(fa, "rb").read(), kmer_size, num_bits, 1, modulus=modulus, rolling=kmer_size <= 32) for fa in fasta_paths]
+        n = len(f)
+        inter = [[O.bf_and_popcount(f[i], f[j]) for j in range(n)] for i in range(n)]
+        once, twice = np.zeros_like(f[0]), np.zeros_like(f[0])
+        for w in f:
+            twice |= once & w
+            once |= w
+        return [inter[i][i] for i in range(n)], inter, O.bf_popcount(once), O.bf_popcount(twice)
+
     def union(self, src_paths: Sequence[str], out_path: str) -> None:
         self._store(out_path, O.bf_or([self._load(p) for p in src_paths]))
 

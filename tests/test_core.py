@@ -112,9 +112,6 @@ def test_cli_rejects_what_is_out_of_scope(tmp_path):
             "--filter-size", "4096"]
     with pytest.raises(NotImplementedError):
         cli.MetaSBT(base + ["--pack"], backend=object())
-    with pytest.raises(NotImplementedError):
-        cli.MetaSBT(["index", "--workdir", str(tmp_path / "w2"), "--database", "db", "--references", refs,
-                     "--filter-size", "4096"], backend=object())  # k-mer size estimation = kitsune
     with pytest.raises(FileNotFoundError):
         cli.MetaSBT(["profile", "--workdir", str(tmp_path / "nope"), "--database", "db", "--genome", refs])
 
