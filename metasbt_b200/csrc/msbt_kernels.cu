@@ -46,6 +46,12 @@ struct msbt_ctx {
     bool tiled_attr_set;  // dynamic-smem opt-in done for this device
     bool fused_attr_set;
     bool phased_attr_set;
+    // side streams of the `--min >= 2` build: consecutive genomes run concurrently (their passes are bound by different
+    // units: L2 atomics, issue slots, latency), forked from and joined to the caller's stream inside the call
+    cudaStream_t side[4];
+    cudaEvent_t side_done[4];
+    cudaEvent_t fork_ev;
+    int n_side;
 };
 
 static int fail(msbt_ctx *ctx, int code, const char *fmt, ...) {
@@ -196,6 +202,11 @@ extern "C" void msbt_ctx_destroy(msbt_ctx *ctx) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->stage_free) cudaEventDestroy(ctx->stage_free);
+    for (int i = 0; i < ctx->n_side; i++) {
+        cudaStreamDestroy(ctx->side[i]);
+        cudaEventDestroy(ctx->side_done[i]);
+    }
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
     delete ctx;
 }
 
@@ -824,6 +835,18 @@ struct PreState {
 };
 constexpr unsigned long long PRE_OCC = 1ull << 63;  // k <= 31: keys < 2^62, so an occupied slot is never 0
 constexpr uint32_t PRE_BLOCK_LIST = 1024;           // candidates a block gathers in shared memory before one global reservation
+// The count pass reads a table that holds ~2 % of the k-mers: a two-probe Bloom bitmap of the candidate keys (2^20 bits =
+// 128 KiB, filled by the insert pass, copied into shared memory by every CTA of the count pass) answers "not a candidate"
+// for ~95 % of the k-mers without an L2 access.
+constexpr uint32_t PRE_CB_LOG2_MAX = 20;
+constexpr uint32_t PRE_CB_WORDS_MAX = 1u << (PRE_CB_LOG2_MAX - 5);
+constexpr int PRE_COUNT_THREADS = 1024;
+// the two bitmap probes of a key; `mult`: one multiplication instead of fmix64 (tuning switch)
+__device__ __forceinline__ void pre_cb_bits(uint64_t key, uint32_t cb_mask, uint32_t mult, uint32_t &b1, uint32_t &b2) {
+    const uint64_t h = mult ? (key ^ (key >> 29)) * 0xC2B2AE3D27D4EB4FULL : msbt_fmix64(key ^ 0xC2B2AE3D27D4EB4FULL);
+    b1 = (uint32_t)(h >> 40) & cb_mask;
+    b2 = (uint32_t)(h >> 18) & cb_mask;
+}
 
 __device__ __forceinline__ void pre_mark(uint64_t key, uint32_t *__restrict__ bits, uint64_t bit_mask, uint64_t *s_list,
                                          uint32_t *s_n, uint64_t *__restrict__ cand, PreState *st) {
@@ -878,8 +901,10 @@ __device__ __forceinline__ uint32_t pre_slots(uint32_t n_cand, uint32_t max_slot
 }
 
 __global__ void __launch_bounds__(256)
-kmer_pre_prepare_kernel(PreState *st, unsigned long long *__restrict__ tab, uint32_t *__restrict__ cnt, uint32_t max_slots) {
+kmer_pre_prepare_kernel(PreState *st, unsigned long long *__restrict__ tab, uint32_t *__restrict__ cnt, uint32_t max_slots,
+                        uint32_t *__restrict__ cbits, uint32_t cb_words) {
     const uint32_t slots = pre_slots(st->n_cand, max_slots);
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cb_words; s += gridDim.x * blockDim.x) cbits[s] = 0u;
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < slots; s += gridDim.x * blockDim.x) {
         tab[s] = 0ull;
         cnt[s] = 0u;
@@ -888,14 +913,22 @@ kmer_pre_prepare_kernel(PreState *st, unsigned long long *__restrict__ tab, uint
 }
 
 __global__ void __launch_bounds__(256)
-kmer_pre_insert_kernel(const PreState *st, const uint64_t *__restrict__ cand, unsigned long long *__restrict__ tab) {
+kmer_pre_insert_kernel(const PreState *st, const uint64_t *__restrict__ cand, unsigned long long *__restrict__ tab,
+                       uint32_t *__restrict__ cbits, uint32_t cb_mask, uint32_t cb_mult) {
     const uint32_t n = st->n_cand, mask = st->slot_mask;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         const unsigned long long want = cand[i] | PRE_OCC;
         uint32_t slot = (uint32_t)ht_slot(cand[i], mask);
         while (true) {
             const unsigned long long old = atomicCAS(tab + slot, 0ull, want);
-            if (old == 0ull || old == want) break;
+            if (old == 0ull) {  // the thread that placed the key also publishes it in the bitmap
+                uint32_t b1, b2;
+                pre_cb_bits(cand[i], cb_mask, cb_mult, b1, b2);
+                atomicOr(cbits + (b1 >> 5), 1u << (b1 & 31));
+                atomicOr(cbits + (b2 >> 5), 1u << (b2 & 31));
+                break;
+            }
+            if (old == want) break;
             slot = (slot + 1) & mask;
         }
     }
@@ -936,6 +969,65 @@ kmer_pre_count_kernel(const uint64_t *__restrict__ packed, const uint32_t *__res
             kb.advance8();
         }
     }
+}
+
+// The same count with the candidate bitmap in shared memory.  Work unit = a quarter word (8 k-mers): with one 1,024-thread
+// CTA per SM a 5 Mbp genome has ~4 units per thread, so the last, partly filled round costs little.
+#define MSBT_PRE_COUNT_STEP_CB(J)                                                                      \
+    {                                                                                                  \
+        uint64_t lo_, hi_;                                                                             \
+        kb.template get<J>(lo_, hi_);                                                                  \
+        uint32_t b1_, b2_;                                                                             \
+        pre_cb_bits(lo_, cb_mask, cb_mult, b1_, b2_);                                                  \
+        const uint32_t hit_ = (s_cb[b1_ >> 5] >> (b1_ & 31)) & (s_cb[b2_ >> 5] >> (b2_ & 31)) & (vg >> J) & 1u; \
+        if (hit_) {                                                                                    \
+            const unsigned long long want_ = lo_ | PRE_OCC;                                            \
+            uint32_t slot_ = (uint32_t)ht_slot(lo_, mask);                                             \
+            while (true) {                                                                             \
+                const unsigned long long v_ = __ldg(tab + slot_);                                      \
+                if (v_ == 0ull) break;                                                                 \
+                if (v_ == want_) { atomicAdd(cnt + slot_, 1u); break; }                                \
+                slot_ = (slot_ + 1) & mask;                                                            \
+            }                                                                                          \
+        }                                                                                              \
+    }
+
+// `ug` = groups of 8 k-mers per work unit (1, 2 or 4): with one or two 1,024-thread CTAs per SM a 5 Mbp genome has only a
+// few units per thread, so finer units make the last, partly filled round cheap at the price of repeated set-up.
+__global__ void __launch_bounds__(PRE_COUNT_THREADS, 2)
+kmer_pre_count_cb_kernel(const uint64_t *__restrict__ packed, const uint32_t *__restrict__ run_ends, DevGenome g, uint32_t k,
+                         const PreState *st, const unsigned long long *__restrict__ tab, uint32_t *__restrict__ cnt,
+                         const uint32_t *__restrict__ cbits, uint32_t cb_mask, uint32_t cb_mult, uint32_t ug) {
+    extern __shared__ __align__(16) uint32_t s_cb[];
+    if (st->n_cand == 0) return;  // no k-mer can occur twice
+    for (uint32_t i = threadIdx.x; i < (cb_mask + 1u) / 128u; i += PRE_COUNT_THREADS) ((uint4 *)s_cb)[i] = __ldcg((const uint4 *)cbits + i);
+    __syncthreads();
+    const uint32_t mask = st->slot_mask;
+    const uint32_t upw = 4u / ug;  // units per packed word
+    const uint32_t n_units = ((g.n_bases + 31) / 32) * upw;
+    for (uint32_t u = blockIdx.x * PRE_COUNT_THREADS + threadIdx.x; u < n_units; u += gridDim.x * PRE_COUNT_THREADS) {
+        const uint32_t w = u / upw, g0 = (u % upw) * ug;
+        const uint32_t vm = valid_mask(run_ends + g.run_off, g.n_runs, w * 32, k) >> (8 * g0);
+        if ((ug == 4 ? vm : (vm & ((1u << (8 * ug)) - 1u))) == 0) continue;
+        KmerBlock<1> kb;
+        kb.init(packed + g.packed_word_off + w, k);
+        for (uint32_t a = 0; a < g0; a++) kb.advance8();
+#pragma unroll 1
+        for (uint32_t grp = 0; grp < ug; grp++) {
+            const uint32_t vg = (vm >> (8 * grp)) & 0xFFu;
+            MSBT_PRE_COUNT_STEP_CB(0) MSBT_PRE_COUNT_STEP_CB(1) MSBT_PRE_COUNT_STEP_CB(2) MSBT_PRE_COUNT_STEP_CB(3)
+            MSBT_PRE_COUNT_STEP_CB(4) MSBT_PRE_COUNT_STEP_CB(5) MSBT_PRE_COUNT_STEP_CB(6) MSBT_PRE_COUNT_STEP_CB(7)
+            kb.advance8();
+        }
+    }
+}
+
+// zero-fill with streaming stores (evict-first in L2): a filter zeroed next to the mark pass of another genome must not push
+// that genome's bit table out of L2
+__global__ void __launch_bounds__(256)
+bf_zero_stream_kernel(uint4 *__restrict__ dst, uint64_t vec) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < vec; i += (uint64_t)gridDim.x * blockDim.x)
+        __stcs(dst + i, make_uint4(0, 0, 0, 0));
 }
 
 __global__ void __launch_bounds__(256)
@@ -1469,8 +1561,13 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
         return MSBT_OK;
     }
 
+    // MSBT_PRE_ZERO_INLINE=1 (tuning): the `--min >= 2` build zeroes each filter on its genome's side stream right before the
+    // emit pass instead of all of them up front
+    const bool pre_path = min_abund >= 2 && k <= 31 && max_bases < (1ull << 30) && !getenv("MSBT_MIN_TABLE");
+    const char *zi_env = getenv("MSBT_PRE_ZERO_INLINE");
+    const bool pre_zero_inline = pre_path && distinct && zi_env && zi_env[0] == '1';
     // zero-fill every output filter (the reference always writes a complete new file)
-    {
+    if (!pre_zero_inline) {
         // one memset per maximal contiguous span of output filters (ascending filter_index, dense stride)
         std::vector<uint64_t> offs(n_genomes);
         for (uint32_t i = 0; i < n_genomes; i++) offs[i] = dg[i].filter_word_off;
@@ -1483,7 +1580,7 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
         }
     }
 
-    if (min_abund >= 2 && k <= 31 && max_bases < (1ull << 30) && !getenv("MSBT_MIN_TABLE")) {
+    if (pre_path) {
         // prefiltered exact counting (see kmer_pre_mark_kernel); MSBT_MIN_TABLE=1 selects the plain count tables below
         uint64_t bit_count = 1ull << 16;
         while (bit_count < 32 * max_bases && bit_count < (1ull << 33)) bit_count <<= 1;
@@ -1493,35 +1590,91 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
         const size_t cand_off = align_up(bits_off + bit_count / 8, 256);
         const size_t tab_off = align_up(cand_off + max_bases * 8, 256);
         const size_t cnt_off = align_up(tab_off + max_slots * 8, 256);
-        int rc = ensure_scratch(ctx, cnt_off + max_slots * 4);
+        const size_t cb_off = align_up(cnt_off + max_slots * 4, 256);
+        const size_t slot_bytes = align_up(cb_off + PRE_CB_WORDS_MAX * 4, 256);
+        // MSBT_PRE_STREAMS (1..4, default 3): genomes in flight at once, each with its own scratch slot and side stream
+        int n_streams = 3;
+        if (const char *e = getenv("MSBT_PRE_STREAMS")) n_streams = std::min(4, std::max(1, atoi(e)));
+        n_streams = (int)std::min<uint32_t>((uint32_t)n_streams, n_genomes);
+        int rc = ensure_scratch(ctx, slot_bytes * n_streams);
         if (rc) return rc;
-        char *S = (char *)ctx->d_scratch;
-        PreState *st = (PreState *)(S + st_off);
-        uint32_t *bits = (uint32_t *)(S + bits_off);
-        uint64_t *cand = (uint64_t *)(S + cand_off);
-        unsigned long long *tab = (unsigned long long *)(S + tab_off);
-        uint32_t *cnt = (uint32_t *)(S + cnt_off);
+        if (n_streams > 1) {
+            if (!ctx->fork_ev) CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+            while (ctx->n_side < n_streams) {
+                CU_TRY(ctx, cudaStreamCreateWithFlags(&ctx->side[ctx->n_side], cudaStreamNonBlocking));
+                CU_TRY(ctx, cudaEventCreateWithFlags(&ctx->side_done[ctx->n_side], cudaEventDisableTiming));
+                ctx->n_side++;
+            }
+            CU_TRY(ctx, cudaEventRecord(ctx->fork_ev, stream));  // the zeroed filters and the staged tables are ready
+            for (int q = 0; q < n_streams; q++) CU_TRY(ctx, cudaStreamWaitEvent(ctx->side[q], ctx->fork_ev, 0));
+        }
+        // MSBT_PRE_COUNT_CB=0: the count pass without the shared-memory candidate bitmap (every k-mer reads the table);
+        // tuning: MSBT_PRE_CB_LOG2 (16..20; <= 19 lets two CTAs share an SM), MSBT_PRE_CB_UNIT (1, 2, 4), MSBT_PRE_CB_MULT
+        const char *cb_env = getenv("MSBT_PRE_COUNT_CB");
+        const bool use_cb = !(cb_env && cb_env[0] == '0');
+        uint32_t cb_log2 = 19, cb_ug = 1, cb_mult = 1;
+        if (const char *e = getenv("MSBT_PRE_CB_LOG2")) cb_log2 = std::min<uint32_t>(PRE_CB_LOG2_MAX, std::max<uint32_t>(16, (uint32_t)atoi(e)));
+        if (const char *e = getenv("MSBT_PRE_CB_UNIT")) cb_ug = atoi(e) == 4 ? 4 : (atoi(e) == 2 ? 2 : 1);
+        if (const char *e = getenv("MSBT_PRE_CB_MULT")) cb_mult = e[0] == '1';
+        const uint32_t cb_words = 1u << (cb_log2 - 5), cb_mask = (1u << cb_log2) - 1u;
+        static bool cb_attr_set = false;
+        if (use_cb && !cb_attr_set) {
+            CU_TRY(ctx, cudaFuncSetAttribute(kmer_pre_count_cb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(PRE_CB_WORDS_MAX * 4)));
+            cb_attr_set = true;
+        }
+        uint32_t turn = 0;
         for (uint32_t i = 0; i < n_genomes; i++) {
-            if (dg[i].n_bases < k) continue;
+            if (dg[i].n_bases < k) {
+                if (pre_zero_inline) CU_TRY(ctx, cudaMemsetAsync(d_filters + dg[i].filter_word_off, 0, words * 8, stream));
+                continue;
+            }
+            const int q = (int)(turn++ % (uint32_t)n_streams);
+            cudaStream_t qs = n_streams > 1 ? ctx->side[q] : stream;
+            char *S = (char *)ctx->d_scratch + (size_t)q * slot_bytes;
+            PreState *st = (PreState *)(S + st_off);
+            uint32_t *bits = (uint32_t *)(S + bits_off);
+            uint64_t *cand = (uint64_t *)(S + cand_off);
+            unsigned long long *tab = (unsigned long long *)(S + tab_off);
+            uint32_t *cnt = (uint32_t *)(S + cnt_off);
+            uint32_t *cbits = (uint32_t *)(S + cb_off);
             uint64_t gbits = 1ull << 16;
             while (gbits < 32ull * dg[i].n_bases && gbits < bit_count) gbits <<= 1;
             uint64_t gslots = 1024;
             while (gslots < 2ull * dg[i].n_bases) gslots <<= 1;
-            CU_TRY(ctx, cudaMemsetAsync(S, 0, bits_off + gbits / 8, stream));  // state + bit table
+            CU_TRY(ctx, cudaMemsetAsync(S, 0, bits_off + gbits / 8, qs));  // state + bit table
             const uint32_t n_words = (dg[i].n_bases + 31) / 32;
             const int grid = (int)std::min<uint64_t>((n_words + TILE_THREADS - 1) / TILE_THREADS, (uint64_t)ctx->num_sms * 8);
             const int grid2 = ctx->num_sms * 8;
-            kmer_pre_mark_kernel<<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, dg[i], k, bits, gbits - 1, cand, st);
+            kmer_pre_mark_kernel<<<grid, TILE_THREADS, 0, qs>>>(d_packed, d_run_ends, dg[i], k, bits, gbits - 1, cand, st);
             LAUNCH_CHECK(ctx);
-            kmer_pre_prepare_kernel<<<grid2, 256, 0, stream>>>(st, tab, cnt, (uint32_t)gslots);
+            kmer_pre_prepare_kernel<<<grid2, 256, 0, qs>>>(st, tab, cnt, (uint32_t)gslots, cbits, cb_words);
             LAUNCH_CHECK(ctx);
-            kmer_pre_insert_kernel<<<grid2, 256, 0, stream>>>(st, cand, tab);
+            kmer_pre_insert_kernel<<<grid2, 256, 0, qs>>>(st, cand, tab, cbits, cb_mask, cb_mult);
             LAUNCH_CHECK(ctx);
-            kmer_pre_count_kernel<<<grid, TILE_THREADS, 0, stream>>>(d_packed, d_run_ends, dg[i], k, st, tab, cnt);
+            if (use_cb) {
+                const uint64_t units = (uint64_t)n_words * (4 / cb_ug);
+                const int grid3 = (int)std::min<uint64_t>((units + PRE_COUNT_THREADS - 1) / PRE_COUNT_THREADS,
+                                                          (uint64_t)ctx->num_sms * (cb_log2 <= 19 ? 2 : 1));
+                kmer_pre_count_cb_kernel<<<grid3, PRE_COUNT_THREADS, cb_words * 4, qs>>>(d_packed, d_run_ends, dg[i], k, st, tab, cnt, cbits,
+                                                                                       cb_mask, cb_mult, cb_ug);
+            } else {
+                kmer_pre_count_kernel<<<grid, TILE_THREADS, 0, qs>>>(d_packed, d_run_ends, dg[i], k, st, tab, cnt);
+            }
             LAUNCH_CHECK(ctx);
-            kmer_pre_emit_kernel<<<grid2, 256, 0, stream>>>(st, tab, cnt, min_abund, spec,
-                                                            (uint32_t *)(d_filters + dg[i].filter_word_off));
+            if (pre_zero_inline) {
+                if (zi_env[1] == 's' && (words & 1) == 0) {  // "1s": streaming stores
+                    bf_zero_stream_kernel<<<ctx->num_sms * 2, 256, 0, qs>>>((uint4 *)(d_filters + dg[i].filter_word_off), words / 2);
+                    LAUNCH_CHECK(ctx);
+                } else CU_TRY(ctx, cudaMemsetAsync(d_filters + dg[i].filter_word_off, 0, words * 8, qs));
+            }
+            kmer_pre_emit_kernel<<<grid2, 256, 0, qs>>>(st, tab, cnt, min_abund, spec, (uint32_t *)(d_filters + dg[i].filter_word_off));
             LAUNCH_CHECK(ctx);
+        }
+        if (n_streams > 1) {
+            for (int q = 0; q < n_streams; q++) {
+                CU_TRY(ctx, cudaEventRecord(ctx->side_done[q], ctx->side[q]));
+                CU_TRY(ctx, cudaStreamWaitEvent(stream, ctx->side_done[q], 0));
+            }
         }
         return MSBT_OK;
     }
