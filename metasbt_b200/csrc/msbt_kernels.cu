@@ -1582,8 +1582,10 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
 
     if (pre_path) {
         // prefiltered exact counting (see kmer_pre_mark_kernel); MSBT_MIN_TABLE=1 selects the plain count tables below
+        uint64_t bits_per_base = 32;  // MSBT_PRE_BITS_PER_BASE (tuning): a smaller mark table leaves more of L2 to the other genomes in flight
+        if (const char *e = getenv("MSBT_PRE_BITS_PER_BASE")) bits_per_base = std::min<uint64_t>(64, std::max<uint64_t>(1, strtoull(e, nullptr, 10)));
         uint64_t bit_count = 1ull << 16;
-        while (bit_count < 32 * max_bases && bit_count < (1ull << 33)) bit_count <<= 1;
+        while (bit_count < bits_per_base * max_bases && bit_count < (1ull << 33)) bit_count <<= 1;
         uint64_t max_slots = 1024;
         while (max_slots < 2 * max_bases) max_slots <<= 1;
         const size_t st_off = 0, bits_off = 256;
@@ -1638,7 +1640,7 @@ extern "C" int msbt_kmer_bloom_build(msbt_ctx *ctx, const uint64_t *d_packed, co
             uint32_t *cnt = (uint32_t *)(S + cnt_off);
             uint32_t *cbits = (uint32_t *)(S + cb_off);
             uint64_t gbits = 1ull << 16;
-            while (gbits < 32ull * dg[i].n_bases && gbits < bit_count) gbits <<= 1;
+            while (gbits < bits_per_base * dg[i].n_bases && gbits < bit_count) gbits <<= 1;
             uint64_t gslots = 1024;
             while (gslots < 2ull * dg[i].n_bases) gslots <<= 1;
             CU_TRY(ctx, cudaMemsetAsync(S, 0, bits_off + gbits / 8, qs));  // state + bit table

@@ -17,7 +17,7 @@ out = ctx.alloc_filters(n, 1 << lb)
 
 
 def timed(env):
-    for key in ("MSBT_PRE_COUNT_CB", "MSBT_PRE_CB_LOG2", "MSBT_PRE_CB_UNIT", "MSBT_PRE_CB_MULT", "MSBT_PRE_STREAMS", "MSBT_PRE_ZERO_INLINE"):
+    for key in ("MSBT_PRE_COUNT_CB", "MSBT_PRE_CB_LOG2", "MSBT_PRE_CB_UNIT", "MSBT_PRE_CB_MULT", "MSBT_PRE_STREAMS", "MSBT_PRE_ZERO_INLINE", "MSBT_PRE_BITS_PER_BASE"):
         os.environ.pop(key, None)
     os.environ.update(env)
     ctx.build_filters(batch, 31, 1 << lb, min_abund=2, out=out)
@@ -32,11 +32,11 @@ def timed(env):
 
 
 rows = []
-settings = [{"MSBT_PRE_STREAMS": "1"}, {"MSBT_PRE_STREAMS": "3"}]
-for streams in ("2", "3", "4"):
-    settings.append({"MSBT_PRE_STREAMS": streams, "MSBT_PRE_ZERO_INLINE": "1s"})
-settings.append({"MSBT_PRE_STREAMS": "3", "MSBT_PRE_ZERO_INLINE": "1"})
-settings.append({})
+settings = [{}]
+for bpb in ("32", "16", "8", "4"):
+    for log2 in ("19", "20"):
+        settings.append({"MSBT_PRE_BITS_PER_BASE": bpb, "MSBT_PRE_CB_LOG2": log2})
+settings.append({"MSBT_PRE_BITS_PER_BASE": "16", "MSBT_PRE_CB_LOG2": "20", "MSBT_PRE_STREAMS": "4"})
 for env in settings:
     us, pop = timed(env)
     rows.append({"env": env, "us_per_genome": us, "popcount_filter1": pop})
