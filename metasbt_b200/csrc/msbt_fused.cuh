@@ -451,6 +451,7 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
                 uint32_t n = 0;
                 for (uint32_t sub = 0; sub < tpb; sub++) {
                     const bool last = sub + 1 == tpb;
+                    FU_T(la0)
                     // A
                     uint4 *tv = (uint4 *)tile;
 #pragma unroll
@@ -462,7 +463,9 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
                         claim[4] = nxt;
                         claim[5] = nxt_gi;
                     }
+                    FU_T(la1)
                     fu_bar(2, FU_B_THREADS);
+                    FU_T(la2)
                     // B
                     if (tpb == 1) {
 #pragma unroll
@@ -487,21 +490,29 @@ kmer_bloom_fused_kernel(FusedParams P, KmerSpec spec) {
                             if ((p >> FU_TILE_LOG2) == tf) FU_B_OR1(p)
                         }
                     }
+                    FU_T(la3)
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     fu_bar(2, FU_B_THREADS);
+                    FU_T(la4)
                     // C
                     if (last) {
                         item = claim[4];
                         gi = claim[5];
                         if (item < n_items) FU_B_FAST_LOADS()
                     }
+                    FU_T(la5)
                     if (tid == 0) {
                         asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;" ::"l"(dst + (uint64_t)sub * (FU_TILE_BYTES / 8)), "r"(saddr), "r"(FU_TILE_BYTES), "l"(evict_first) : "memory");
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                         asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     }
+                    FU_T(la6)
                     if (last && tid == 64) atomicAdd(P.consumed + cur_gi, 1u);
                     fu_bar(2, FU_B_THREADS);
+                    FU_T(la7)
+                    // lean loop phases: tid 0 (issues the store and waits for the read-out) and tid 96 (a plain worker lane)
+                    if (tid == 0) { FU_ACC(8, la5, la6) FU_ACC(10, la0, la1) FU_ACC(11, la2, la3) FU_ACC(14, la4, la5) FU_ACC(15, 0, 1) FU_ACC(16, la0, la7) }
+                    if (tid == 96) { FU_ACC(9, la1, la2) FU_ACC(12, la3, la4) FU_ACC(13, la6, la7) FU_ACC(17, la0, la7) }
                 }
             }
 #undef FU_B_OR2
