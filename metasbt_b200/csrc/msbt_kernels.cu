@@ -3197,8 +3197,10 @@ query_sliced_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint
 constexpr int QSR_MAX_WARPS = 8;  // pieces of a row one CTA covers (10,000 leaves: 5); more leaves take grid.z
 // (register-capped instantiations for 7 / 8 resident CTAs per SM were measured: 56 registers 82.4 ms, 48 registers with
 // spills 92.0 ms, against 79.4 ms for the plain 63-register build with 6 CTAs per SM)
+// (the chain with pending weight-16 / weight-32 carries needs 72 registers uncapped: probe 145.7 -> 143.6 ms per 512 MAGs;
+// capped at 64 with 8 bytes of spill it keeps 6 CTAs per SM: 139.6 ms)
 template <int G>   // groups of 8 row loads in flight per lane (1 or 2)
-__global__ void __launch_bounds__(QSR_MAX_WARPS * 32)
+__global__ void __launch_bounds__(QSR_MAX_WARPS * 32, 4)   // 64 registers: 6 CTAs of 5 warps per SM at 10,000 leaves
 query_sliced_rows_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves, uint32_t lw, uint32_t ls, uint64_t row_begin, uint64_t row_end,
                          const uint32_t *__restrict__ positions, const ulonglong2 *__restrict__ q_rng, uint32_t *__restrict__ hits,
                          uint32_t n_groups, uint32_t sub) {
@@ -3233,12 +3235,16 @@ query_sliced_rows_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves,
     // the low counter planes: 8 rows fold into planes 0-2 with 7 full adders and leave one carry of weight 8; two such
     // carries meet in one more full adder on plane 3, and only its carry (weight 16) ripples through planes 4-11 -- 2.9 ALU
     // operations per row and lane word instead of 4.6 for the 7 -> 3 compression + 12-plane ripple of the kernel above.
+    // The weight-16 carries of a round's two halves meet on plane 4, and the weight-32 carries of two consecutive rounds on
+    // plane 5; only that carry (weight 64, once per 64 rows) ripples through planes 6-11: 2.2 operations per row and word.
     uint32_t nextpos = (sub_b + lane < sub_e) ? positions[sub_b + lane] : 0xFFFFFFFFu;
+    uint32_t pend32[W];
+    bool odd_round = false;
     for (unsigned long long base = sub_b; base < sub_e; base += 32) {
         const uint32_t mypos = nextpos;
         const unsigned long long idx = base + 32 + lane;
         nextpos = (idx < sub_e) ? positions[idx] : 0xFFFFFFFFu;
-        uint32_t pend[W];
+        uint32_t pend[W], pend16[W];
 #pragma unroll
         for (int g8 = 0; g8 < 4; g8 += G) {
             QsVec<W> x[G][8];
@@ -3270,10 +3276,31 @@ query_sliced_rows_kernel(const uint32_t *__restrict__ sliced, uint32_t n_leaves,
                     } else {
                         uint32_t k;
                         full_add(P[w][3], pend[w], c8, P[w][3], k);   // k: carry of weight 16
+                        if (((g8 + g) & 2) == 0) {
+                            pend16[w] = k;
+                        } else {
+                            uint32_t k32;
+                            full_add(P[w][4], pend16[w], k, P[w][4], k32);   // carry of weight 32, one per round
+                            if (!odd_round) {
+                                pend32[w] = k32;
+                            } else {
+                                uint32_t k64;
+                                full_add(P[w][5], pend32[w], k32, P[w][5], k64);
 #pragma unroll
-                        for (int i = 4; i < 12; i++) { const uint32_t t = P[w][i] & k; P[w][i] ^= k; k = t; }
+                                for (int i = 6; i < 12; i++) { const uint32_t t = P[w][i] & k64; P[w][i] ^= k64; k64 = t; }
+                            }
+                        }
                     }
                 }
+        }
+        odd_round = !odd_round;
+    }
+    if (odd_round) {  // an unpaired weight-32 carry is still pending
+#pragma unroll
+        for (int w = 0; w < W; w++) {
+            uint32_t k = pend32[w];
+#pragma unroll
+            for (int i = 5; i < 12; i++) { const uint32_t t = P[w][i] & k; P[w][i] ^= k; k = t; }
         }
     }
     if (live) {
