@@ -43,6 +43,30 @@ def read_files(paths: Sequence[str], threads: Optional[int] = None) -> List[byte
         return list(ex.map(read_fasta_bytes, paths))
 
 
+# All pairs through K3 (AND + popcount over whole filters: n^2 / 2 filter passes) or through K4 (transpose once, then every
+# filter's set bits probe the bit-sliced matrix: work ~ set bits x row width).  Rates measured on B200:
+# the carry-save all-pairs kernel does 591 k pairs/s at 2^28 bits; the row-coherent probe 24 G positions/s on 128-byte rows
+# and 8.6 TB/s of row bytes on wide rows; the transposition moves 2 x n x m / 8 bytes at 3.2 TB/s per pass.
+PROBE_MIN_FILTERS = 192
+BIT_ROUTE_PAIRS_PER_S_AT_2P28 = 591e3
+PROBE_POSITIONS_PER_S = 24e9
+PROBE_ROW_BYTES_PER_S = 8.6e12
+TRANSPOSE_BYTES_PER_S = 3.2e12
+
+
+def allpairs_route(n: int, num_bits: int, total_popcount: int, row_words: int, slice_bytes: int) -> str:
+    """'probe' when the K4 formulation of an n-filter all-pairs matrix is expected to be clearly faster than K3's."""
+    if n < 2 or num_bits > (1 << 32):
+        return "bit"
+    t_bit = (n * (n + 1) / 2.0) * (num_bits / float(1 << 28)) / BIT_ROUTE_PAIRS_PER_S_AT_2P28
+    row_bytes = row_words * 4
+    passes = max(1, -(-(num_bits * row_bytes) // max(int(slice_bytes), row_bytes)))
+    t_probe = total_popcount / min(PROBE_POSITIONS_PER_S, PROBE_ROW_BYTES_PER_S / row_bytes)
+    t_probe += 2.0 * n * (num_bits / 8.0) / TRANSPOSE_BYTES_PER_S          # the transposition, once over all passes
+    t_probe += passes * n * (num_bits / 8.0) / 2.7e12                        # one extraction of every filter per pass
+    return "probe" if t_probe < 0.7 * t_bit else "bit"
+
+
 def _retry_after_oom(method):
     """An operator that runs out of device memory drops the backend's caches (row-major filters, bit-sliced matrices,
     torch's cached blocks) and runs once more -- budgets come from cudaMemGetInfo at construction, other users of the
@@ -413,7 +437,16 @@ class CudaBackend:
         n = len(paths)
         step = self._chunk(2)
         if n <= step:
-            return self.ctx.bf_allpairs([self.filter(p) for p in paths], self.num_bits)
+            rows = [self.filter(p) for p in paths]
+            route = os.environ.get("MSBT_ALLPAIRS_ROUTE", "auto")  # bit | probe | auto
+            if route == "auto" and n >= PROBE_MIN_FILTERS and self.num_bits <= (1 << 32):
+                free, _total = torch.cuda.mem_get_info(self.ctx.device)
+                total_pop = int(self.ctx.bf_popcount(rows, self.num_bits).sum().item())
+                route = allpairs_route(n, self.num_bits, total_pop, self.ctx.sliced_row_words(n), free // 2)
+            if route == "probe" and self.num_bits <= (1 << 32):
+                free, _total = torch.cuda.mem_get_info(self.ctx.device)
+                return self.ctx.bf_allpairs_probe(rows, self.num_bits, slice_bytes=max(1 << 28, free // 2))
+            return self.ctx.bf_allpairs(rows, self.num_bits)
         # more filters than may be resident at once: tile the matrix; only two half-chunks are alive at a time
         half = max(1, step // 2)
         blocks = [(lo, min(lo + half, n)) for lo in range(0, n, half)]

@@ -768,3 +768,53 @@ def test_query_sliced_rows_of_several_pieces(ctx, oracle, n_leaves, rows_kernel,
     part = ctx.query_batch_sliced(ctx.bitslice(leaves, 0, half), n_leaves, 0, half, positions) + \
         ctx.query_batch_sliced(ctx.bitslice(leaves, half, num_bits), n_leaves, half, num_bits, positions)
     assert np.array_equal(part.cpu().numpy().astype(np.uint64), want)
+
+
+@pytest.mark.gpu
+def test_allpairs_through_the_probe_equals_the_and_popcount_kernel(ctx, oracle, tmp_path, monkeypatch):
+    """All pairs the K4 way (transpose once, every filter's set bits probe the bit-sliced matrix; work ~ set bits): the
+    same integers as the K3 kernel -- for ragged sizes, several row passes, several query batches, an empty and a full
+    filter -- and through the backend when the route is forced."""
+    import torch
+    from metasbt_b200 import backend as B, bffile, ops
+    rng = np.random.default_rng(5)
+    for num_bits, n, density in ((200_003, 70, 0.02), (1 << 20, 33, 0.05), (64 * 5, 9, 0.3)):
+        words = ops.filter_words(num_bits)
+        bits = rng.random((n, words * 64)) < density
+        bits[:, num_bits:] = False
+        bits[0, :] = False                      # an empty filter
+        bits[1, :num_bits] = True               # a full one
+        host = np.packbits(bits, axis=1, bitorder="little").view(np.uint64).reshape(n, words)
+        dev = ctx.alloc_filters(n, num_bits)
+        dev.zero_()
+        dev[:, :words] = torch.from_numpy(host.view(np.int64)).to(dev.device)
+        rows = [dev[i] for i in range(n)]
+        want = ctx.bf_allpairs(rows, num_bits)
+        row_bytes = ctx.sliced_row_words(n) * 4
+        for slice_bytes, batch in ((48 << 30, 256), (row_bytes * (num_bits // 3 + 7), 16), (row_bytes * 64, 5)):
+            got = ctx.bf_allpairs_probe(rows, num_bits, slice_bytes=slice_bytes, batch=batch)
+            assert torch.equal(got, want), (num_bits, n, slice_bytes, batch)
+        assert int(want[1, 1]) == num_bits and int(want[0].sum()) == 0
+        assert np.array_equal(want.cpu().numpy()[2:6, 2:6],
+                              np.array([[oracle.bf_and_popcount(host[i], host[j]) for j in range(2, 6)] for i in range(2, 6)]))
+    # through the backend: forced routes agree, and the automatic rule stays with K3 for a handful of filters
+    k, num_bits = 21, 1 << 16
+    be = B.CudaBackend(k, num_bits)
+    rnd = random.Random(9)
+    fas, bfs = [], []
+    for i in range(12):
+        fa = tmp_path / ("p%02d.fa" % i)
+        fa.write_bytes(util.messy_fasta(rnd, 2, 1500, "ACGTN"))
+        fas.append(str(fa))
+        bfs.append(str(tmp_path / ("p%02d.bf" % i)))
+    be.sketch_many(fas, bfs, 1)
+    monkeypatch.setenv("MSBT_ALLPAIRS_ROUTE", "bit")
+    by_bit = be.dist_all_pairs(bfs)
+    monkeypatch.setenv("MSBT_ALLPAIRS_ROUTE", "probe")
+    before = be.ctx.launch_count
+    by_probe = be.dist_all_pairs(bfs)
+    assert be.ctx.launch_count - before >= 3     # transpose + extraction + probe
+    monkeypatch.delenv("MSBT_ALLPAIRS_ROUTE")
+    assert np.array_equal(by_bit, by_probe) and np.array_equal(be.dist_all_pairs(bfs), by_bit)
+    flt = [bffile.read_bf(p)[1] for p in bfs]
+    assert np.array_equal(by_probe, np.array([[oracle.bf_and_popcount(a, b) for b in flt] for a in flt], dtype=np.int64))

@@ -258,3 +258,21 @@ def test_bf_header_constants_follow_the_spec(tmp_path, monkeypatch):
             bffile.read_bf(p)  # another magic: not one of ours
     finally:
         bffile.configure(magic=old[0], version=old[1])
+
+
+def test_allpairs_route_model():
+    """backend.allpairs_route: K3 (AND + popcount per pair) for a handful of filters or dense ones, K4 (transpose + probe with
+    the set bits) for many sparse ones."""
+    from metasbt_b200 import backend as B
+    m = 1 << 28
+
+    def lw(n):
+        return ((n + 31) // 32 + 7) // 8 * 8
+    sparse = 5_000_000                                       # a 5 Mbp genome: 1.9 % of 2^28 bits
+    assert B.allpairs_route(64, m, 64 * sparse, lw(64), 48 << 30) == "bit"
+    assert B.allpairs_route(1024, m, 1024 * sparse, lw(1024), 48 << 30) == "probe"
+    assert B.allpairs_route(10000, m, 10000 * sparse, lw(10000), 48 << 30) == "probe"
+    assert B.allpairs_route(2000, m, 2000 * 60_000_000, lw(2000), 48 << 30) == "bit"     # 22 % dense
+    assert B.allpairs_route(1, m, sparse, 8, 48 << 30) == "bit"
+    assert B.allpairs_route(5000, 1 << 33, 5000 * sparse, lw(5000), 48 << 30) == "bit"   # positions are 32-bit
+    assert B.PROBE_MIN_FILTERS >= 64

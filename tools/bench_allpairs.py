@@ -28,6 +28,8 @@ def main():
     ap.add_argument("--genome-bp", type=int, default=5_000_000)
     ap.add_argument("--filter-bits", type=int, default=1 << 28)
     ap.add_argument("--chunk", type=int, default=128, help="peer filters per send/recv + rectangular launch")
+    ap.add_argument("--route", choices=("bit", "probe"), default="bit",
+                    help="one GPU only: 'probe' = ops.bf_allpairs_probe (transpose once, every filter's set bits probe the bit-sliced matrix)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -58,14 +60,23 @@ def main():
         torch.cuda.synchronize()
 
     # warm-up on a small block (kernel attributes, NCCL channels)
-    shard.all_pairs_ring(ctx, mat[: min(32, hi - lo)], m, chunk=16)
+    if a.route == "probe":
+        if world != 1:
+            raise SystemExit("--route probe runs on one GPU")
+        ctx.bf_allpairs_probe([mat[i] for i in range(min(32, hi - lo))], m)
+    else:
+        shard.all_pairs_ring(ctx, mat[: min(32, hi - lo)], m, chunk=16)
     barrier()
     launches0 = ctx.launch_count
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         barrier()
         e0.record()
-        out = shard.all_pairs_ring(ctx, mat, m, chunk=a.chunk)
+        if a.route == "probe":
+            free, _ = torch.cuda.mem_get_info(dev)
+            out = ctx.bf_allpairs_probe([mat[i] for i in range(hi - lo)], m, slice_bytes=max(1 << 28, free // 2))
+        else:
+            out = shard.all_pairs_ring(ctx, mat, m, chunk=a.chunk)
         e1.record()
         barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -74,6 +85,9 @@ def main():
     diag = torch.diagonal(out[:, lo:hi])
     pc = ctx.bf_popcount([mat[i] for i in range(min(64, hi - lo))], m)
     ok = bool(torch.equal(diag[: pc.numel()], pc))
+    if a.route == "probe":  # cross-check a block against the AND + popcount kernel
+        nb = min(48, hi - lo)
+        ok = ok and bool(torch.equal(out[:nb, :nb], ctx.bf_allpairs([mat[i] for i in range(nb)], m)))
     csum = torch.tensor([int(torch.where(out >= 0, out, torch.zeros_like(out)).sum().item() % (1 << 61))], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -94,7 +108,7 @@ def main():
         print(json.dumps({
             "workload": "SURVEY 8d stress shape: all pairs among %d synthetic %.1f Mbp genomes, k=31, 2^%d-bit filters (%.0f GB of filters), %d GPU(s)"
                         % (n, G / 1e6, m.bit_length() - 1, n * (m // 8) / 1e9, world),
-            "n_gpus": world, "pairs": distinct, "seconds": sec, "pairs_per_s": distinct / sec,
+            "n_gpus": world, "route": a.route, "pairs": distinct, "seconds": sec, "pairs_per_s": distinct / sec,
             "pairs_per_s_per_gpu": distinct / sec / world,
             "read_every_filter_once_frac_of_hbm_peak": n * (m // 8) / sec / 1e9 / peak / world,
             "gpu_launches": ctx.launch_count - launches0, "chunk": a.chunk, "clocks": clocks.summary(),
