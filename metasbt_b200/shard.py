@@ -13,7 +13,7 @@ gloo in the CPU tests), so the partition / merge arithmetic is testable without 
 
 from __future__ import annotations
 
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.distributed as dist
@@ -279,6 +279,62 @@ def all_pairs_ring(ctx, mat: torch.Tensor, num_bits: int, group=None, chunk: int
                 block = ctx.bf_rect(my_rows, [buf[i] for i in range(re_ - rb)], num_bits)
                 out[:row_hi, offs[src] + rb: offs[src] + re_] = block
     return out
+
+
+def all_pairs_probe(ctx, mat: torch.Tensor, num_bits: int, group=None, chunk: int = 256, batch: int = 256,
+                    slice_bytes: Optional[int] = None) -> torch.Tensor:
+    """All-pairs intersections of MANY SPARSE filters spread over the ranks (each holds a block of rows `mat`
+    [n_local, stride] int64), the K4 way (ops.bf_allpairs_probe): |A and B| over the whole filter is the sum over bit ranges
+    of |A and B| within the range, so rank r receives range r (bit_ranges) of EVERY filter -- `chunk` filters per peer and
+    round over send/recv --, transposes those sub-filters into its shard of the bit-sliced matrix, lets every sub-filter's
+    set bits probe it, and the partial [n_total, n_total] matrices are summed with one all_reduce.  Returns the full
+    symmetric int64 matrix (diagonal = popcounts) on every rank.  Work per rank ~ (set bits of all filters) / world rows of
+    n_total bits, against n_total^2 / (2 world) whole-filter passes for all_pairs_ring."""
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    n_local = int(mat.shape[0])
+    words = (num_bits + 63) // 64
+    kw = dict() if slice_bytes is None else dict(slice_bytes=slice_bytes)
+    if world == 1:
+        return ctx.bf_allpairs_probe([mat[i] for i in range(n_local)], num_bits, batch=batch, **kw)
+    t = torch.tensor([n_local], dtype=torch.int64, device=mat.device)
+    allc = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(allc, t, group=group)
+    counts = [int(c.item()) for c in allc]
+    offs = [0]
+    for c in counts:
+        offs.append(offs[-1] + c)
+    ranges = bit_ranges(num_bits, world)                      # multiples of 128 bits: word-aligned, 16-byte aligned
+    wr = [(b // 64, min(words, (e + 63) // 64)) for b, e in ranges]
+    my_b, my_e = ranges[rank]
+    my_w = wr[rank][1] - wr[rank][0]
+    stride_r = max(2, (my_w + 1) // 2 * 2)                    # rows of the sub-filter matrix stay 16-byte aligned
+    sub = torch.zeros((offs[-1], stride_r), dtype=mat.dtype, device=mat.device)
+    glob = (lambda r: r) if group is None else (lambda r: dist.get_global_rank(group, r))
+    for c0 in range(0, max(counts), chunk):
+        reqs, landed = [], []
+        for p in range(world):
+            sb, se = min(c0, n_local), min(c0 + chunk, n_local)           # my rows of this round
+            rb, re_ = min(c0, counts[p]), min(c0 + chunk, counts[p])      # peer p's rows of this round
+            if p == rank:
+                if se > sb and my_w:
+                    sub[offs[rank] + sb: offs[rank] + se, :my_w] = mat[sb:se, wr[rank][0]: wr[rank][1]]
+                continue
+            pw = wr[p][1] - wr[p][0]
+            if se > sb and pw:
+                reqs.append(dist.P2POp(dist.isend, mat[sb:se, wr[p][0]: wr[p][1]].contiguous(), glob(p), group))
+            if re_ > rb and my_w:
+                buf = torch.empty((re_ - rb, my_w), dtype=mat.dtype, device=mat.device)
+                reqs.append(dist.P2POp(dist.irecv, buf, glob(p), group))
+                landed.append((offs[p] + rb, offs[p] + re_, buf))
+        for q in (dist.batch_isend_irecv(reqs) if reqs else []):
+            q.wait()
+        for lo, hi, buf in landed:
+            sub[lo:hi, :my_w] = buf
+    partial = ctx.bf_allpairs_probe([sub[i] for i in range(offs[-1])], my_e - my_b, batch=batch, **kw) if my_e > my_b else \
+        torch.zeros((offs[-1], offs[-1]), dtype=torch.int64, device=mat.device)
+    dist.all_reduce(partial, op=dist.ReduceOp.SUM, group=group)
+    return partial
 
 
 def all_pairs_assemble(local: torch.Tensor, group=None) -> torch.Tensor:

@@ -92,6 +92,9 @@ def main():
     full = shard.all_pairs_assemble(local)
     want_pairs = np.array([[O.bf_and_popcount(a, b) for b in want] for a in want], dtype=np.int64)
     assert np.array_equal(full.cpu().numpy(), want_pairs), "K3 all_pairs_ring rank %d" % rank
+    # the same matrix the K4 way (bit ranges of every filter exchanged, transposed and probed with their own set bits)
+    probed = shard.all_pairs_probe(ctx, mine, m, chunk=2, batch=3)
+    assert np.array_equal(probed.cpu().numpy(), want_pairs), "K3 all_pairs_probe rank %d" % rank
     dist.barrier()
     if rank == 0:
         print("multi-GPU parity ok: world=%d, K1 blocks %s, K2 OR-merge, K3 and K4 bit-range shards all match the oracle" % (world, counts))

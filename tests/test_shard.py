@@ -104,6 +104,9 @@ def _worker(rank, world, port, tmp):
             def bf_rect(self, a_rows, b_rows, num_bits):
                 return torch.tensor([[O.bf_and_popcount(a.numpy().view(np.uint64), b.numpy().view(np.uint64)) for b in b_rows] for a in a_rows],
                                     dtype=torch.int64).reshape(len(a_rows), len(b_rows))
+            def bf_allpairs_probe(self, rows, num_bits, batch=256, slice_bytes=None):   # the K4 route's single launch site
+                w = (num_bits + 63) // 64
+                return self.bf_allpairs([r[:w] for r in rows], num_bits)
         for total in (7, 2 * world + 1, world):  # ragged blocks, one filter per rank
             lo, hi = total * rank // world, total * (rank + 1) // world
             pool = [O.makebf(util.codes_to_fasta(util.mutate(util.synthetic_codes(9, 5000), 0.03 * g, 70 + g), "p%d" % g), k, bits) for g in range(total)]
@@ -112,6 +115,17 @@ def _worker(rank, world, port, tmp):
             full = shard.all_pairs_assemble(local)
             want = np.array([[O.bf_and_popcount(a, b) for b in pool] for a in pool], dtype=np.int64)
             assert np.array_equal(full.numpy(), want), (total, rank)
+            # the same matrix the K4 way: bit ranges of every filter exchanged, partial matrices summed
+            for odd_bits in (bits, bits - 37):
+                pool2 = [p.copy() for p in pool]
+                if odd_bits != bits:
+                    for p in pool2:  # a filter of odd_bits bits: nothing set beyond it
+                        p[odd_bits // 64] &= np.uint64((1 << (odd_bits % 64)) - 1)
+                        p[odd_bits // 64 + 1:] = 0
+                mat2 = torch.from_numpy(np.stack(pool2[lo:hi]).view(np.int64)) if hi > lo else torch.zeros((0, bits // 64), dtype=torch.int64)
+                probed = shard.all_pairs_probe(OracleOps(), mat2, odd_bits, chunk=2)
+                want2 = np.array([[O.bf_and_popcount(a, b) for b in pool2] for a in pool2], dtype=np.int64)
+                assert np.array_equal(probed.numpy(), want2), (total, rank, odd_bits)
             computed = torch.tensor([int((local >= 0).sum())], dtype=torch.int64)
             dist.all_reduce(computed)
             assert int(computed) == sum((total * (r + 1) // world - total * r // world) ** 2 for r in range(world)) + \

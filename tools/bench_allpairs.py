@@ -29,7 +29,7 @@ def main():
     ap.add_argument("--filter-bits", type=int, default=1 << 28)
     ap.add_argument("--chunk", type=int, default=128, help="peer filters per send/recv + rectangular launch")
     ap.add_argument("--route", choices=("bit", "probe"), default="bit",
-                    help="one GPU only: 'probe' = ops.bf_allpairs_probe (transpose once, every filter's set bits probe the bit-sliced matrix)")
+                    help="'probe' = shard.all_pairs_probe / ops.bf_allpairs_probe (transpose once, every filter's set bits probe the bit-sliced matrix)")
     a = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -61,9 +61,7 @@ def main():
 
     # warm-up on a small block (kernel attributes, NCCL channels)
     if a.route == "probe":
-        if world != 1:
-            raise SystemExit("--route probe runs on one GPU")
-        ctx.bf_allpairs_probe([mat[i] for i in range(min(32, hi - lo))], m)
+        shard.all_pairs_probe(ctx, mat[: min(32, hi - lo)], m, chunk=16)
     else:
         shard.all_pairs_ring(ctx, mat[: min(32, hi - lo)], m, chunk=16)
     barrier()
@@ -74,7 +72,9 @@ def main():
         e0.record()
         if a.route == "probe":
             free, _ = torch.cuda.mem_get_info(dev)
-            out = ctx.bf_allpairs_probe([mat[i] for i in range(hi - lo)], m, slice_bytes=max(1 << 28, free // 2))
+            # one GPU: the matrix in row passes that fit; several: bit-range shards, the sub-filters arrive over send/recv
+            full = shard.all_pairs_probe(ctx, mat, m, chunk=a.chunk, slice_bytes=max(1 << 28, free // (2 if world == 1 else 4)))
+            out = full[lo:hi]
         else:
             out = shard.all_pairs_ring(ctx, mat, m, chunk=a.chunk)
         e1.record()
@@ -88,11 +88,18 @@ def main():
     if a.route == "probe":  # cross-check a block against the AND + popcount kernel
         nb = min(48, hi - lo)
         ok = ok and bool(torch.equal(out[:nb, :nb], ctx.bf_allpairs([mat[i] for i in range(nb)], m)))
-    csum = torch.tensor([int(torch.where(out >= 0, out, torch.zeros_like(out)).sum().item() % (1 << 61))], dtype=torch.int64, device=dev)
+    # checksum = sum over the entries the ring fills (local blocks both ways, every cross pair once); the probe route fills
+    # every cross pair on both sides, so its cross entries count half
+    filled = torch.where(out >= 0, out, torch.zeros_like(out))
+    local_sum = int(filled[:, lo:hi].sum().item())
+    cross = torch.tensor([int(filled.sum().item()) - local_sum], dtype=torch.int64, device=dev)
+    csum = torch.tensor([local_sum], dtype=torch.int64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(done)
         dist.all_reduce(csum)
+        dist.all_reduce(cross)
+    csum = csum + (cross // 2 if a.route == "probe" else cross)
     if rank == 0:
         n = a.genomes
         sec = float(ms.item()) / 1e3
@@ -113,7 +120,8 @@ def main():
             "read_every_filter_once_frac_of_hbm_peak": n * (m // 8) / sec / 1e9 / peak / world,
             "gpu_launches": ctx.launch_count - launches0, "chunk": a.chunk, "clocks": clocks.summary(),
             "check": {"diagonal_equals_popcounts": ok, "entries_filled": entries, "sum_mod_2_61": int(csum.item() % (1 << 61)),
-                      "all_cross_pairs_once": entries == sum(b * b for b in blocks) + (n * n - sum(b * b for b in blocks)) // 2},
+                      "all_cross_pairs_once": entries == (n * n if a.route == "probe" else
+                                                          sum(b * b for b in blocks) + (n * n - sum(b * b for b in blocks)) // 2)},
         }))
     if world > 1:
         dist.destroy_process_group()
