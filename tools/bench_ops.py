@@ -114,6 +114,19 @@ def run(ctx, n_leaves=1024, filter_bits=1 << 28, n_mags=64, genome_bp=5_000_000,
     t = _time(lambda: ctx.bf_allpairs(rows[:10], m))
     out["K3_allpairs_10"] = entry(t, 10 * fbytes, pairs_per_s=45 / t, note="bytes = each filter read once")
 
+    # ... and over ALL leaves at once: K3 (AND + popcount per pair) against the K4 route (transpose once, every filter's set
+    # bits probe the bit-sliced matrix; ops.bf_allpairs_probe) -- same integers
+    if L >= 256:
+        box = {}
+        t_bit = _time(lambda: box.__setitem__("bit", ctx.bf_allpairs(rows, m)), reps=1)
+        t_probe = _time(lambda: box.__setitem__("probe", ctx.bf_allpairs_probe(rows, m)), reps=1)
+        pairs = L * (L - 1) / 2
+        out["K3_allpairs_%d_bit_route" % L] = {"ms": t_bit * 1e3, "pairs_per_s": pairs / t_bit}
+        out["K3_allpairs_%d_probe_route" % L] = {"ms": t_probe * 1e3, "pairs_per_s": pairs / t_probe, "speedup": t_bit / t_probe,
+                                                 "equal_to_bit_route": bool(torch.equal(box["bit"], box["probe"])),
+                                                 "note": "work ~ set bits x row width instead of n^2 / 2 x filter words"}
+        del box
+
     # K4: MAGs = 5 % mutated prefixes of leaves
     mw = []
     for q in range(n_mags):
