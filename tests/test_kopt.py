@@ -219,3 +219,52 @@ def test_word_counting_on_the_device_and_the_chosen_k(tmp_path, oracle, ctx):
     k_gpu = kopt.optimal_kmer_size(paths, 14, cuda_backend.CudaBackend(14, m), num_bits=m, details=d_gpu)
     k_cpu = kopt.optimal_kmer_size(paths, 14, cpu_backend.OracleBackend(14, m), num_bits=m, details=d_cpu)
     assert k_gpu == k_cpu and d_gpu["acf"] == d_cpu["acf"] and d_gpu["ofc"] == d_cpu["ofc"] and d_gpu["cre_limits"] == d_cpu["cre_limits"]
+
+
+# ------------------------------------------------------------------ properties (hypothesis, CPU)
+
+def _fasta_like():
+    from hypothesis import strategies as st
+    line = st.text(alphabet="ACGTacgtNn \t", min_size=0, max_size=40)
+    header = st.text(alphabet="abc >;_1", min_size=0, max_size=8).map(lambda t: ">" + t.replace("\n", ""))
+    return st.lists(st.one_of(line, header), min_size=0, max_size=12).map(lambda ls: "\n".join(ls).encode())
+
+
+def test_fasta_codes_property(oracle):
+    from hypothesis import given, settings
+
+    @settings(max_examples=150, deadline=None)
+    @given(_fasta_like())
+    def check(text):
+        got = [int(c) for c in kopt.fasta_codes(text)]
+        want = []
+        for r in oracle.py_fasta_records(text):
+            want.append(4)
+            want.extend("ACGT".index(c) if c in "ACGT" else 4 for c in r.upper())
+        while got and got[0] == 4:
+            got.pop(0)
+        while want and want[0] == 4:
+            want.pop(0)
+        # runs of breaks are equivalent (a k-mer never spans one): compare with runs collapsed
+        def squeeze(v):
+            out = []
+            for x in v:
+                if not (x == 4 and out and out[-1] == 4):
+                    out.append(x)
+            while out and out[-1] == 4:
+                out.pop()
+            return out
+        assert squeeze(got) == squeeze(want)
+    check()
+
+
+def test_relative_entropy_property(oracle):
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(st.lists(st.text(alphabet="ACGTN", min_size=0, max_size=60), min_size=1, max_size=4), st.integers(3, 9))
+    def check(records, l):
+        text = "".join(">r%d\n%s\n" % (i, r) for i, r in enumerate(records)).encode()
+        got = kopt.relative_entropies(kopt.fasta_codes(text), l, "cpu")[l]
+        assert got == pytest.approx(oracle.py_relative_entropy(text, l), abs=1e-9)
+    check()
